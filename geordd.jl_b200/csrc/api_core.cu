@@ -1,0 +1,606 @@
+// C ABI, part 1: context, profiling, covariance assembly, single-region GP fit.
+#include "api_internal.h"
+#include <algorithm>
+
+namespace geordd {
+
+const char* const kProfNames[PC_COUNT] = {"cov", "potrf", "solve_fwd", "solve_bwd", "trmm",
+                                          "gemm", "rng", "finish", "lu", "misc"};
+
+// ---- profiling -------------------------------------------------------------------------------------
+ProfScope::ProfScope(geordd_ctx* ctx, int cls) : c(ctx) {
+    if (!c->prof_on) return;
+    cudaEvent_t a, b;
+    if (c->ev_pool.size() >= 2) {
+        a = c->ev_pool.back(); c->ev_pool.pop_back();
+        b = c->ev_pool.back(); c->ev_pool.pop_back();
+    } else {
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+    }
+    cudaEventRecord(a, c->stream);
+    c->recs.push_back({cls, a, b});
+    idx = (int)c->recs.size() - 1;
+}
+ProfScope::~ProfScope() {
+    if (idx >= 0) cudaEventRecord(c->recs[idx].b, c->stream);
+}
+
+static void prof_collect(geordd_ctx* c) {
+    cudaStreamSynchronize(c->stream);
+    for (auto& r : c->recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            c->prof_ms[r.cls] += ms;
+            c->prof_n[r.cls] += 1;
+        }
+        c->ev_pool.push_back(r.a);
+        c->ev_pool.push_back(r.b);
+    }
+    c->recs.clear();
+}
+
+// ---- small helpers ---------------------------------------------------------------------------------
+void ctx_use(geordd_ctx* c) { GD_CUDA(cudaSetDevice(c->device)); }
+
+int ctx_fail(geordd_ctx* c, const ApiError& e) {
+    if (c) c->err = e.what();
+    cudaGetLastError();
+    return e.code;
+}
+
+void check_abort(geordd_ctx* c) {
+    GD_CUDA(cudaMemcpyAsync(c->h_info, c->sched.abort_word, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    GD_CUDA(cudaStreamSynchronize(c->stream));
+    GD_CUDA(cudaGetLastError());
+    if (c->h_info[0] < 0) {
+        GD_CUDA(cudaMemsetAsync(c->sched.abort_word, 0, sizeof(int), c->stream));
+        throw ApiError(GEORDD_ERR_WATCHDOG, "dataflow kernel watchdog fired (scheduling stall)");
+    }
+}
+
+double read_scalar(geordd_ctx* c, const double* d) {
+    GD_CUDA(cudaMemcpyAsync(c->h_scal, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GD_CUDA(cudaStreamSynchronize(c->stream));
+    return c->h_scal[0];
+}
+
+void upload2d(geordd_ctx* c, double* dst, long ldd, const double* src, long lds, int rows, int cols) {
+    if (rows <= 0 || cols <= 0) return;
+    GD_CUDA(cudaMemcpy2DAsync(dst, ldd * sizeof(double), src, lds * sizeof(double), (size_t)rows * sizeof(double), cols,
+                              cudaMemcpyHostToDevice, c->stream));
+}
+void download2d(geordd_ctx* c, double* dst, long ldd, const double* src, long lds, int rows, int cols) {
+    if (rows <= 0 || cols <= 0) return;
+    GD_CUDA(cudaMemcpy2DAsync(dst, ldd * sizeof(double), src, lds * sizeof(double), (size_t)rows * sizeof(double), cols,
+                              cudaMemcpyDeviceToHost, c->stream));
+}
+
+double* dalloc(size_t count, cudaStream_t st, bool zero) {
+    double* p = nullptr;
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(double));
+    if (e != cudaSuccess) throw ApiError(GEORDD_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    if (zero) GD_CUDA(cudaMemsetAsync(p, 0, count * sizeof(double), st));
+    return p;
+}
+
+void ensure_ws(geordd_ctx* c, size_t count) { c->ws.ensure(count, c->stream, false); }
+
+KernelSpecDev to_dev(const geordd_kernel& k) {
+    KernelSpecDev d;
+    d.kind = k.kind; d.ell = k.ell; d.sigma2 = k.sigma2; d.const_sigma2 = k.const_sigma2;
+    return d;
+}
+
+static void check_kernel(const geordd_kernel* k) {
+    if (!k) throw ApiError(GEORDD_ERR_ARG, "kernel is NULL");
+    if (k->kind < 0 || k->kind > 3) throw ApiError(GEORDD_ERR_ARG, "kernel kind must be 0..3 (SE, Mat12, Mat32, Mat52)");
+    if (!(k->ell > 0.0) || !(k->sigma2 >= 0.0) || !(k->const_sigma2 >= 0.0))
+        throw ApiError(GEORDD_ERR_ARG, "kernel parameters must be positive and finite");
+}
+
+int pick_splitk(geordd_ctx* c, int M, int N, int K) {
+    long tiles = (long)(M / TILE) * (N / 64);
+    long kch = K / BK;
+    if (tiles >= 2L * c->sched.num_sms || kch < 16) return 1;
+    long want = (2L * c->sched.num_sms + tiles - 1) / tiles;
+    long maxs = kch / 8;   // at least 8 chunks (K = 128) per split
+    if (maxs < 1) maxs = 1;
+    return (int)std::min(want, maxs);
+}
+
+void gemm(geordd_ctx* c, bool a_mc, bool b_nc, int M, int N, int K, double alpha, const double* A, long lda,
+          const double* B, long ldb, double beta, double* C, long ldc, int splitk) {
+    if (splitk <= 0) splitk = pick_splitk(c, M, N, K);
+    if (splitk > 1) ensure_ws(c, (size_t)splitk * ldc * N);
+    ProfScope ps(c, PC_GEMM);
+    launch_gemm(c->stream, a_mc, b_nc, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, splitk, c->ws.p);
+}
+
+int make_posdef(geordd_ctx* c, double* K, double* L, long ld, int n, int npad, int* rounds) {
+    int nr = 0;
+    for (int attempt = 0; attempt <= 10; ++attempt) {
+        {
+            ProfScope ps(c, PC_POTRF);
+            launch_potrf(c->stream, c->sched, K, L, ld, npad);
+        }
+        GD_CUDA(cudaMemcpyAsync(c->h_info, c->sched.abort_word, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        GD_CUDA(cudaStreamSynchronize(c->stream));
+        GD_CUDA(cudaGetLastError());
+        int info = c->h_info[0];
+        if (info != 0) GD_CUDA(cudaMemsetAsync(c->sched.abort_word, 0, sizeof(int), c->stream));
+        if (info < 0) throw ApiError(GEORDD_ERR_WATCHDOG, "potrf watchdog fired");
+        if (info == 0) {
+            if (rounds) *rounds = nr;
+            return 0;
+        }
+        if (attempt == 10) {
+            if (rounds) *rounds = nr;
+            return info;
+        }
+        // eps = 1e-6 * tr(M) / n on the already-jittered matrix; M[i,i] += eps
+        launch_reduce(c->stream, 0, K, nullptr, ld, n, 0, c->d_scal);
+        double tr = read_scalar(c, c->d_scal);
+        double eps = 1e-6 * tr / (double)n;
+        launch_add_diag(c->stream, K, ld, n, eps);
+        ++nr;
+    }
+    return -1;
+}
+
+void pd_solve(geordd_ctx* c, const double* L, long ldl, int npad, double* B, long ldb, int ncols,
+              const SolveEpilogue& epi_bwd) {
+    SolveEpilogue none;
+    {
+        ProfScope ps(c, PC_FWD);
+        launch_solve(c->stream, c->sched, SOLVE_FWD, L, ldl, npad, B, ldb, ncols, none);
+    }
+    {
+        ProfScope ps(c, PC_BWD);
+        launch_solve(c->stream, c->sched, SOLVE_BWD, L, ldl, npad, B, ldb, ncols, epi_bwd);
+    }
+}
+
+// ---- GP ----------------------------------------------------------------------------------------------
+void gp_free(geordd_gp* gp) {
+    if (!gp) return;
+    cudaFree(gp->dX); cudaFree(gp->dK); cudaFree(gp->dL); cudaFree(gp->dR); cudaFree(gp->dAlpha);
+    delete gp;
+}
+
+void gp_update_alpha(geordd_gp* gp) {
+    geordd_ctx* c = gp->ctx;
+    const int npad = gp->npad;
+    // slab: column 0 = r, others zero
+    GD_CUDA(cudaMemsetAsync(gp->dAlpha, 0, (size_t)npad * 64 * sizeof(double), c->stream));
+    GD_CUDA(cudaMemcpyAsync(gp->dAlpha, gp->dR, (size_t)npad * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    SolveEpilogue none;
+    pd_solve(c, gp->dL, npad, npad, gp->dAlpha, npad, 64, none);
+    launch_reduce(c->stream, 2, gp->dR, gp->dAlpha, 0, gp->n, 0, c->d_scal);
+    check_abort(c);
+    double quad = read_scalar(c, c->d_scal);
+    gp->mll = -quad / 2.0 - gp->logdet / 2.0 - (double)gp->n * std::log(2.0 * M_PI) / 2.0;
+}
+
+static void gp_set_resid(geordd_gp* gp, const double* y) {
+    geordd_ctx* c = gp->ctx;
+    gp->y.assign(y, y + gp->n);
+    std::vector<double> r(gp->npad, 0.0);
+    for (int i = 0; i < gp->n; ++i) r[i] = y[i] - gp->k.mean_const;
+    GD_CUDA(cudaMemcpyAsync(gp->dR, r.data(), (size_t)gp->npad * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    GD_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+geordd_gp* gp_create(geordd_ctx* c, const geordd_kernel* k, const double* X, int dim, int n, const double* y,
+                     double log_noise, int* info_out) {
+    check_kernel(k);
+    if (!X || !y || n <= 0 || dim <= 0 || dim > 8) throw ApiError(GEORDD_ERR_ARG, "gp_fit: bad X / y / n / dim (1..8)");
+    geordd_gp* gp = new geordd_gp();
+    try {
+        gp->ctx = c; gp->k = *k; gp->log_noise = log_noise; gp->n = n; gp->dim = dim;
+        gp->npad = round_up(n, TILE);
+        const size_t np = gp->npad;
+        gp->X.assign(X, X + (size_t)dim * n);
+        gp->dX = dalloc((size_t)dim * n, c->stream, false);
+        gp->dK = dalloc(np * np, c->stream, false);
+        gp->dL = dalloc(np * np, c->stream, false);
+        gp->dR = dalloc(np, c->stream, true);
+        gp->dAlpha = dalloc(np * 64, c->stream, true);
+        GD_CUDA(cudaMemcpyAsync(gp->dX, X, (size_t)dim * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        const double noise = std::exp(2.0 * log_noise) + 2.220446049250313e-16;   // exp(2 logNoise) + eps()
+        {
+            ProfScope ps(c, PC_COV);
+            launch_cov(c->stream, to_dev(*k), gp->dX, n, gp->dX, n, dim, true, false, noise, gp->dK, np, gp->npad,
+                       gp->npad, false);
+        }
+        int info = make_posdef(c, gp->dK, gp->dL, np, n, gp->npad, &gp->jitter_rounds);
+        if (info_out) *info_out = info;
+        if (info != 0) {
+            gp_free(gp);
+            return nullptr;
+        }
+        launch_logdiag_sum(c->stream, gp->dL, np, n, c->d_scal + 1);
+        gp->logdet = 2.0 * read_scalar(c, c->d_scal + 1);
+        gp_set_resid(gp, y);
+        gp_update_alpha(gp);
+    } catch (...) {
+        gp_free(gp);
+        throw;
+    }
+    return gp;
+}
+
+void gp_ensure_full_K(geordd_gp* gp) {
+    if (gp->k_full) return;
+    geordd_ctx* c = gp->ctx;
+    // mirror the lower triangle into the upper (tile transposes), keeps the jittered diagonal
+    launch_mirror_lower(c->stream, gp->dK, gp->npad, gp->npad);
+    gp->k_full = true;
+}
+
+}  // namespace geordd
+
+using namespace geordd;
+
+#define API_BEGIN(ctxptr)                  \
+    geordd_ctx* c__ = (ctxptr);            \
+    if (!c__) return GEORDD_ERR_ARG;       \
+    try {                                  \
+        ctx_use(c__);
+#define API_END                            \
+    }                                      \
+    catch (const ApiError& e) {            \
+        return ctx_fail(c__, e);           \
+    }                                      \
+    catch (const std::exception& e) {      \
+        c__->err = e.what();               \
+        return GEORDD_ERR_CUDA;            \
+    }                                      \
+    return 0;
+
+extern "C" {
+
+int geordd_version(void) { return 100; }
+
+int geordd_ctx_create(geordd_ctx** out, int device) {
+    if (!out) return GEORDD_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return GEORDD_ERR_CUDA;   // no GPU: there is deliberately no CPU fallback
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) return GEORDD_ERR_CUDA;
+    geordd_ctx* c = new geordd_ctx();
+    try {
+        c->device = device;
+        GD_CUDA(cudaSetDevice(device));
+        GD_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+        c->stream = c->own_stream;
+        c->sched.num_sms = prop.multiProcessorCount;
+        c->sched.flags_cap = 4u << 20;
+        c->sched.jobs_cap = 1u << 20;
+        GD_CUDA(cudaMalloc(&c->sched.counter, 16 * sizeof(unsigned)));
+        GD_CUDA(cudaMalloc(&c->sched.flags, c->sched.flags_cap * sizeof(unsigned)));
+        GD_CUDA(cudaMalloc(&c->sched.abort_word, sizeof(int)));
+        GD_CUDA(cudaMalloc(&c->sched.jobs, c->sched.jobs_cap * sizeof(int2)));
+        GD_CUDA(cudaMemset(c->sched.counter, 0, 16 * sizeof(unsigned)));
+        GD_CUDA(cudaMemset(c->sched.flags, 0, c->sched.flags_cap * sizeof(unsigned)));
+        GD_CUDA(cudaMemset(c->sched.abort_word, 0, sizeof(int)));
+        c->sched.epoch = 0;
+        GD_CUDA(cudaMalloc(&c->d_scal, 64 * sizeof(double)));
+        GD_CUDA(cudaMallocHost(&c->h_scal, 64 * sizeof(double)));
+        GD_CUDA(cudaMalloc(&c->d_info, 4 * sizeof(int)));
+        GD_CUDA(cudaMallocHost(&c->h_info, 4 * sizeof(int)));
+        GD_CUDA(cudaMalloc(&c->d_tally, 8 * sizeof(unsigned long long)));
+        GD_CUDA(cudaMallocHost(&c->h_tally, 8 * sizeof(unsigned long long)));
+    } catch (const ApiError&) {
+        delete c;
+        return GEORDD_ERR_CUDA;
+    }
+    *out = c;
+    return 0;
+}
+
+int geordd_ctx_destroy(geordd_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    cudaFree(c->sched.counter); cudaFree(c->sched.flags); cudaFree(c->sched.abort_word); cudaFree(c->sched.jobs);
+    cudaFree(c->d_scal); cudaFreeHost(c->h_scal); cudaFree(c->d_info); cudaFreeHost(c->h_info);
+    cudaFree(c->d_tally); cudaFreeHost(c->h_tally);
+    c->ws.release(); c->tmp0.release(); c->tmp1.release(); c->tmp2.release(); c->tmp3.release();
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+    return 0;
+}
+
+const char* geordd_last_error(const geordd_ctx* c) { return c ? c->err.c_str() : "no context (no usable sm_100 GPU)"; }
+
+int geordd_ctx_set_stream(geordd_ctx* c, void* s) {
+    if (!c) return GEORDD_ERR_ARG;
+    cudaStreamSynchronize(c->stream);
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return 0;
+}
+
+int geordd_ctx_sync(geordd_ctx* c) {
+    API_BEGIN(c)
+    GD_CUDA(cudaStreamSynchronize(c->stream));
+    API_END
+}
+
+int geordd_ctx_profile(geordd_ctx* c, int enable) {
+    API_BEGIN(c)
+    prof_collect(c);
+    for (int i = 0; i < PC_COUNT; ++i) { c->prof_ms[i] = 0.0; c->prof_n[i] = 0; }
+    c->prof_on = enable != 0;
+    API_END
+}
+
+int geordd_ctx_profile_get(geordd_ctx* c, const char* name, double* ms, long long* launches) {
+    API_BEGIN(c)
+    prof_collect(c);
+    double t = 0.0;
+    long long n = 0;
+    bool found = false;
+    for (int i = 0; i < PC_COUNT; ++i) {
+        if (!strcmp(name, "*") || !strcmp(name, kProfNames[i])) {
+            t += c->prof_ms[i]; n += c->prof_n[i]; found = true;
+        }
+    }
+    if (!found) throw ApiError(GEORDD_ERR_ARG, "unknown profile class");
+    if (ms) *ms = t;
+    if (launches) *launches = n;
+    API_END
+}
+
+int geordd_ctx_set_max_batch(geordd_ctx* c, long mb) {
+    if (!c || mb < 0) return GEORDD_ERR_ARG;
+    c->max_batch = mb;
+    return 0;
+}
+
+int geordd_cov_sym(geordd_ctx* c, const geordd_kernel* k, const double* X, int dim, int n, double diag_add, double* K) {
+    API_BEGIN(c)
+    check_kernel(k);
+    if (!X || !K || n <= 0 || dim <= 0 || dim > 8) throw ApiError(GEORDD_ERR_ARG, "cov_sym: bad arguments");
+    double* dX = dalloc((size_t)dim * n, c->stream, false);
+    double* dK = nullptr;
+    try {
+        dK = dalloc((size_t)n * n, c->stream, false);
+        GD_CUDA(cudaMemcpyAsync(dX, X, (size_t)dim * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        {
+            ProfScope ps(c, PC_COV);
+            launch_cov(c->stream, to_dev(*k), dX, n, dX, n, dim, true, true, diag_add, dK, n, n, n, false);
+        }
+        GD_CUDA(cudaMemcpyAsync(K, dK, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        GD_CUDA(cudaStreamSynchronize(c->stream));
+    } catch (...) {
+        cudaFree(dX); cudaFree(dK);
+        throw;
+    }
+    cudaFree(dX); cudaFree(dK);
+    API_END
+}
+
+int geordd_cov_cross(geordd_ctx* c, const geordd_kernel* k, const double* X1, int n1, const double* X2, int n2, int dim,
+                     double* K) {
+    API_BEGIN(c)
+    check_kernel(k);
+    if (!X1 || !X2 || !K || n1 <= 0 || n2 <= 0 || dim <= 0 || dim > 8) throw ApiError(GEORDD_ERR_ARG, "cov_cross: bad arguments");
+    double *d1 = nullptr, *d2 = nullptr, *dK = nullptr;
+    try {
+        d1 = dalloc((size_t)dim * n1, c->stream, false);
+        d2 = dalloc((size_t)dim * n2, c->stream, false);
+        dK = dalloc((size_t)n1 * n2, c->stream, false);
+        GD_CUDA(cudaMemcpyAsync(d1, X1, (size_t)dim * n1 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        GD_CUDA(cudaMemcpyAsync(d2, X2, (size_t)dim * n2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        {
+            ProfScope ps(c, PC_COV);
+            launch_cov(c->stream, to_dev(*k), d1, n1, d2, n2, dim, false, false, 0.0, dK, n1, n1, n2, false);
+        }
+        GD_CUDA(cudaMemcpyAsync(K, dK, (size_t)n1 * n2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        GD_CUDA(cudaStreamSynchronize(c->stream));
+    } catch (...) {
+        cudaFree(d1); cudaFree(d2); cudaFree(dK);
+        throw;
+    }
+    cudaFree(d1); cudaFree(d2); cudaFree(dK);
+    API_END
+}
+
+int geordd_gp_fit(geordd_ctx* c, const geordd_kernel* k, const double* X, int dim, int n, const double* y,
+                  double log_noise, geordd_gp** out, double* alpha, double* mll, double* cholU, int* jitter_rounds) {
+    if (out) *out = nullptr;
+    API_BEGIN(c)
+    if (!out) throw ApiError(GEORDD_ERR_ARG, "gp_fit: out is NULL");
+    int info = 0;
+    geordd_gp* gp = gp_create(c, k, X, dim, n, y, log_noise, &info);
+    if (!gp) {
+        c->err = "matrix is not positive definite; Cholesky factorization failed";
+        return info;
+    }
+    if (alpha) GD_CUDA(cudaMemcpyAsync(alpha, gp->dAlpha, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (mll) *mll = gp->mll;
+    if (jitter_rounds) *jitter_rounds = gp->jitter_rounds;
+    if (cholU) {
+        // U = L' : transpose-copy the logical n x n block through scratch
+        c->tmp0.ensure((size_t)n * n, c->stream, false);
+        launch_copy2d(c->stream, c->tmp0.p, n, gp->dL, gp->npad, n, n, true);
+        GD_CUDA(cudaMemcpyAsync(cholU, c->tmp0.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    GD_CUDA(cudaStreamSynchronize(c->stream));
+    *out = gp;
+    API_END
+}
+
+int geordd_gp_set_y(geordd_gp* gp, const double* y, double* alpha, double* mll) {
+    if (!gp) return GEORDD_ERR_ARG;
+    API_BEGIN(gp->ctx)
+    if (!y) throw ApiError(GEORDD_ERR_ARG, "set_y: y is NULL");
+    geordd::gp_set_resid(gp, y);
+    gp_update_alpha(gp);
+    if (alpha) GD_CUDA(cudaMemcpyAsync(alpha, gp->dAlpha, (size_t)gp->n * sizeof(double), cudaMemcpyDeviceToHost, c__->stream));
+    if (mll) *mll = gp->mll;
+    GD_CUDA(cudaStreamSynchronize(c__->stream));
+    API_END
+}
+
+int geordd_gp_get_K(geordd_gp* gp, double* K) {
+    if (!gp) return GEORDD_ERR_ARG;
+    API_BEGIN(gp->ctx)
+    if (!K) throw ApiError(GEORDD_ERR_ARG, "get_K: K is NULL");
+    gp_ensure_full_K(gp);
+    download2d(c__, K, gp->n, gp->dK, gp->npad, gp->n, gp->n);
+    GD_CUDA(cudaStreamSynchronize(c__->stream));
+    API_END
+}
+
+int geordd_gp_nobs(const geordd_gp* gp) { return gp ? gp->n : GEORDD_ERR_ARG; }
+
+int geordd_gp_destroy(geordd_gp* gp) {
+    if (!gp) return 0;
+    cudaSetDevice(gp->ctx->device);
+    cudaStreamSynchronize(gp->ctx->stream);
+    gp_free(gp);
+    return 0;
+}
+
+int geordd_dbg_normals(geordd_ctx* c, unsigned long long seed, unsigned long long draw0, int ndraws, int n, double* Z) {
+    API_BEGIN(c)
+    if (!Z || n <= 0 || ndraws <= 0) throw ApiError(GEORDD_ERR_ARG, "dbg_normals: bad arguments");
+    int npad = round_up(n, 2);
+    double* dZ = dalloc((size_t)npad * ndraws, c->stream, false);
+    try {
+        {
+            ProfScope ps(c, PC_RNG);
+            launch_philox_normals(c->stream, seed, draw0, ndraws, n, dZ, npad, npad);
+        }
+        download2d(c, Z, n, dZ, npad, n, ndraws);
+        GD_CUDA(cudaStreamSynchronize(c->stream));
+    } catch (...) {
+        cudaFree(dZ);
+        throw;
+    }
+    cudaFree(dZ);
+    API_END
+}
+
+int geordd_dbg_gemm(geordd_ctx* c, int transa, int transb, int M, int N, int K, double alpha, const double* A, int lda,
+                    const double* B, int ldb, double beta, double* C, int ldc, int splitk) {
+    API_BEGIN(c)
+    if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C) throw ApiError(GEORDD_ERR_ARG, "dbg_gemm: bad arguments");
+    const int Mp = round_up(M, TILE), Np = round_up(N, 64), Kp = round_up(K, BK);
+    // op(A) is M x K.  transa == 0: stored M x K col-major -> A(m,k) at k*lda+m (a_mc).  transa == 1: stored K x M.
+    const int ar = transa ? K : M, ac = transa ? M : K, arp = transa ? Kp : Mp, acp = transa ? Mp : Kp;
+    const int br = transb ? N : K, bc = transb ? K : N, brp = transb ? Np : Kp, bcp = transb ? Kp : Np;
+    double *dA = nullptr, *dB = nullptr, *dC = nullptr;
+    try {
+        dA = dalloc((size_t)arp * acp, c->stream, true);
+        dB = dalloc((size_t)brp * bcp, c->stream, true);
+        dC = dalloc((size_t)Mp * Np, c->stream, true);
+        upload2d(c, dA, arp, A, lda, ar, ac);
+        upload2d(c, dB, brp, B, ldb, br, bc);
+        upload2d(c, dC, Mp, C, ldc, M, N);
+        // B(k,n): transb == 0 stored K x N col-major -> at n*ldb + k (k contiguous, b_nc = false)
+        gemm(c, !transa, transb != 0, Mp, Np, Kp, alpha, dA, arp, dB, brp, beta, dC, Mp, splitk);
+        download2d(c, C, ldc, dC, Mp, M, N);
+        GD_CUDA(cudaStreamSynchronize(c->stream));
+        GD_CUDA(cudaGetLastError());
+    } catch (...) {
+        cudaFree(dA); cudaFree(dB); cudaFree(dC);
+        throw;
+    }
+    cudaFree(dA); cudaFree(dB); cudaFree(dC);
+    API_END
+}
+
+static void upload_spd_padded(geordd_ctx* c, double* dA, int npad, const double* A, int n) {
+    GD_CUDA(cudaMemsetAsync(dA, 0, (size_t)npad * npad * sizeof(double), c->stream));
+    upload2d(c, dA, npad, A, n, n, n);
+    if (npad > n) launch_add_diag(c->stream, dA + (size_t)n * npad + n, npad, npad - n, 1.0);
+}
+
+int geordd_dbg_potrf(geordd_ctx* c, const double* A, int n, double* L, double* ms) {
+    API_BEGIN(c)
+    if (!A || !L || n <= 0) throw ApiError(GEORDD_ERR_ARG, "dbg_potrf: bad arguments");
+    const int npad = round_up(n, TILE);
+    double *dA = nullptr, *dL = nullptr;
+    int info = 0;
+    try {
+        dA = dalloc((size_t)npad * npad, c->stream, false);
+        dL = dalloc((size_t)npad * npad, c->stream, true);
+        upload_spd_padded(c, dA, npad, A, n);
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        GD_CUDA(cudaStreamSynchronize(c->stream));
+        cudaEventRecord(e0, c->stream);
+        launch_potrf(c->stream, c->sched, dA, dL, npad, npad);
+        cudaEventRecord(e1, c->stream);
+        GD_CUDA(cudaMemcpyAsync(c->h_info, c->sched.abort_word, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        GD_CUDA(cudaStreamSynchronize(c->stream));
+        GD_CUDA(cudaGetLastError());
+        float t = 0.f;
+        cudaEventElapsedTime(&t, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (ms) *ms = t;
+        info = c->h_info[0];
+        GD_CUDA(cudaMemsetAsync(c->sched.abort_word, 0, sizeof(int), c->stream));
+        if (info < 0) throw ApiError(GEORDD_ERR_WATCHDOG, "potrf watchdog fired");
+        // zero the strictly-upper tiles for the copy-out (they are never written by the kernel)
+        std::vector<double> tmp((size_t)n * n);
+        download2d(c, tmp.data(), n, dL, npad, n, n);
+        GD_CUDA(cudaStreamSynchronize(c->stream));
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < n; ++i) L[(size_t)j * n + i] = (i >= j) ? tmp[(size_t)j * n + i] : 0.0;
+    } catch (...) {
+        cudaFree(dA); cudaFree(dL);
+        throw;
+    }
+    cudaFree(dA); cudaFree(dL);
+    if (info > 0) return info;
+    API_END
+}
+
+int geordd_dbg_trsm(geordd_ctx* c, int mode, const double* L, int n, double* B, int nrhs, double* ms) {
+    API_BEGIN(c)
+    if (!L || !B || n <= 0 || nrhs <= 0 || mode < 0 || mode > 2) throw ApiError(GEORDD_ERR_ARG, "dbg_trsm: bad arguments");
+    const int npad = round_up(n, TILE), ncols = round_up(nrhs, 64);
+    double *dL = nullptr, *dB = nullptr, *dO = nullptr;
+    try {
+        dL = dalloc((size_t)npad * npad, c->stream, false);
+        dB = dalloc((size_t)npad * ncols, c->stream, true);
+        upload_spd_padded(c, dL, npad, L, n);
+        upload2d(c, dB, npad, B, n, n, nrhs);
+        SolveEpilogue epi;
+        if (mode == 2) {
+            dO = dalloc((size_t)npad * ncols, c->stream, true);
+            epi.out0 = dO; epi.ld0 = npad; epi.nrows = n; epi.split = n;
+        }
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        GD_CUDA(cudaStreamSynchronize(c->stream));
+        cudaEventRecord(e0, c->stream);
+        launch_solve(c->stream, c->sched, (SolveMode)mode, dL, npad, npad, dB, npad, ncols, epi);
+        cudaEventRecord(e1, c->stream);
+        check_abort(c);
+        float t = 0.f;
+        cudaEventElapsedTime(&t, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (ms) *ms = t;
+        download2d(c, B, n, mode == 2 ? dO : dB, npad, n, nrhs);
+        GD_CUDA(cudaStreamSynchronize(c->stream));
+    } catch (...) {
+        cudaFree(dL); cudaFree(dB); cudaFree(dO);
+        throw;
+    }
+    cudaFree(dL); cudaFree(dB); cudaFree(dO);
+    API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,73 @@
+// geordd_b200 -- shared device helpers (sm_100a only).
+//
+// FP64 on Blackwell reaches the tensor pipe through warp-level mma.sync (SASS DMMA.8x8x4);
+// tcgen05 has no f64 kind.  Everything dense in this library is built from the
+// m8n8k4 f64 MMA below, fed from shared memory staged by cp.async (LDGSTS).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "kernels.h"
+
+namespace geordd {
+
+constexpr int NTHREADS = 256;    // 8 warps per CTA
+constexpr int PAD = 4;           // smem row padding (doubles): stride == 4 (mod 16) -> conflict-free LDS.64 fragments
+
+// ---- FP64 tensor-core MMA: D(8x8) += A(8x4,row) * B(4x8,col) ---------------------------------
+// lane l: g = l>>2, t = l&3.  a = A[g][t], b = B[t][g], c0 = C[g][2t], c1 = C[g][2t+1].
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// ---- cp.async (16 B, L2 only: tiles are produced by other CTAs, never trust L1) ----------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// ---- dataflow flags ------------------------------------------------------------------------------
+// A tile is published with st.release.gpu after __threadfence()+__syncthreads(); consumers poll with
+// ld.acquire.gpu.  Flags carry the launch epoch so they never need clearing.
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_volatile_int(const int* p) {
+    int v;
+    asm volatile("ld.volatile.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Spin (one thread) until *flag == epoch.  A watchdog turns a scheduling bug into an error code
+// instead of a hung GPU: after ~4 s (at ~2 GHz) the abort word is set and every waiter returns false.
+constexpr long long WATCHDOG_CYCLES = 8000000000LL;
+__device__ __forceinline__ bool wait_flag(const unsigned* flag, unsigned epoch, int* abort_word) {
+    if (ld_acquire(flag) == epoch) return true;
+    long long t0 = clock64();
+    unsigned ns = 20;
+    while (true) {
+        if (ld_acquire(flag) == epoch) return true;
+        if (ld_volatile_int(abort_word) != 0) return false;
+        if (clock64() - t0 > WATCHDOG_CYCLES) {
+            atomicCAS(abort_word, 0, -9);
+            return false;
+        }
+        __nanosleep(ns);
+        if (ns < 200) ns += 20;
+    }
+}
+
+__device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }
+
+}  // namespace geordd

@@ -1,0 +1,132 @@
+// K1: covariance-matrix assembly (SE / Matern-1/2,3/2,5/2 isotropic kernels + Const + noise on the
+// diagonal).  Replaces GaussianProcesses.cov / cov! / cov_ij over KernelData distance matrices
+// (call sites: GPE ctor at src/region_gp_fit.jl:12,28 and src/hypotest.jl:4; addcov!/add_diag!
+// src/gp_utils.jl:24-44; cov(kernel, Xb, gp.x) src/hypotest_chi2.jl:38-39, src/power.jl:60-62).
+//
+// HBM-write bound: one 64x64 output tile per CTA, the 2x64 coordinate columns of the tile are staged
+// in shared memory once, distances are direct differences (no Gram trick), every
+// store is a coalesced 512-byte row segment.  Symmetric assembly computes only the tiles on or below
+// the diagonal and mirrors them through a padded smem transpose, halving the exp() work.
+#include "kernels.h"
+
+namespace geordd {
+
+constexpr int CT = 64;
+constexpr int MAXDIM = 8;
+
+__device__ __forceinline__ double kern_eval(int kind, double r2, double ell, double sigma2, double csig2) {
+    double k;
+    if (kind == 0) {
+        k = sigma2 * exp(-0.5 * r2 / (ell * ell));
+    } else {
+        double r = sqrt(r2);
+        if (kind == 1) {
+            k = sigma2 * exp(-r / ell);
+        } else if (kind == 2) {
+            double s = 1.7320508075688772 * r / ell;
+            k = sigma2 * (1.0 + s) * exp(-s);
+        } else {
+            double s = 2.23606797749979 * r / ell;
+            k = sigma2 * (1.0 + s + s * s / 3.0) * exp(-s);
+        }
+    }
+    return k + csig2;
+}
+
+struct CovParams {
+    KernelSpecDev spec;
+    const double* X1; int n1;
+    const double* X2; int n2;
+    int dim;
+    int sym;          // 1: X1 == X2, compute tiles bi >= bj only
+    int mirror;       // sym only: also write the transposed tile
+    double diag_add;
+    double* K; long ldk;
+    int n1p, n2p;     // padded extents to fill (>= n1, n2)
+    int accumulate;   // K += instead of K =
+};
+
+__global__ void __launch_bounds__(256) cov_kernel(CovParams p) {
+    __shared__ double xs1[MAXDIM][CT], xs2[MAXDIM][CT];
+    __shared__ double tile[CT][CT + 1];
+    int bi, bj;
+    if (p.sym) {
+        // linear index over the lower triangle of tile pairs
+        int t = blockIdx.x;
+        int bjj = (int)floor((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+        while ((long)(bjj + 1) * (bjj + 2) / 2 <= t) ++bjj;
+        while ((long)bjj * (bjj + 1) / 2 > t) --bjj;
+        bi = bjj;                       // row tile
+        bj = t - bjj * (bjj + 1) / 2;   // col tile <= row tile
+    } else {
+        bi = blockIdx.x;
+        bj = blockIdx.y;
+    }
+    const int tid = threadIdx.x;
+    const int i0 = bi * CT, j0 = bj * CT;
+    for (int idx = tid; idx < p.dim * CT; idx += 256) {
+        int d = idx % p.dim, c = idx / p.dim;
+        xs1[d][c] = (i0 + c < p.n1) ? p.X1[(long)(i0 + c) * p.dim + d] : 0.0;
+        xs2[d][c] = (j0 + c < p.n2) ? p.X2[(long)(j0 + c) * p.dim + d] : 0.0;
+    }
+    __syncthreads();
+    const int li = tid % CT, lj0 = tid / CT;
+    const int i = i0 + li;
+    double xi[MAXDIM];
+    for (int d = 0; d < p.dim; ++d) xi[d] = xs1[d][li];
+#pragma unroll 4
+    for (int jj = 0; jj < CT / 4; ++jj) {
+        const int lj = lj0 + 4 * jj;
+        const int j = j0 + lj;
+        double v;
+        if (i < p.n1 && j < p.n2) {
+            double r2 = 0.0;
+            for (int d = 0; d < p.dim; ++d) {
+                double df = xi[d] - xs2[d][lj];
+                r2 += df * df;
+            }
+            v = kern_eval(p.spec.kind, r2, p.spec.ell, p.spec.sigma2, p.spec.const_sigma2);
+            if (p.sym && i == j) v += p.diag_add;
+        } else {
+            v = (p.sym && i == j) ? 1.0 : 0.0;
+        }
+        if (i < p.n1p && j < p.n2p) {
+            double* dst = p.K + (long)j * p.ldk + i;
+            if (p.accumulate) *dst += v; else *dst = v;
+        }
+        if (p.mirror) tile[li][lj] = v;
+    }
+    if (p.mirror && bi != bj) {
+        __syncthreads();
+        // transposed tile: element (row = j0 + a, col = i0 + b) = tile[b][a]; a contiguous
+        const int a = tid % CT, b0 = tid / CT;
+#pragma unroll 4
+        for (int bb = 0; bb < CT / 4; ++bb) {
+            const int b = b0 + 4 * bb;
+            const int row = j0 + a, col = i0 + b;
+            if (row < p.n2p && col < p.n1p) {
+                double* dst = p.K + (long)col * p.ldk + row;
+                if (p.accumulate) *dst += tile[b][a]; else *dst = tile[b][a];
+            }
+        }
+    }
+}
+
+void launch_cov(cudaStream_t st, const KernelSpecDev& spec, const double* X1, int n1, const double* X2, int n2,
+                int dim, bool sym, bool mirror, double diag_add, double* K, long ldk, int n1p, int n2p,
+                bool accumulate) {
+    CovParams p;
+    p.spec = spec; p.X1 = X1; p.n1 = n1; p.X2 = X2; p.n2 = n2; p.dim = dim; p.sym = sym ? 1 : 0;
+    p.mirror = (sym && mirror) ? 1 : 0; p.diag_add = diag_add; p.K = K; p.ldk = ldk; p.n1p = n1p; p.n2p = n2p;
+    p.accumulate = accumulate ? 1 : 0;
+    int tb1 = (n1p + CT - 1) / CT, tb2 = (n2p + CT - 1) / CT;
+    if (sym) {
+        int nt = tb1 * (tb1 + 1) / 2;
+        cov_kernel<<<nt, 256, 0, st>>>(p);
+    } else {
+        dim3 grid(tb1, tb2);
+        cov_kernel<<<grid, 256, 0, st>>>(p);
+    }
+}
+
+}  // namespace geordd

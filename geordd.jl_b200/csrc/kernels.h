@@ -1,0 +1,88 @@
+// Internal launcher interface between api.cu and the kernel translation units.
+// Everything here works on DEVICE pointers; matrices are column-major, padded to multiples of
+// TILE (128) in both dimensions unless noted.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace geordd {
+
+constexpr int TILE = 128;        // matrix tile edge: all device matrices are padded to multiples of TILE
+constexpr int BK = 16;           // K-chunk of the mainloop
+
+struct KernelSpecDev {
+    int kind;            // 0 SE, 1 Mat12, 2 Mat32, 3 Mat52
+    double ell, sigma2, const_sigma2;
+};
+
+// Shared scheduling scratch for the dataflow kernels (one per context / stream).
+struct Sched {
+    unsigned* counter;   // job counters (device), 16 words
+    unsigned* flags;     // done-flags (device)
+    size_t flags_cap;    // in words
+    int* abort_word;     // device int: 0 ok, >0 potrf info, <0 watchdog
+    unsigned epoch;      // host-side launch epoch (monotone)
+    int2* jobs;          // device job table scratch
+    size_t jobs_cap;
+    int jobs_T = 0;      // tile count the cached potrf job table was built for
+    int num_sms;
+};
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---- cov.cu ---------------------------------------------------------------------------------------
+// K(i,j) = k(|x1_i - x2_j|) (+ diag_add on i==j when sym).  X1: dim x n1, X2: dim x n2 (column =
+// unit).  Output leading dimension ldk; rows/cols beyond n1/n2 up to the padded size (n1p, n2p) are
+// written as 0 except a unit diagonal when sym (so the padded matrix stays SPD).  sym computes only the
+// tiles on/below the diagonal; mirror additionally writes their transposes (full symmetric matrix).
+void launch_cov(cudaStream_t st, const KernelSpecDev& spec, const double* X1, int n1, const double* X2, int n2,
+                int dim, bool sym, bool mirror, double diag_add, double* K, long ldk, int n1p, int n2p,
+                bool accumulate);
+
+// ---- potrf.cu -------------------------------------------------------------------------------------
+// L = chol(A) (lower), out of place, npad x npad, only the lower triangle of A is read; the strict
+// upper triangle of the diagonal tiles of L is zeroed, upper tiles are not touched.
+// Result code is left in sched.abort_word (0 ok, k>0: pivot k non-positive, <0 watchdog).
+void launch_potrf(cudaStream_t st, Sched& sched, const double* A, double* L, long ld, int npad);
+// out[0] = sum_i log L(i,i) for i < n
+void launch_logdiag_sum(cudaStream_t st, const double* L, long ld, int n, double* out);
+
+// ---- solve.cu -------------------------------------------------------------------------------------
+enum SolveMode { SOLVE_FWD = 0, SOLVE_BWD = 1, SOLVE_TRMM = 2 };
+// In-place triangular solve / multiply against lower factor L (npad x npad) for ncols right-hand
+// sides (ncols multiple of 64): B (npad x ncols, ldb) is overwritten.
+//   FWD:  B <- L^-1 B      BWD: B <- L^-T B      TRMM: Bout <- L * B (out of place, needs Bout)
+struct SolveEpilogue {
+    // FWD/BWD: fused statistic partials, written per row block (deterministic; reduced later):
+    //   dot0[rb*ncols + c] = sum_{r in block rb} (wmat(r,c) + (r < wrows ? wshift : 0)) * X(r,c)
+    //   dot1[rb*ncols + c] = sum_{r in block rb} wvec[r] * X(r,c)
+    const double* wmat = nullptr; long ldw = 0; double wshift = 0.0; int wrows = 0;
+    double* dot0 = nullptr;
+    const double* wvec = nullptr;
+    double* dot1 = nullptr;
+    // TRMM only: Y = L*Z (+ add_const on logical rows, + add_T on rows < split) scattered to
+    //   out0 / out1 : full copies of (Y - sub_0), (Y - sub_1)   (padded rows written as 0)
+    //   outT        : rows [0, split)      of (Y - sub_T)
+    //   outC        : rows [split, nrows)  of (Y - sub_C), re-based to row 0
+    double* out0 = nullptr; long ld0 = 0;
+    double* out1 = nullptr; long ld1 = 0;
+    double* outT = nullptr; long ldT = 0;
+    double* outC = nullptr; long ldC = 0;
+    int split = 0; int nrows = 0;
+    double add_const = 0.0, add_T = 0.0;
+    double sub_0 = 0.0, sub_1 = 0.0, sub_T = 0.0, sub_C = 0.0;
+};
+void launch_solve(cudaStream_t st, Sched& sched, SolveMode mode, const double* L, long ldl, int npad, double* B,
+                  long ldb, int ncols, const SolveEpilogue& epi);
+
+// ---- gemm.cu --------------------------------------------------------------------------------------
+// C(M x N) = alpha * op(A) * op(B) + beta * C.  M multiple of 128, N multiple of 64, K multiple of 16.
+//   a_mc: A(m,k) at A[k*lda+m] else A[m*lda+k];  b_nc: B(k,n) at B[k*ldb+n] else B[n*ldb+k]
+// splitk > 1: partial tiles go to ws (splitk * ldc * N doubles) and are summed in fixed order.
+void launch_gemm(cudaStream_t st, bool a_mc, bool b_nc, int M, int N, int K, double alpha, const double* A, long lda,
+                 const double* B, long ldb, double beta, double* C, long ldc, int splitk, double* ws);
+
+// ---- stats.cu -------------------------------------------------------------------------------------
+void launch_philox_normals(cudaStream_t st, unsigned long long seed, unsigned long long draw0, int ndraws, int n,
+                           double* Z, long ldz, int npad);
+
+}  // namespace geordd

@@ -1,0 +1,175 @@
+// K2: FP64 Cholesky as ONE persistent dataflow kernel (replaces LAPACK dpotrf reached through
+// GaussianProcesses.make_posdef! / PDMats.PDMat -- reference call sites src/gp_utils.jl:45-50,
+// src/GPrealisationsCovars.jl:139, src/hypotest.jl:4).
+//
+// The matrix is cut into 128x128 tiles.  Job (i,j), i >= j, produces the FINAL tile L_ij:
+//     acc = A_ij - sum_{k<j} L_ik L_jk^T        (DMMA mainloop, operands streamed from L2/HBM)
+//     i == j :  L_jj = chol(acc)                (in shared memory)
+//     i >  j :  L_ij = acc * L_jj^-T            (in shared memory)
+// so every tile of L is written exactly once (left-looking per tile).  Jobs are handed out in
+// column-major order by an atomic counter; a job only ever waits (acquire-polling a per-tile flag)
+// on jobs with a smaller index, which are already running on resident CTAs, hence no deadlock and no
+// cooperative launch.  No host round trips, no per-panel launches, natural look-ahead.
+#include "kernels.h"
+#include "mainloop.cuh"
+#include "tileops.cuh"
+
+namespace geordd {
+
+using PotrfML = Mainloop<128, /*A_MC=*/true, /*B_NC=*/true, 4>;
+constexpr int CHUNKS_PER_TILE = TILE / BK;
+
+struct PotrfSrc {
+    const double* L;
+    long lda, ldb;
+    int i, j, T;
+    const unsigned* flags;
+    unsigned epoch;
+    int* abort_word;
+    __device__ __forceinline__ const double* a_ptr(int c) const {
+        return L + (long)(c * BK) * lda + (long)i * TILE;
+    }
+    __device__ __forceinline__ const double* b_ptr(int c) const {
+        return L + (long)(c * BK) * ldb + (long)j * TILE;
+    }
+    __device__ __forceinline__ bool ready(int c) const {
+        if (c % CHUNKS_PER_TILE != 0) return true;
+        int kt = c / CHUNKS_PER_TILE;
+        int ok = 1;
+        if (threadIdx.x == 0) {
+            ok = wait_flag(flags + (long)i * T + kt, epoch, abort_word) &&
+                 wait_flag(flags + (long)j * T + kt, epoch, abort_word);
+        }
+        return __syncthreads_and(ok);
+    }
+};
+
+constexpr int POTRF_CS_ELEMS = TILE * SC;
+constexpr int POTRF_LP_ELEMS = NB * SC;
+constexpr size_t POTRF_SMEM = (size_t)(POTRF_CS_ELEMS + POTRF_LP_ELEMS + TILE) * sizeof(double);
+static_assert(PotrfML::SMEM_BYTES <= POTRF_CS_ELEMS * sizeof(double), "stage ring must fit under the C tile");
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+potrf_dataflow_kernel(const double* __restrict__ A, double* __restrict__ L, long ld, int T, const int2* __restrict__ jobs,
+                      int njobs, unsigned* flags, unsigned epoch, unsigned* counter, int* abort_word) {
+    extern __shared__ __align__(16) double smem[];
+    double* Cs = smem;                       // aliases the mainloop stage ring
+    double* Lp = smem + POTRF_CS_ELEMS;
+    double* invd = Lp + POTRF_LP_ELEMS;
+    __shared__ int sh_job;
+    __shared__ int sh_info;
+    const int tid = threadIdx.x;
+
+    while (true) {
+        if (tid == 0) {
+            int jb = (int)atomicAdd(counter, 1u);
+            if (ld_volatile_int(abort_word) != 0) jb = njobs;
+            sh_job = jb;
+            sh_info = 0;
+        }
+        __syncthreads();
+        const int job = sh_job;
+        if (job >= njobs) break;
+        const int2 ij = jobs[job];
+        const int i = ij.x, j = ij.y;
+
+        PotrfML::Acc acc;
+        {   // acc = -A_ij  (issued first so the loads overlap the pipeline prologue)
+            const double* Aij = A + (long)j * TILE * ld + (long)i * TILE;
+#pragma unroll
+            for (int a = 0; a < PotrfML::MI; ++a)
+#pragma unroll
+                for (int b = 0; b < PotrfML::NJ; ++b)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        acc.v[a][b][e] = -ldcg(Aij + (long)PotrfML::acc_col(b, e) * ld + PotrfML::acc_row(a));
+        }
+        PotrfSrc src{L, ld, ld, i, j, T, flags, epoch, abort_word};
+        bool ok = PotrfML::run(smem, j * CHUNKS_PER_TILE, src, acc);
+        if (!ok) break;
+#pragma unroll
+        for (int a = 0; a < PotrfML::MI; ++a)
+#pragma unroll
+            for (int b = 0; b < PotrfML::NJ; ++b)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    Cs[PotrfML::acc_col(b, e) * SC + PotrfML::acc_row(a)] = -acc.v[a][b][e];
+        __syncthreads();
+
+        double* Lij = L + (long)j * TILE * ld + (long)i * TILE;
+        if (i == j) {
+            potrf_tile(Cs, invd, &sh_info);
+            __syncthreads();
+            if (sh_info != 0) {
+                if (tid == 0) atomicCAS(abort_word, 0, j * TILE + sh_info);
+                break;
+            }
+            for (int idx = tid; idx < TILE * TILE; idx += NTHREADS) {
+                int n = idx / TILE, m = idx % TILE;
+                Lij[(long)n * ld + m] = (m >= n) ? Cs[n * SC + m] : 0.0;
+            }
+        } else {
+            int okf = 1;
+            if (tid == 0) okf = wait_flag(flags + (long)j * T + j, epoch, abort_word);
+            if (!__syncthreads_and(okf)) break;
+            trsm_right_tile(Cs, Lp, invd, L + (long)j * TILE * ld + (long)j * TILE, ld);
+            for (int idx = tid; idx < TILE * TILE; idx += NTHREADS) {
+                int n = idx / TILE, m = idx % TILE;
+                Lij[(long)n * ld + m] = Cs[n * SC + m];
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) st_release(flags + (long)i * T + j, epoch);
+    }
+}
+
+static void build_potrf_jobs(int T, int2* host) {
+    int p = 0;
+    for (int j = 0; j < T; ++j)
+        for (int i = j; i < T; ++i) host[p++] = make_int2(i, j);
+}
+
+void launch_potrf(cudaStream_t st, Sched& sched, const double* A, double* L, long ld, int npad) {
+    const int T = npad / TILE;
+    const int njobs = T * (T + 1) / 2;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(potrf_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM);
+        attr_set = true;
+    }
+    if (sched.jobs_T != T) {   // job table cached per tile count
+        int2* hjobs = (int2*)malloc(sizeof(int2) * njobs);
+        build_potrf_jobs(T, hjobs);
+        cudaMemcpyAsync(sched.jobs, hjobs, sizeof(int2) * njobs, cudaMemcpyHostToDevice, st);
+        cudaStreamSynchronize(st);   // hjobs is pageable: complete the copy before free
+        free(hjobs);
+        sched.jobs_T = T;
+    }
+    cudaMemsetAsync(sched.counter, 0, sizeof(unsigned), st);
+    cudaMemsetAsync(sched.abort_word, 0, sizeof(int), st);
+    sched.epoch++;
+    int grid = njobs < sched.num_sms ? njobs : sched.num_sms;
+    potrf_dataflow_kernel<<<grid, NTHREADS, POTRF_SMEM, st>>>(A, L, ld, T, sched.jobs, njobs, sched.flags, sched.epoch,
+                                                              sched.counter, sched.abort_word);
+}
+
+__global__ void logdiag_sum_kernel(const double* __restrict__ L, long ld, int n, double* out) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += log(L[(long)i * ld + i]);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) out[0] = s;
+    }
+}
+
+void launch_logdiag_sum(cudaStream_t st, const double* L, long ld, int n, double* out) {
+    logdiag_sum_kernel<<<1, 1024, 0, st>>>(L, ld, n, out);
+}
+
+}  // namespace geordd

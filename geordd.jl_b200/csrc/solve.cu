@@ -1,0 +1,225 @@
+// K3/K4: batched triangular solves and triangular multiply over many right-hand sides (= null
+// draws), as persistent dataflow kernels on the DMMA pipe.
+//
+// Replaces, batched over draws, the per-draw level-2 BLAS of the reference hot loops:
+//   prior_rand      y = mu + U'z            dtrmv   src/hypotest.jl:13-18           -> SOLVE_TRMM
+//   update_alpha!   alpha = cK \ (y - m)     dpotrs  src/gp_utils.jl:15-18           -> SOLVE_FWD + SOLVE_BWD
+//   PDcliff \ mu                             dpotrs  src/hypotest_chi2.jl:16          -> SOLVE_FWD + SOLVE_BWD
+// and the whitening solve of predict_f (src/cliff_face.jl:4-5) with the sentinels as columns.
+//
+// Right-hand sides are cut into slabs of 64 columns, the factor into 128-row blocks.  Job (rb, s)
+// produces the final 128x64 block X(rb, s):
+//     acc = B(rb,s) - sum_j L(rb,j) X(j,s)      (DMMA mainloop; L from L2/HBM, X from this slab)
+//     X(rb,s) = L(rb,rb)^-1 acc                 (substitution in shared memory)
+// Jobs are issued level by level (rb ascending for forward, descending for backward) through an
+// atomic counter; a job waits only on lower-index jobs of its own slab (acquire-polled flags).
+// With many slabs nobody ever waits; with few slabs (cliff face: nb = 100 sentinels) the row blocks
+// of one slab pipeline across CTAs instead of serialising on one SM.
+#include "kernels.h"
+#include "mainloop.cuh"
+#include "tileops.cuh"
+
+namespace geordd {
+
+constexpr int SLAB = 64;
+constexpr int CHUNKS_PER_TILE_S = TILE / BK;
+
+template <int MODE>
+struct SolveCfg {
+    static constexpr bool A_MC = (MODE != SOLVE_BWD);
+    using ML = Mainloop<SLAB, A_MC, /*B_NC=*/false, 3>;
+};
+
+template <int MODE>
+struct SolveSrc {
+    const double* L;
+    const double* X;   // slab base: column 0 of this slab, row 0
+    long lda, ldb;
+    int rb, T, s, nslabs;
+    const unsigned* flags;
+    unsigned epoch;
+    int* abort_word;
+    __device__ __forceinline__ int ktile(int c) const {
+        return MODE == SOLVE_BWD ? (T - 1 - c / CHUNKS_PER_TILE_S) : c / CHUNKS_PER_TILE_S;
+    }
+    __device__ __forceinline__ const double* a_ptr(int c) const {
+        int kt = ktile(c), kk = (c % CHUNKS_PER_TILE_S) * BK;
+        if (MODE == SOLVE_BWD)   // A(m,k) = L(kt*128+kk+k, rb*128+m): k contiguous
+            return L + (long)rb * TILE * lda + (long)kt * TILE + kk;
+        return L + ((long)kt * TILE + kk) * lda + (long)rb * TILE;   // A(m,k) = L(rb*128+m, kt*128+kk+k)
+    }
+    __device__ __forceinline__ const double* b_ptr(int c) const {
+        int kt = ktile(c), kk = (c % CHUNKS_PER_TILE_S) * BK;
+        return X + (long)kt * TILE + kk;   // B(k,n) = X(kt*128+kk+k, n): k contiguous
+    }
+    __device__ __forceinline__ bool ready(int c) const {
+        if (MODE == SOLVE_TRMM) return true;
+        if (c % CHUNKS_PER_TILE_S != 0) return true;
+        int ok = 1;
+        if (threadIdx.x == 0) ok = wait_flag(flags + (long)ktile(c) * nslabs + s, epoch, abort_word);
+        return __syncthreads_and(ok);
+    }
+};
+
+struct SolveParams {
+    const double* L;
+    long ldl;
+    int T;
+    double* B;         // FWD/BWD: in place.  TRMM: input Z
+    long ldb;
+    int nslabs;
+    unsigned* flags;
+    unsigned epoch;
+    unsigned* counter;
+    int* abort_word;
+    SolveEpilogue epi;
+};
+
+constexpr int SOLVE_CS_ELEMS = SLAB * SC;                       // 8448
+constexpr int SOLVE_PANEL_ELEMS = TILE * LRS;                   // 4608 >= NB*SC = 4224
+constexpr int SOLVE_SMEM_ELEMS = SOLVE_CS_ELEMS + SOLVE_PANEL_ELEMS + NB;
+constexpr size_t SOLVE_SMEM = (size_t)SOLVE_SMEM_ELEMS * sizeof(double);
+
+template <int MODE>
+__global__ void __launch_bounds__(NTHREADS, 2) solve_dataflow_kernel(SolveParams p) {
+    using ML = typename SolveCfg<MODE>::ML;
+    static_assert(ML::SMEM_BYTES <= SOLVE_SMEM, "stage ring must fit");
+    extern __shared__ __align__(16) double smem[];
+    double* Cs = smem;
+    double* Lp = smem + SOLVE_CS_ELEMS;
+    double* invd = Lp + SOLVE_PANEL_ELEMS;
+    __shared__ int sh_job;
+    const int tid = threadIdx.x;
+    const int njobs = p.T * p.nslabs;
+    const long ncols = (long)p.nslabs * SLAB;
+
+    while (true) {
+        if (tid == 0) {
+            int jb = (int)atomicAdd(p.counter, 1u);
+            if (ld_volatile_int(p.abort_word) != 0) jb = njobs;
+            sh_job = jb;
+        }
+        __syncthreads();
+        const int job = sh_job;
+        if (job >= njobs) break;
+        const int lvl = job / p.nslabs, s = job % p.nslabs;
+        const int rb = (MODE == SOLVE_FWD) ? lvl : (p.T - 1 - lvl);
+        double* Bslab = p.B + (long)s * SLAB * p.ldb;
+
+        typename ML::Acc acc;
+        if (MODE == SOLVE_TRMM) {
+            ML::zero(acc);
+        } else {
+            const double* Brb = Bslab + (long)rb * TILE;
+#pragma unroll
+            for (int a = 0; a < ML::MI; ++a)
+#pragma unroll
+                for (int b = 0; b < ML::NJ; ++b)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        acc.v[a][b][e] = -ldcg(Brb + (long)ML::acc_col(b, e) * p.ldb + ML::acc_row(a));
+        }
+        SolveSrc<MODE> src{p.L, Bslab, p.ldl, p.ldb, rb, p.T, s, p.nslabs, p.flags, p.epoch, p.abort_word};
+        int nchunks = (MODE == SOLVE_FWD) ? rb * CHUNKS_PER_TILE_S
+                    : (MODE == SOLVE_BWD) ? (p.T - 1 - rb) * CHUNKS_PER_TILE_S
+                                          : (rb + 1) * CHUNKS_PER_TILE_S;
+        bool ok = ML::run(smem, nchunks, src, acc);
+        if (!ok) break;
+        const double sgn = (MODE == SOLVE_TRMM) ? 1.0 : -1.0;
+#pragma unroll
+        for (int a = 0; a < ML::MI; ++a)
+#pragma unroll
+            for (int b = 0; b < ML::NJ; ++b)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) Cs[ML::acc_col(b, e) * SC + ML::acc_row(a)] = sgn * acc.v[a][b][e];
+        __syncthreads();
+
+        const double* Ldiag = p.L + (long)rb * TILE * p.ldl + (long)rb * TILE;
+        if (MODE == SOLVE_FWD) solve_fwd_tile(Cs, SLAB, Lp, invd, Ldiag, p.ldl);
+        if (MODE == SOLVE_BWD) solve_bwd_tile(Cs, SLAB, Lp, invd, Ldiag, p.ldl);
+
+        const SolveEpilogue& e = p.epi;
+        if (MODE == SOLVE_TRMM) {
+            for (int idx = tid; idx < SLAB * TILE; idx += NTHREADS) {
+                int n = idx / TILE, m = idx % TILE;
+                long col = (long)s * SLAB + n;
+                int r = rb * TILE + m;
+                double v = Cs[n * SC + m];
+                bool live = r < e.nrows;
+                if (live) v += e.add_const + (r < e.split ? e.add_T : 0.0);
+                if (e.out0) e.out0[col * e.ld0 + r] = live ? v - e.sub_0 : 0.0;
+                if (e.out1) e.out1[col * e.ld1 + r] = live ? v - e.sub_1 : 0.0;
+                if (live) {
+                    if (r < e.split) {
+                        if (e.outT) e.outT[col * e.ldT + r] = v - e.sub_T;
+                    } else {
+                        if (e.outC) e.outC[col * e.ldC + (r - e.split)] = v - e.sub_C;
+                    }
+                }
+            }
+        } else {
+            double* Brb = Bslab + (long)rb * TILE;
+            for (int idx = tid; idx < SLAB * TILE; idx += NTHREADS) {
+                int n = idx / TILE, m = idx % TILE;
+                Brb[(long)n * p.ldb + m] = Cs[n * SC + m];
+            }
+            // fused statistic partials: 4 threads per column, 32 rows each, quad shuffle-reduce
+            if (e.dot0 || e.dot1) {
+                const int n = tid >> 2, q = tid & 3;
+                const long col = (long)s * SLAB + n;
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll 4
+                for (int mm = 0; mm < 32; ++mm) {
+                    int m = q * 32 + mm;
+                    int r = rb * TILE + m;
+                    double x = Cs[n * SC + m];
+                    if (e.dot0) {
+                        double w = ldcg(e.wmat + col * e.ldw + r);
+                        if (r < e.wrows) w += e.wshift;
+                        s0 += w * x;
+                    }
+                    if (e.dot1) s1 += e.wvec[r] * x;
+                }
+                s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+                s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+                if (q == 0) {
+                    if (e.dot0) e.dot0[(long)rb * ncols + col] = s0;
+                    if (e.dot1) e.dot1[(long)rb * ncols + col] = s1;
+                }
+            }
+            __threadfence();
+        }
+        __syncthreads();
+        if (MODE != SOLVE_TRMM && tid == 0) st_release(p.flags + (long)rb * p.nslabs + s, p.epoch);
+    }
+}
+
+template <int MODE>
+static void launch_mode(cudaStream_t st, Sched& sched, const SolveParams& p) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(solve_dataflow_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM);
+        attr_set = true;
+    }
+    int njobs = p.T * p.nslabs;
+    int grid = 2 * sched.num_sms;
+    if (grid > njobs) grid = njobs;
+    solve_dataflow_kernel<MODE><<<grid, NTHREADS, SOLVE_SMEM, st>>>(p);
+}
+
+void launch_solve(cudaStream_t st, Sched& sched, SolveMode mode, const double* L, long ldl, int npad, double* B,
+                  long ldb, int ncols, const SolveEpilogue& epi) {
+    SolveParams p;
+    p.L = L; p.ldl = ldl; p.T = npad / TILE; p.B = B; p.ldb = ldb; p.nslabs = ncols / SLAB;
+    p.flags = sched.flags; p.counter = sched.counter; p.abort_word = sched.abort_word; p.epi = epi;
+    cudaMemsetAsync(sched.counter, 0, sizeof(unsigned), st);
+    sched.epoch++;
+    p.epoch = sched.epoch;
+    if (mode == SOLVE_FWD) launch_mode<SOLVE_FWD>(st, sched, p);
+    else if (mode == SOLVE_BWD) launch_mode<SOLVE_BWD>(st, sched, p);
+    else launch_mode<SOLVE_TRMM>(st, sched, p);
+}
+
+}  // namespace geordd

@@ -1,0 +1,351 @@
+// Small kernels around the dense core: counter-based normal draws, statistic finishing with
+// integer exceedance tallies, the pivoted-LU solve used for the OBSERVED statistics (Julia's generic
+// `Sigma \ mu` on a Matrix is lu(), src/hypotest_chi2.jl:9, src/average_treatment_effect.jl:6-7),
+// and a handful of vector/matrix utilities.
+#include "kernels.h"
+#include "smallops.h"
+
+namespace geordd {
+
+// ---------------------------------------------------------------------------------------------------
+// Philox-4x32-10 -> Box-Muller standard normals.  Element pair (2j, 2j+1) of draw d comes from
+// counter (j, 0, d_lo, d_hi), key (seed_lo, seed_hi); the oracle implements the same generator
+// (oracle/geordd_oracle.py: philox_normals).  One randn(n) per draw, consumed in order, exactly as
+// rand(MvNormal) does in src/hypotest.jl:13-18.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox_round(unsigned& c0, unsigned& c1, unsigned& c2, unsigned& c3, unsigned k0,
+                                             unsigned k1) {
+    const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    unsigned hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    unsigned hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    unsigned n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+
+__global__ void philox_normals_kernel(unsigned long long seed, unsigned long long draw0, int ndraws, int n,
+                                      double* __restrict__ Z, long ldz, int npad) {
+    const int npairp = npad / 2;
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)npairp * ndraws) return;
+    int j = (int)(idx % npairp);
+    int s = (int)(idx / npairp);
+    double z0 = 0.0, z1 = 0.0;
+    if (2 * j < n) {
+        unsigned long long d = draw0 + (unsigned long long)s;
+        unsigned c0 = (unsigned)j, c1 = 0u, c2 = (unsigned)(d & 0xffffffffull), c3 = (unsigned)(d >> 32);
+        unsigned k0 = (unsigned)(seed & 0xffffffffull), k1 = (unsigned)(seed >> 32);
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            philox_round(c0, c1, c2, c3, k0, k1);
+            k0 += 0x9E3779B9u;
+            k1 += 0xBB67AE85u;
+        }
+        unsigned long long w1 = ((unsigned long long)c0 << 32) | c1;
+        unsigned long long w2 = ((unsigned long long)c2 << 32) | c3;
+        double u1 = ((double)(w1 >> 11) + 0.5) * 1.1102230246251565e-16;   // 2^-53
+        double u2 = ((double)(w2 >> 11) + 0.5) * 1.1102230246251565e-16;
+        double rad = sqrt(-2.0 * log(u1));
+        double sn, cs;
+        sincospi(2.0 * u2, &sn, &cs);
+        z0 = rad * cs;
+        z1 = (2 * j + 1 < n) ? rad * sn : 0.0;
+    }
+    double2* dst = reinterpret_cast<double2*>(Z + (long)s * ldz + 2 * j);
+    *dst = make_double2(z0, z1);
+}
+
+void launch_philox_normals(cudaStream_t st, unsigned long long seed, unsigned long long draw0, int ndraws, int n,
+                           double* Z, long ldz, int npad) {
+    long tot = (long)(npad / 2) * ndraws;
+    philox_normals_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(seed, draw0, ndraws, n, Z, ldz, npad);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Statistic finishing.  Partials come from the solve epilogue as [nblocks x ncols] arrays and are
+// summed in block order (deterministic).  Tallies are integer atomics (order independent).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double sum_partials(const double* part, int nblocks, long ncols, long c) {
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += part[(long)b * ncols + c];
+    return s;
+}
+
+__device__ __forceinline__ void block_tally(bool hit, unsigned long long* counter) {
+    unsigned ballot = __ballot_sync(0xffffffffu, hit);
+    __shared__ int sh_cnt;
+    if (threadIdx.x == 0) sh_cnt = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(&sh_cnt, __popc(ballot));
+    __syncthreads();
+    if (threadIdx.x == 0 && sh_cnt) atomicAdd(counter, (unsigned long long)sh_cnt);
+}
+
+// mll_X = -0.5 * dot_X + c_X with c_X = -0.5 logdet_X - n_X/2 log(2 pi)   (src/gp_utils.jl:19-22)
+__global__ void finish_mll_kernel(FinishMll f) {
+    long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool hit = false;
+    if (c < f.ndraws) {
+        double dN = sum_partials(f.partN, f.nbN, f.ncols, c);
+        double dT = sum_partials(f.partT, f.nbT, f.ncols, c);
+        double dC = sum_partials(f.partC, f.nbC, f.ncols, c);
+        double mllN = -dN / 2.0 - f.halflogdetN - f.constN;
+        double mllT = -dT / 2.0 - f.halflogdetT - f.constT;
+        double mllC = -dC / 2.0 - f.halflogdetC - f.constC;
+        double alt = mllT + mllC;
+        if (f.out_null) f.out_null[f.out_off + c] = mllN;
+        if (f.out_alt) f.out_alt[f.out_off + c] = alt;
+        hit = (alt - mllN) > f.dmll_obs;     // mean(dmll_sim .> dmll_obs), src/hypotest_mll.jl:42-44
+    }
+    block_tally(hit, f.tally);
+}
+void launch_finish_mll(cudaStream_t st, const FinishMll& f) {
+    finish_mll_kernel<<<(unsigned)((f.ndraws + 255) / 256), 256, 0, st>>>(f);
+}
+
+// chi2 = dot(mu, Sigma \ mu) (src/hypotest_chi2.jl:16); invvar: tau = sum(Sigma\mu)/denom,
+// V = 1/denom, p = 2 min(cdf(N(tau, sqrt V), 0), ccdf(...)) (src/average_treatment_effect.jl:3-11,
+// src/hypotest_invvar.jl:16-18; Normal cdf via erfc as StatsFuns does).
+__global__ void finish_cliff_kernel(FinishCliff f) {
+    long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool hit_chi = false, hit_inv = false;
+    if (c < f.ndraws) {
+        if (f.part_chi) {
+            double chi = sum_partials(f.part_chi, f.nb, f.ncols, c);
+            if (f.out_chi) f.out_chi[f.out_off + c] = chi;
+            hit_chi = chi > f.chi_obs;
+        }
+        if (f.part_num) {
+            double num = sum_partials(f.part_num, f.nb, f.ncols, c);
+            double tau = num / f.denom;
+            double sd = sqrt(1.0 / f.denom);
+            double z = (0.0 - tau) / sd;
+            double cdf = erfc(-z * 0.7071067811865476) / 2.0;
+            double ccdf = erfc(z * 0.7071067811865476) / 2.0;
+            double p = 2.0 * fmin(cdf, ccdf);
+            if (f.out_pval) f.out_pval[f.out_off + c] = p;
+            if (f.out_num) f.out_num[f.out_off + c] = num;
+            hit_inv = p < f.pval_obs;
+        }
+    }
+    if (f.part_chi) block_tally(hit_chi, f.tally_chi);
+    if (f.part_num) block_tally(hit_inv, f.tally_inv);
+}
+void launch_finish_cliff(cudaStream_t st, const FinishCliff& f) {
+    finish_cliff_kernel<<<(unsigned)((f.ndraws + 255) / 256), 256, 0, st>>>(f);
+}
+
+// out[s] = mean(ref .> x[s]) (greater != 0) or mean(ref .< x[s])   (src/power.jl:31,35,40)
+__global__ void frac_compare_kernel(const double* ref, long nref, const double* x, long n, int greater, double* out) {
+    long s = blockIdx.x;
+    if (s >= n) return;
+    double xv = x[s];
+    int cnt = 0;
+    for (long i = threadIdx.x; i < nref; i += blockDim.x) cnt += greater ? (ref[i] > xv) : (ref[i] < xv);
+    __shared__ int sh;
+    if (threadIdx.x == 0) sh = 0;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&sh, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) out[s] = (double)sh / (double)nref;
+}
+void launch_frac_compare(cudaStream_t st, const double* ref, long nref, const double* x, long n, bool greater,
+                         double* out) {
+    if (n > 0) frac_compare_kernel<<<(unsigned)n, 256, 0, st>>>(ref, nref, x, n, greater ? 1 : 0, out);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Pivoted LU solve, single CTA (n up to a few thousand; nb x nb cliff-face systems).  A is
+// overwritten by its LU factors, B (n x nrhs) by the solution.  Partial pivoting picks the first
+// row of maximum modulus (idamax), scaling multiplies by the reciprocal pivot (dgetf2).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) lu_solve_kernel(double* A, long lda, int n, double* B, long ldb, int nrhs,
+                                                        int* info) {
+    __shared__ double sval[32];
+    __shared__ int sidx[32];
+    __shared__ int spiv;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int k = 0; k < n; ++k) {
+        double best = -1.0;
+        int bi = n;
+        for (int i = k + tid; i < n; i += nt) {
+            double v = fabs(A[(long)k * lda + i]);
+            if (v > best) { best = v; bi = i; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            double ov = __shfl_down_sync(0xffffffffu, best, o);
+            int oi = __shfl_down_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if ((tid & 31) == 0) { sval[tid >> 5] = best; sidx[tid >> 5] = bi; }
+        __syncthreads();
+        if (tid < 32) {
+            best = tid < (nt >> 5) ? sval[tid] : -1.0;
+            bi = tid < (nt >> 5) ? sidx[tid] : n;
+            for (int o = 16; o > 0; o >>= 1) {
+                double ov = __shfl_down_sync(0xffffffffu, best, o);
+                int oi = __shfl_down_sync(0xffffffffu, bi, o);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            if (tid == 0) {
+                spiv = bi;
+                if (!(best > 0.0) && *info == 0) *info = k + 1;
+            }
+        }
+        __syncthreads();
+        const int piv = spiv;
+        if (piv != k && piv < n) {
+            for (int j = tid; j < n; j += nt) {
+                double t = A[(long)j * lda + k];
+                A[(long)j * lda + k] = A[(long)j * lda + piv];
+                A[(long)j * lda + piv] = t;
+            }
+            for (int j = tid; j < nrhs; j += nt) {
+                double t = B[(long)j * ldb + k];
+                B[(long)j * ldb + k] = B[(long)j * ldb + piv];
+                B[(long)j * ldb + piv] = t;
+            }
+        }
+        __syncthreads();
+        const double rp = 1.0 / A[(long)k * lda + k];
+        for (int i = k + 1 + tid; i < n; i += nt) A[(long)k * lda + i] *= rp;
+        __syncthreads();
+        const int rem = n - k - 1;
+        if (rem > 0) {
+            const long tot = (long)rem * (rem + nrhs);
+            for (long idx = tid; idx < tot; idx += nt) {
+                int i = k + 1 + (int)(idx % rem);
+                int jj = (int)(idx / rem);
+                double lik = A[(long)k * lda + i];
+                if (jj < rem) {
+                    int j = k + 1 + jj;
+                    A[(long)j * lda + i] -= lik * A[(long)j * lda + k];
+                } else {
+                    int j = jj - rem;
+                    B[(long)j * ldb + i] -= lik * B[(long)j * ldb + k];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // back substitution with U, column oriented
+    for (int k = n - 1; k >= 0; --k) {
+        const double ukk = A[(long)k * lda + k];
+        for (int j = tid; j < nrhs; j += nt) B[(long)j * ldb + k] /= ukk;
+        __syncthreads();
+        const long tot = (long)k * nrhs;
+        for (long idx = tid; idx < tot; idx += nt) {
+            int i = (int)(idx % k), j = (int)(idx / k);
+            B[(long)j * ldb + i] -= A[(long)k * lda + i] * B[(long)j * ldb + k];
+        }
+        __syncthreads();
+    }
+}
+void launch_lu_solve(cudaStream_t st, double* A, long lda, int n, double* B, long ldb, int nrhs, int* info) {
+    cudaMemsetAsync(info, 0, sizeof(int), st);
+    lu_solve_kernel<<<1, 1024, 0, st>>>(A, lda, n, B, ldb, nrhs, info);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Utilities
+// ---------------------------------------------------------------------------------------------------
+__global__ void fill_kernel(double* p, long n, double v) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+void launch_fill(cudaStream_t st, double* p, long n, double v) {
+    if (n > 0) fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, v);
+}
+
+// dst(r, c) = src(r, c) for r < rows, c < cols; optional transpose of the source.
+__global__ void copy2d_kernel(double* dst, long ldd, const double* src, long lds, int rows, int cols, int trans) {
+    __shared__ double t[32][33];
+    int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    if (!trans) {
+        for (int cc = threadIdx.y; cc < 32; cc += blockDim.y) {
+            int r = r0 + threadIdx.x, c = c0 + cc;
+            if (r < rows && c < cols) dst[(long)c * ldd + r] = src[(long)c * lds + r];
+        }
+    } else {
+        // dst(r, c) = src(c, r)
+        for (int cc = threadIdx.y; cc < 32; cc += blockDim.y) {
+            int sr = c0 + threadIdx.x, sc = r0 + cc;   // src row (contiguous) = dst col
+            if (sr < cols && sc < rows) t[cc][threadIdx.x] = src[(long)sc * lds + sr];
+        }
+        __syncthreads();
+        for (int cc = threadIdx.y; cc < 32; cc += blockDim.y) {
+            int r = r0 + threadIdx.x, c = c0 + cc;
+            if (r < rows && c < cols) dst[(long)c * ldd + r] = t[threadIdx.x][cc];
+        }
+    }
+}
+void launch_copy2d(cudaStream_t st, double* dst, long ldd, const double* src, long lds, int rows, int cols,
+                   bool trans) {
+    if (rows <= 0 || cols <= 0) return;
+    dim3 grid((rows + 31) / 32, (cols + 31) / 32), block(32, 8);
+    copy2d_kernel<<<grid, block, 0, st>>>(dst, ldd, src, lds, rows, cols, trans ? 1 : 0);
+}
+
+// A(i,i) += v for i < n
+__global__ void add_diag_kernel(double* A, long ld, int n, double v) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) A[(long)i * ld + i] += v;
+}
+void launch_add_diag(cudaStream_t st, double* A, long ld, int n, double v) {
+    if (n > 0) add_diag_kernel<<<(n + 255) / 256, 256, 0, st>>>(A, ld, n, v);
+}
+
+// Single-block reductions: mode 0 trace(A), 1 sum(x), 2 dot(x,y), 3 sum of all entries of A (n x n2)
+__global__ void reduce_kernel(int mode, const double* x, const double* y, long ld, long n, long n2, double* out) {
+    __shared__ double red[32];
+    double s = 0.0;
+    if (mode == 0) for (long i = threadIdx.x; i < n; i += blockDim.x) s += x[i * ld + i];
+    else if (mode == 1) for (long i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+    else if (mode == 2) for (long i = threadIdx.x; i < n; i += blockDim.x) s += x[i] * y[i];
+    else for (long idx = threadIdx.x; idx < n * n2; idx += blockDim.x) s += x[(idx / n) * ld + idx % n];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) out[0] = s;
+    }
+}
+void launch_reduce(cudaStream_t st, int mode, const double* x, const double* y, long ld, long n, long n2, double* out) {
+    reduce_kernel<<<1, 1024, 0, st>>>(mode, x, y, ld, n, n2, out);
+}
+
+// M(r, c) += v for r < rows, c < cols
+__global__ void add_const_kernel(double* M, long ld, int rows, long cols, double v) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)rows * cols) return;
+    M[(idx / rows) * ld + idx % rows] += v;
+}
+void launch_add_const(cudaStream_t st, double* M, long ld, int rows, long cols, double v) {
+    long tot = (long)rows * cols;
+    if (tot > 0 && v != 0.0) add_const_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(M, ld, rows, cols, v);
+}
+
+// y = a*x + b*y elementwise over n
+__global__ void axpby_kernel(long n, double a, const double* x, double b, double* y) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = a * x[i] + (b != 0.0 ? b * y[i] : 0.0);
+}
+void launch_axpby(cudaStream_t st, long n, double a, const double* x, double b, double* y) {
+    if (n > 0) axpby_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, a, x, b, y);
+}
+
+// Mirror the lower triangle of an n x n matrix into the upper (copytri!)
+__global__ void mirror_lower_kernel(double* A, long ld, int n) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)n * n) return;
+    int r = (int)(idx % n), c = (int)(idx / n);
+    if (r < c) A[(long)c * ld + r] = A[(long)r * ld + c];
+}
+void launch_mirror_lower(cudaStream_t st, double* A, long ld, int n) {
+    long tot = (long)n * n;
+    if (tot > 0) mirror_lower_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(A, ld, n);
+}
+
+}  // namespace geordd

@@ -1,0 +1,251 @@
+// In-shared-memory operations on one 128 x N tile (the "finalize" step of every dataflow job):
+// Cholesky of a diagonal tile, right/left triangular solves against a diagonal tile.
+//
+// Tile layout in smem: C(m, n) at Cs[n * SC + m], SC = 132 (column-major, padded).
+// Every op is blocked by NB = 32: a thread-per-row (or per-column) substitution on the 32-wide
+// diagonal block (true substitution, reciprocal of the pivot like OpenBLAS/LAPACK dpotf2), then a
+// DMMA rank-32 update of the remainder straight out of shared memory.
+#pragma once
+#include "common.cuh"
+
+namespace geordd {
+
+constexpr int SC = TILE + PAD;   // 132: stride of tiles held in smem
+constexpr int NB = 32;           // inner block
+constexpr int LRS = NB + PAD;    // 36: stride of a row-panel held k-contiguous
+
+// C(m0.., n0..) -= A * B over K = NB, for 8x8 output tiles (mt, nt), mt in [0,mtiles), nt in
+// [0,ntiles); fa(m,k), fb(k,n) fetch operands (m, n relative to m0, n0).  If `lower`, only tiles
+// with m0+8mt >= n0+8nt are touched.  All 8 warps participate; caller syncs before/after.
+template <class FA, class FB>
+__device__ __forceinline__ void tile_update(double* Cs, int m0, int mtiles, int n0, int ntiles, FA fa, FB fb,
+                                            bool lower) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, tq = lane & 3;
+    for (int mt = warp; mt < mtiles; mt += 8) {
+        double a[NB / 4];
+#pragma unroll
+        for (int kk = 0; kk < NB / 4; ++kk) a[kk] = fa(mt * 8 + g, kk * 4 + tq);
+        int ntl = ntiles;
+        if (lower) {
+            int lim = (m0 + mt * 8 - n0) / 8 + 1;   // tiles with n-tile start <= m-tile start
+            ntl = lim < ntiles ? lim : ntiles;
+        }
+        for (int nt0 = 0; nt0 < ntl; nt0 += 4) {
+            double c[4][2];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int nt = nt0 + u;
+                if (nt < ntl) {
+                    int n = n0 + nt * 8 + 2 * tq, m = m0 + mt * 8 + g;
+                    c[u][0] = -Cs[n * SC + m];
+                    c[u][1] = -Cs[(n + 1) * SC + m];
+                }
+            }
+#pragma unroll
+            for (int kk = 0; kk < NB / 4; ++kk) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    int nt = nt0 + u;
+                    if (nt < ntl) {
+                        double b = fb(kk * 4 + tq, nt * 8 + g);
+                        dmma(c[u][0], c[u][1], a[kk], b);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int nt = nt0 + u;
+                if (nt < ntl) {
+                    int n = n0 + nt * 8 + 2 * tq, m = m0 + mt * 8 + g;
+                    Cs[n * SC + m] = -c[u][0];
+                    Cs[(n + 1) * SC + m] = -c[u][1];
+                }
+            }
+        }
+    }
+}
+
+// ---- Cholesky of the 128x128 lower triangle held in Cs (in place).  sh_info: shared int, must be
+// 0 on entry; set to (local index + 1) of the first non-positive pivot.  The strict upper triangle
+// is left untouched (caller zeroes it on write-out).  invd[128] receives 1/L(c,c).
+__device__ inline void potrf_tile(double* Cs, double* invd, int* sh_info) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int o = 0; o < TILE; o += NB) {
+        // 1. 32x32 diagonal block, one warp, row per lane, registers + shuffles
+        if (warp == 0) {
+            double a[NB];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) a[c] = Cs[(o + c) * SC + o + lane];
+            bool failed = false;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                double dcc = __shfl_sync(0xffffffffu, a[c], c);
+                if (!(dcc > 0.0)) {   // also catches NaN
+                    if (!failed && lane == 0) atomicCAS(sh_info, 0, o + c + 1);
+                    failed = true;
+                    dcc = 1.0;
+                }
+                double d = sqrt(dcc);
+                double inv = 1.0 / d;
+                a[c] = (lane == c) ? d : a[c] * inv;
+                if (lane == c) invd[o + c] = inv;
+#pragma unroll
+                for (int c2 = c + 1; c2 < NB; ++c2) {
+                    double l2 = __shfl_sync(0xffffffffu, a[c], c2);
+                    a[c2] -= a[c] * l2;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < NB; ++c)
+                if (lane >= c) Cs[(o + c) * SC + o + lane] = a[c];
+        }
+        __syncthreads();
+        const int rest = TILE - o - NB;
+        if (rest == 0) break;
+        // 2. panel below: X = C * L^-T, one row per thread
+        if (tid < rest) {
+            const int r = o + NB + tid;
+            double x[NB];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) x[c] = Cs[(o + c) * SC + r];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                x[c] *= invd[o + c];
+#pragma unroll
+                for (int c2 = c + 1; c2 < NB; ++c2) x[c2] -= x[c] * Cs[(o + c) * SC + o + c2];
+            }
+#pragma unroll
+            for (int c = 0; c < NB; ++c) Cs[(o + c) * SC + r] = x[c];
+        }
+        __syncthreads();
+        // 3. trailing lower triangle -= P P^T
+        {
+            const double* P = Cs + o * SC + (o + NB);   // P(m,k) at P[k*SC + m]
+            tile_update(
+                Cs, o + NB, rest / 8, o + NB, rest / 8, [&](int m, int k) { return P[k * SC + m]; },
+                [&](int k, int n) { return P[k * SC + n]; }, true);
+        }
+        __syncthreads();
+    }
+}
+
+// Load columns [o, o+NB) of the lower-triangular 128x128 tile Lt (global, leading dim ld), rows
+// [o, 128), into Lp(k, m) = Lp[k * SC + m] (m absolute row in the tile) and the pivot reciprocals
+// of that block into invd[0..NB).
+__device__ __forceinline__ void load_col_panel(double* Lp, double* invd, const double* Lt, long ld, int o) {
+    const int rows = TILE - o;
+    for (int id = threadIdx.x; id < NB * rows; id += NTHREADS) {
+        int k = id / rows, m = o + id % rows;
+        Lp[k * SC + m] = ldcg(Lt + (long)(o + k) * ld + m);
+    }
+    if (threadIdx.x < NB) invd[threadIdx.x] = 1.0 / ldcg(Lt + (long)(o + threadIdx.x) * ld + o + threadIdx.x);
+}
+
+// Load rows [o, o+NB) of tile Lt, columns [0, o+NB), into Lr(c, k) = Lr[c * LRS + k], k = row - o.
+__device__ __forceinline__ void load_row_panel(double* Lr, double* invd, const double* Lt, long ld, int o) {
+    const int cols = o + NB;
+    for (int id = threadIdx.x; id < NB * cols; id += NTHREADS) {
+        int c = id / NB, k = id % NB;
+        Lr[c * LRS + k] = ldcg(Lt + (long)c * ld + o + k);
+    }
+    if (threadIdx.x < NB) invd[threadIdx.x] = 1.0 / ldcg(Lt + (long)(o + threadIdx.x) * ld + o + threadIdx.x);
+}
+
+// ---- X * Lt^T = C  (C: 128 x 128 in Cs, overwritten by X).  Rows are independent. -------------
+__device__ inline void trsm_right_tile(double* Cs, double* Lp, double* invd, const double* Lt, long ld) {
+    const int tid = threadIdx.x;
+    for (int o = 0; o < TILE; o += NB) {
+        load_col_panel(Lp, invd, Lt, ld, o);
+        __syncthreads();
+        if (tid < TILE) {
+            const int r = tid;
+            double x[NB];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) x[c] = Cs[(o + c) * SC + r];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                x[c] *= invd[c];
+#pragma unroll
+                for (int c2 = c + 1; c2 < NB; ++c2) x[c2] -= x[c] * Lp[c * SC + o + c2];
+            }
+#pragma unroll
+            for (int c = 0; c < NB; ++c) Cs[(o + c) * SC + r] = x[c];
+        }
+        __syncthreads();
+        const int rest = TILE - o - NB;
+        if (rest > 0) {
+            // C(:, n') -= X(:, o..o+NB) * L(n', o..o+NB)^T  for n' >= o+NB
+            const double* X = Cs + o * SC;
+            tile_update(
+                Cs, 0, TILE / 8, o + NB, rest / 8, [&](int m, int k) { return X[k * SC + m]; },
+                [&](int k, int n) { return Lp[k * SC + o + NB + n]; }, false);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- Lt * X = C  (forward; C: 128 x ncols in Cs, overwritten).  Columns are independent. -------
+__device__ inline void solve_fwd_tile(double* Cs, int ncols, double* Lp, double* invd, const double* Lt, long ld) {
+    const int tid = threadIdx.x;
+    for (int o = 0; o < TILE; o += NB) {
+        load_col_panel(Lp, invd, Lt, ld, o);
+        __syncthreads();
+        if (tid < ncols) {
+            double* col = Cs + tid * SC + o;
+            double x[NB];
+#pragma unroll
+            for (int r = 0; r < NB; ++r) x[r] = col[r];
+#pragma unroll
+            for (int r = 0; r < NB; ++r) {
+                x[r] *= invd[r];
+#pragma unroll
+                for (int r2 = r + 1; r2 < NB; ++r2) x[r2] -= x[r] * Lp[r * SC + o + r2];
+            }
+#pragma unroll
+            for (int r = 0; r < NB; ++r) col[r] = x[r];
+        }
+        __syncthreads();
+        const int rest = TILE - o - NB;
+        if (rest > 0) {
+            // C(m', :) -= L(m', o..o+NB) * X(o..o+NB, :)   for m' >= o+NB
+            tile_update(
+                Cs, o + NB, rest / 8, 0, ncols / 8, [&](int m, int k) { return Lp[k * SC + o + NB + m]; },
+                [&](int k, int n) { return Cs[n * SC + o + k]; }, false);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- Lt^T * X = C  (backward with the transposed lower tile). -----------------------------------
+__device__ inline void solve_bwd_tile(double* Cs, int ncols, double* Lr, double* invd, const double* Lt, long ld) {
+    const int tid = threadIdx.x;
+    for (int o = TILE - NB; o >= 0; o -= NB) {
+        load_row_panel(Lr, invd, Lt, ld, o);
+        __syncthreads();
+        if (tid < ncols) {
+            double* col = Cs + tid * SC + o;
+            double x[NB];
+#pragma unroll
+            for (int r = 0; r < NB; ++r) x[r] = col[r];
+#pragma unroll
+            for (int r = NB - 1; r >= 0; --r) {
+                x[r] *= invd[r];
+#pragma unroll
+                for (int r2 = 0; r2 < r; ++r2) x[r2] -= x[r] * Lr[(o + r2) * LRS + r];
+            }
+#pragma unroll
+            for (int r = 0; r < NB; ++r) col[r] = x[r];
+        }
+        __syncthreads();
+        if (o > 0) {
+            // C(m', :) -= L(o..o+NB, m')^T * X(o..o+NB, :)   for m' < o
+            tile_update(
+                Cs, 0, o / 8, 0, ncols / 8, [&](int m, int k) { return Lr[m * LRS + k]; },
+                [&](int k, int n) { return Cs[n * SC + o + k]; }, false);
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace geordd

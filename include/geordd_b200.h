@@ -1,0 +1,195 @@
+/* geordd_b200.h -- C ABI of libgeordd_b200.so: the B200-native (sm_100a) implementation of the
+ * GeoRDD.jl data-parallel hot path.
+ *
+ * The reference (maximerischard/GeoRDD.jl) has no FFI boundary: the hot path is ordinary Julia
+ * calls into GaussianProcesses.jl / PDMats / LinearAlgebra.  This header is the boundary the
+ * reference-side wrappers `ccall` into (see INTEGRATION.md and julia/GeoRDDB200.jl); each entry
+ * point cites the reference function whose body it replaces.
+ *
+ * Conventions
+ *   - All array arguments are caller-owned HOST memory, FP64, column-major (Julia layout):
+ *     coordinates are dim x n (unit i = column i), sentinels 2 x nb, D is p x n.
+ *     The library copies in/out and never retains a host pointer after return.
+ *   - Device state lives in opaque handles freed by the matching *_destroy.
+ *   - Return value: 0 ok; > 0 LAPACK-style index of the first non-positive pivot once the
+ *     make_posdef! jitter budget (10 rounds) is exhausted (wrapper throws PosDefException(info),
+ *     keeping src/GPrealisationsCovars.jl:239-241,261-263 working); < 0 argument / CUDA error, text
+ *     from geordd_last_error().
+ *   - One context = one GPU = one CUDA stream; a context is not re-entrant.  Multi-GPU runs use one
+ *     process (context) per GPU; null draws are sharded by draw index (`draw0`), results depend only
+ *     on (seed, draw index) and the integer tallies are summed by the caller (NCCL all-reduce).
+ *   - There is NO CPU fallback: every entry point fails with GEORDD_ERR_CUDA if no sm_100 device
+ *     is usable.
+ */
+#ifndef GEORDD_B200_H
+#define GEORDD_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GEORDD_API __attribute__((visibility("default")))
+#else
+#define GEORDD_API
+#endif
+
+#define GEORDD_ERR_ARG (-1)
+#define GEORDD_ERR_CUDA (-2)
+#define GEORDD_ERR_WATCHDOG (-3)
+#define GEORDD_ERR_NOMEM (-4)
+
+typedef struct geordd_ctx geordd_ctx;
+typedef struct geordd_gp geordd_gp;
+typedef struct geordd_null geordd_null;
+typedef struct geordd_multigp geordd_multigp;
+
+/* Isotropic spatial kernel (+ optional Const kernel) and constant mean.
+ * kind: 0 SEIso, 1 Mat12Iso, 2 Mat32Iso, 3 Mat52Iso (GaussianProcesses.jl kernels);
+ * ell: length scale (sqrt(l2) for SEIso); sigma2: signal variance;
+ * const_sigma2: variance of a summed Const kernel (0 = none); mean_const: MeanConst (0 = MeanZero). */
+typedef struct {
+    int kind;
+    double ell, sigma2, const_sigma2, mean_const;
+} geordd_kernel;
+
+GEORDD_API int geordd_version(void);
+
+/* ---- context ------------------------------------------------------------------------------- */
+GEORDD_API int geordd_ctx_create(geordd_ctx** out, int device);
+GEORDD_API int geordd_ctx_destroy(geordd_ctx* ctx);
+GEORDD_API const char* geordd_last_error(const geordd_ctx* ctx);
+/* Run all work of this context on an existing CUDA stream (e.g. the caller's current torch stream)
+ * so that the caller's CUDA events bracket it.  NULL restores the context's own stream. */
+GEORDD_API int geordd_ctx_set_stream(geordd_ctx* ctx, void* cuda_stream);
+GEORDD_API int geordd_ctx_sync(geordd_ctx* ctx);
+/* Per-kernel-class CUDA-event timing (on the launching stream).  enable != 0 starts/clears it.
+ * geordd_ctx_profile_get returns accumulated milliseconds and launch count for a kernel class
+ * ("cov", "potrf", "solve_fwd", "solve_bwd", "trmm", "gemm", "rng", "finish", "lu", "misc"),
+ * or for "*" the total over all classes. */
+GEORDD_API int geordd_ctx_profile(geordd_ctx* ctx, int enable);
+GEORDD_API int geordd_ctx_profile_get(geordd_ctx* ctx, const char* name, double* ms, long long* launches);
+/* Upper bound on null draws processed per internal batch (0 = automatic). */
+GEORDD_API int geordd_ctx_set_max_batch(geordd_ctx* ctx, long max_batch);
+
+/* ---- K1 covariance assembly: cov(kernel, X, X) + diag_add*I and cov(kernel, X1, X2) ----------
+ * replaces GaussianProcesses.cov / cov! (call sites src/hypotest_chi2.jl:38-39, src/power.jl:60-62,
+ * src/hypotest_invvar.jl:80-86) and addcov!/add_diag! (src/gp_utils.jl:24-44).  K: n x n / n1 x n2. */
+GEORDD_API int geordd_cov_sym(geordd_ctx* ctx, const geordd_kernel* k, const double* X, int dim, int n, double diag_add,
+                   double* K);
+GEORDD_API int geordd_cov_cross(geordd_ctx* ctx, const geordd_kernel* k, const double* X1, int n1, const double* X2, int n2,
+                     int dim, double* K);
+
+/* ---- a1: GPE(x, y, mean, kernel, logNoise) (src/region_gp_fit.jl:12,28; src/hypotest.jl:4) ----
+ * K = k(X,X) + (exp(2 logNoise) + eps) I; make_posdef! (jitter retries); alpha = K \ (y - m);
+ * mll (src/gp_utils.jl:19-22).  alpha (n), mll (1), cholU (n x n upper factor, nullable),
+ * jitter_rounds (nullable) are outputs. */
+GEORDD_API int geordd_gp_fit(geordd_ctx* ctx, const geordd_kernel* k, const double* X, int dim, int n, const double* y,
+                  double log_noise, geordd_gp** out, double* alpha, double* mll, double* cholU, int* jitter_rounds);
+/* a9: gp.y = y; update_alpha!(gp); mll(gp) with the frozen factor (src/gp_utils.jl:15-22). */
+GEORDD_API int geordd_gp_set_y(geordd_gp* gp, const double* y, double* alpha, double* mll);
+/* predict_mu(gp, Xb, cK) = m(Xb) + cov(kernel, Xb, gp.x) * alpha (src/gp_utils.jl:1-5). */
+GEORDD_API int geordd_gp_predict_mu(geordd_gp* gp, const double* Xb, int nb, double* mu);
+/* cK.mat (jittered covariance incl. noise), n x n. */
+GEORDD_API int geordd_gp_get_K(geordd_gp* gp, double* K);
+GEORDD_API int geordd_gp_nobs(const geordd_gp* gp);
+GEORDD_API int geordd_gp_destroy(geordd_gp* gp);
+
+/* ---- a7: cliff_face(gpT, gpC, sentinels) (src/cliff_face.jl:3-9): mu (nb), Sigma (nb x nb) ---- */
+GEORDD_API int geordd_cliff_face(geordd_gp* T, geordd_gp* C, const double* Xb, int nb, double* mu, double* Sigma);
+
+/* ---- a11 (LATE): inverse_variance(mu, Sigma; nugget) (src/average_treatment_effect.jl:3-11),
+ * Sigma a plain Matrix => + nugget*I and LU solves.  Also unweighted/weighted means (:13-29). */
+GEORDD_API int geordd_inverse_variance(geordd_ctx* ctx, const double* mu, const double* Sigma, int nb, double nugget,
+                            double* tau_hat, double* var_tau);
+/* weight_at_units(gp, sentinels, weights) (src/weight_at_units.jl:12-18): w_unit (n). */
+GEORDD_API int geordd_weight_at_units(geordd_gp* gp, const double* Xb, int nb, const double* w_border, double* w_unit);
+
+/* ---- observed statistics (LU on the raw cliff-face covariance) --------------------------------
+ * chistat(gpT,gpC,Xb) (src/hypotest_chi2.jl:4-10); pval_invvar_uncalib(gpT,gpC,Xb;nugget)
+ * (src/hypotest_invvar.jl:1-6); pval_invvar_calib(gpT,gpC,Xb;nugget) (src/hypotest_invvar.jl:74-105). */
+GEORDD_API int geordd_chistat_obs(geordd_gp* T, geordd_gp* C, const double* Xb, int nb, double* chi2);
+GEORDD_API int geordd_invvar_obs(geordd_gp* T, geordd_gp* C, const double* Xb, int nb, double nugget, double* tau_hat,
+                      double* var_tau, double* pval);
+GEORDD_API int geordd_invvar_calib(geordd_gp* T, geordd_gp* C, const double* Xb, int nb, double nugget, double* pval);
+
+/* ---- a8/a10/a11/a13/a14: Monte-Carlo sharp-null machinery -------------------------------------
+ * geordd_null_prepare = the draw-independent setup of nsim_chi (src/hypotest_chi2.jl:33-48),
+ * nsim_invvar_pval_uncalib (src/hypotest_invvar.jl:48-59) and nsim_power (src/power.jl:53-66):
+ * make_null (pooled fit, src/hypotest.jl:1-12), cliff face, make_posdef!(Sigma + nugget I),
+ * cK_T/cK_C = cov(kernel, Xb, gp.x).  Xb may be NULL with nb = 0 for the mll test alone.
+ * T and C must outlive the handle.
+ *
+ * Draws: Z == NULL  -> device Philox-4x32-10 / Box-Muller normals keyed by (seed, draw0 + s, element);
+ *        Z != NULL  -> host normals, n x nsim column-major, column s = the randn(n) of draw s
+ *                      (exactly the order rand(MvNormal) consumes them, src/hypotest.jl:13-18).
+ * Every draw: y = m + L_N z (prior_rand); alpha_T, alpha_C (update_alpha!); statistic. */
+GEORDD_API int geordd_null_prepare(geordd_gp* T, geordd_gp* C, const double* Xb, int nb, double nugget, geordd_null** out,
+                        int* jitter_rounds, double* mll_null);
+/* Re-run only the sentinel-dependent part of the setup on an existing handle (new Xb and/or nugget). */
+GEORDD_API int geordd_null_set_sentinels(geordd_null* h, const double* Xb, int nb, double nugget, int* jitter_rounds);
+/* Borrow the pooled null GP (make_null result; owned by the handle). */
+GEORDD_API int geordd_null_gp(geordd_null* h, geordd_gp** gp);
+/* a8: prior_rand(gp) for nsim draws (src/hypotest.jl:13-18): Y (n x nsim) = m + L z. Z as below. */
+GEORDD_API int geordd_gp_prior_rand(geordd_gp* gp, long nsim, unsigned long long seed, unsigned long long draw0,
+                         const double* Z, double* Y);
+/* nsim_chi / boot_chi2test (src/hypotest_chi2.jl:19-59): stats (nsim, nullable), n_exceed = #{chi > chi_obs}. */
+GEORDD_API int geordd_null_chi2(geordd_null* h, long nsim, unsigned long long seed, unsigned long long draw0, const double* Z,
+                     double chi_obs, double* stats, long long* n_exceed);
+/* nsim_invvar_pval_uncalib / boot_invvar (src/hypotest_invvar.jl:11-69): pvals, n_below = #{p < pval_obs}. */
+GEORDD_API int geordd_null_invvar(geordd_null* h, long nsim, unsigned long long seed, unsigned long long draw0, const double* Z,
+                       double pval_obs, double* pvals, long long* n_below);
+/* sim_logP! / nsim_logP / boot_mlltest (src/hypotest_mll.jl:1-45): mll_null, mll_alt (nsim, nullable),
+ * n_exceed = #{(alt - null) > dmll_obs}.  last_y / last_alpha (n, nullable) receive the pooled GP's y and
+ * alpha after the final draw (the reference mutates gpNull, src/hypotest_mll.jl:6,10,14). */
+GEORDD_API int geordd_null_mll(geordd_null* h, long nsim, unsigned long long seed, unsigned long long draw0, const double* Z,
+                    double dmll_obs, double* mll_null, double* mll_alt, long long* n_exceed, double* last_y,
+                    double* last_alpha);
+/* All three statistics from the same draws in one pass (used by power.jl-style studies and the bench). */
+GEORDD_API int geordd_null_all(geordd_null* h, long nsim, unsigned long long seed, unsigned long long draw0, const double* Z,
+                    double tau, double* chi, double* pvals, double* mll_null, double* mll_alt);
+/* nsim_power (src/power.jl:1-73): out5 is 5 x nsim column-major: (pval_mll, pval_chi2, pval_invvar_obs,
+ * invvar_bootcalib, invvar_calib) per draw.  compat_calib_bug != 0 reproduces the as-shipped
+ * 7-argument pval_invvar_calib (missing '+', src/hypotest_invvar.jl:125-128). */
+GEORDD_API int geordd_power(geordd_null* h, double tau, long nsim, unsigned long long seed, unsigned long long draw0,
+                 const double* Z, const double* chi_null, const double* mll_null, const double* pinv_null, long nnull,
+                 int compat_calib_bug, double* out5);
+GEORDD_API int geordd_null_destroy(geordd_null* h);
+
+/* ---- a3/a4/a5: MultiGPCovars numerics (src/GPrealisationsCovars.jl) ---------------------------
+ * create: uploads D (p x n), X (dim x n, groups contiguous), group offsets (ngroups+1), y; builds
+ * D'D once (KernelData(LinIso, D, D), :42).  mll = update_mll! (:110-125): cK = D'D/lin_ell2 +
+ * blockdiag(K_g) + max(exp(2 logNoise),1e-8) I -> make_posdef! -> alpha -> mll.
+ * mll_grad = update_mll_and_dmll! (:145-193); dmll order [logNoise][mean][log ell, log sigma,
+ * (log sigma_const)][LinIso ll], entries selected by the noise/domean/kern/beta flags.
+ * postmean_beta = postmean_beta (:335-344). */
+GEORDD_API int geordd_multigp_create(geordd_ctx* ctx, const double* D, int p, const double* X, int dim, const int* group_off,
+                          int ngroups, const double* y, geordd_multigp** out);
+GEORDD_API int geordd_multigp_mll(geordd_multigp* h, const geordd_kernel* k, double lin_ell2, double log_noise, double* alpha,
+                       double* mll, int* jitter_rounds);
+GEORDD_API int geordd_multigp_mll_grad(geordd_multigp* h, const geordd_kernel* k, double lin_ell2, double log_noise, int noise,
+                            int domean, int kern, int beta, double* mll, double* dmll, int* ndmll);
+GEORDD_API int geordd_multigp_postmean_beta(geordd_multigp* h, const geordd_kernel* k, double lin_ell2, double log_noise,
+                                 double* beta_hat);
+GEORDD_API int geordd_multigp_destroy(geordd_multigp* h);
+
+/* ---- debug / test hooks (not part of the reference-facing surface) -----------------------------
+ * Device Philox normals copied to the host: Z is n x ndraws. */
+GEORDD_API int geordd_dbg_normals(geordd_ctx* ctx, unsigned long long seed, unsigned long long draw0, int ndraws, int n,
+                       double* Z);
+/* C = alpha*op(A)*op(B) + beta*C through the DMMA mainloop (host matrices, column-major). transa/transb:
+ * 0 = as stored, 1 = transposed. */
+GEORDD_API int geordd_dbg_gemm(geordd_ctx* ctx, int transa, int transb, int M, int N, int K, double alpha, const double* A,
+                    int lda, const double* B, int ldb, double beta, double* C, int ldc, int splitk);
+/* Cholesky of a host SPD matrix (n x n) through the dataflow kernel: L lower, returns info. */
+GEORDD_API int geordd_dbg_potrf(geordd_ctx* ctx, const double* A, int n, double* L, double* ms);
+/* Triangular ops with a host lower factor: mode 0 B <- L^-1 B, 1 B <- L^-T B, 2 B <- L B. */
+GEORDD_API int geordd_dbg_trsm(geordd_ctx* ctx, int mode, const double* L, int n, double* B, int nrhs, double* ms);
+/* Device-resident micro-benchmarks (synthetic SPD matrix built on device): times in ms. */
+GEORDD_API int geordd_bench_potrf(geordd_ctx* ctx, int n, int reps, double* ms_best, double* ms_mean);
+GEORDD_API int geordd_bench_dmma_peak(geordd_ctx* ctx, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEORDD_B200_H */
