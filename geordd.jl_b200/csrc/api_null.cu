@@ -495,6 +495,32 @@ int geordd_inverse_variance(geordd_ctx* c, const double* mu, const double* Sigma
     API_END
 }
 
+int geordd_solve_general(geordd_ctx* c, const double* A, int n, double* B, int nrhs) {
+    API_BEGIN(c)
+    if (!A || !B || n <= 0 || nrhs <= 0) throw ApiError(GEORDD_ERR_ARG, "solve_general: bad arguments");
+    double* dA = dalloc((size_t)n * n, c->stream, false);
+    double* dB = nullptr;
+    try {
+        dB = dalloc((size_t)n * nrhs, c->stream, false);
+        GD_CUDA(cudaMemcpyAsync(dA, A, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        GD_CUDA(cudaMemcpyAsync(dB, B, (size_t)n * nrhs * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        {
+            ProfScope ps(c, PC_LU);
+            launch_lu_solve(c->stream, dA, n, n, dB, n, nrhs, c->d_info);
+        }
+        GD_CUDA(cudaMemcpyAsync(B, dB, (size_t)n * nrhs * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        GD_CUDA(cudaMemcpyAsync(c->h_info + 1, c->d_info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        GD_CUDA(cudaStreamSynchronize(c->stream));
+        GD_CUDA(cudaGetLastError());
+        if (c->h_info[1] != 0) throw ApiError(GEORDD_ERR_ARG, "solve_general: matrix is singular");   // SingularException
+    } catch (...) {
+        cudaFree(dA); cudaFree(dB);
+        throw;
+    }
+    cudaFree(dA); cudaFree(dB);
+    API_END
+}
+
 int geordd_weight_at_units(geordd_gp* gp, const double* Xb, int nb, const double* w_border, double* w_unit) {
     if (!gp) return GEORDD_ERR_ARG;
     API_BEGIN(gp->ctx)

@@ -1,0 +1,965 @@
+"""Host-side mirror of the GeoRDD.jl entry points on the hot path (same names, argument meaning and
+error behaviour as the Julia package), calling libgeordd_b200.so through the C ABI.
+
+Julia is not available in this environment, so this module plays the role of the thin Julia wrappers
+(julia/GeoRDDB200.jl shows the `ccall` twin): it pattern-matches GaussianProcesses.jl-style kernel
+objects into the `geordd_kernel` POD, keeps host arrays alive across the call, converts status codes
+into exceptions (`PosDefException`, `ArgumentError` -> ValueError) and owns the device handles.
+
+All numerics run on the GPU.  Nothing here falls back to NumPy: if the library cannot be loaded or
+no B200 is present the constructors raise.
+
+Reference citations are to /root/reference (GeoRDD.jl v0.2.0).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Dict, Hashable, Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from . import capi
+from .capi import GeorddError, Kernel as _CKernel, PosDefException, dptr, fmat
+
+
+# ----------------------------------------------------------------------------------------------
+# GaussianProcesses.jl-style kernel / mean objects (parameterisation: SURVEY App. A.1)
+# ----------------------------------------------------------------------------------------------
+class KernelBase:
+    def __add__(self, other):
+        return SumKernel(self, other)
+
+
+@dataclass
+class SEIso(KernelBase):
+    ll: float
+    lsigma: float
+
+    @property
+    def ell2(self):  # field name in GaussianProcesses: l2
+        return math.exp(2.0 * self.ll)
+
+    @property
+    def sigma2(self):
+        return math.exp(2.0 * self.lsigma)
+
+
+@dataclass
+class _MatIso(KernelBase):
+    ll: float
+    lsigma: float
+
+    @property
+    def ell(self):
+        return math.exp(self.ll)
+
+    @property
+    def sigma2(self):
+        return math.exp(2.0 * self.lsigma)
+
+
+class Mat12Iso(_MatIso):
+    pass
+
+
+class Mat32Iso(_MatIso):
+    pass
+
+
+class Mat52Iso(_MatIso):
+    pass
+
+
+@dataclass
+class Const(KernelBase):
+    lsigma: float
+
+    @property
+    def sigma2(self):
+        return math.exp(2.0 * self.lsigma)
+
+
+@dataclass
+class LinIso(KernelBase):
+    ll: float
+
+    @property
+    def ell2(self):
+        return math.exp(2.0 * self.ll)
+
+
+@dataclass
+class SumKernel(KernelBase):
+    kleft: KernelBase
+    kright: KernelBase
+
+
+@dataclass
+class FixedKernel(KernelBase):
+    kernel: KernelBase
+
+
+def fix(k):
+    """GaussianProcesses.fix(k): same values, parameters hidden from get_params."""
+    return FixedKernel(k)
+
+
+@dataclass
+class MeanZero:
+    pass
+
+
+@dataclass
+class MeanConst:
+    beta: float
+
+
+_KIND = {SEIso: 0, Mat12Iso: 1, Mat32Iso: 2, Mat52Iso: 3}
+
+
+def _unfix(k):
+    return k.kernel if isinstance(k, FixedKernel) else k
+
+
+def kernel_spec(kernel, mean=None) -> _CKernel:
+    """Pattern-match SEIso / MatXXIso / SumKernel(spatial, Const) (+ fix) and MeanZero / MeanConst into the
+    ABI struct; anything else is an ArgumentError (no fallback, BASELINE north_star)."""
+    k = _unfix(kernel)
+    const_s2 = 0.0
+    if isinstance(k, SumKernel):
+        a, b = _unfix(k.kleft), _unfix(k.kright)
+        if isinstance(a, Const):
+            a, b = b, a
+        if not isinstance(b, Const) or type(a) not in _KIND:
+            raise ValueError("ArgumentError: only SEIso/Mat12Iso/Mat32Iso/Mat52Iso (+ Const) kernels are supported")
+        const_s2 = b.sigma2
+        k = a
+    if type(k) not in _KIND:
+        raise ValueError("ArgumentError: only SEIso/Mat12Iso/Mat32Iso/Mat52Iso (+ Const) kernels are supported")
+    ell = math.sqrt(k.ell2) if isinstance(k, SEIso) else k.ell
+    if mean is None or isinstance(mean, MeanZero):
+        mc = 0.0
+    elif isinstance(mean, MeanConst):
+        mc = float(mean.beta)
+    else:
+        raise ValueError("ArgumentError: only MeanZero / MeanConst are supported")
+    return _CKernel(_KIND[type(k)], ell, k.sigma2, const_s2, mc)
+
+
+def get_params(kernel) -> List[float]:
+    """get_params order of GaussianProcesses kernels: [log ell, log sigma] (+ [log sigma_const])."""
+    if isinstance(kernel, FixedKernel):
+        return []
+    if isinstance(kernel, SumKernel):
+        return get_params(kernel.kleft) + get_params(kernel.kright)
+    if isinstance(kernel, (SEIso, _MatIso)):
+        return [kernel.ll, kernel.lsigma]
+    if isinstance(kernel, Const):
+        return [kernel.lsigma]
+    if isinstance(kernel, LinIso):
+        return [kernel.ll]
+    raise ValueError("unsupported kernel")
+
+
+def set_params(kernel, hyp: Sequence[float]) -> None:
+    if isinstance(kernel, FixedKernel):
+        return
+    if isinstance(kernel, SumKernel):
+        nl = len(get_params(kernel.kleft))
+        set_params(kernel.kleft, hyp[:nl])
+        set_params(kernel.kright, hyp[nl:])
+    elif isinstance(kernel, (SEIso, _MatIso)):
+        kernel.ll, kernel.lsigma = float(hyp[0]), float(hyp[1])
+    elif isinstance(kernel, Const):
+        kernel.lsigma = float(hyp[0])
+    elif isinstance(kernel, LinIso):
+        kernel.ll = float(hyp[0])
+
+
+# ----------------------------------------------------------------------------------------------
+# Context
+# ----------------------------------------------------------------------------------------------
+class Context:
+    """One GPU, one stream (geordd_ctx).  Raises if no B200-class device / library is available."""
+
+    def __init__(self, device: int = 0):
+        self.lib = capi.load_library()
+        self._h = C.c_void_p()
+        rc = self.lib.geordd_ctx_create(C.byref(self._h), int(device))
+        if rc != 0:
+            raise GeorddError(rc, "no usable sm_100 CUDA device (this package has no CPU fallback)")
+        self.device = device
+
+    def check(self, rc: int) -> None:
+        if rc == 0:
+            return
+        msg = self.lib.geordd_last_error(self._h).decode()
+        if rc > 0:
+            raise PosDefException(rc, msg)
+        if rc == capi_ERR_ARG:
+            raise ValueError("ArgumentError: " + msg)
+        raise GeorddError(rc, msg)
+
+    def set_stream(self, cuda_stream: Optional[int]) -> None:
+        self.check(self.lib.geordd_ctx_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def sync(self) -> None:
+        self.check(self.lib.geordd_ctx_sync(self._h))
+
+    def set_max_batch(self, n: int) -> None:
+        self.check(self.lib.geordd_ctx_set_max_batch(self._h, int(n)))
+
+    def profile(self, enable: bool) -> None:
+        self.check(self.lib.geordd_ctx_profile(self._h, 1 if enable else 0))
+
+    def profile_get(self, name: str = "*"):
+        ms, n = C.c_double(), C.c_longlong()
+        self.check(self.lib.geordd_ctx_profile_get(self._h, name.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def dmma_peak_tflops(self) -> float:
+        t = C.c_double()
+        self.check(self.lib.geordd_bench_dmma_peak(self._h, C.byref(t)))
+        return t.value
+
+    def bench_potrf(self, n: int, reps: int = 3):
+        b, m = C.c_double(), C.c_double()
+        self.check(self.lib.geordd_bench_potrf(self._h, int(n), int(reps), C.byref(b), C.byref(m)))
+        return b.value, m.value
+
+    def close(self):
+        if self._h:
+            self.lib.geordd_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+capi_ERR_ARG = -1
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        import os
+        _default_ctx = Context(int(os.environ.get("GEORDD_DEVICE", os.environ.get("LOCAL_RANK", "0"))))
+    return _default_ctx
+
+
+# ----------------------------------------------------------------------------------------------
+# Covariance assembly (K1)
+# ----------------------------------------------------------------------------------------------
+def cov(kernel, X1, X2=None, *, diag_add: float = 0.0, ctx: Optional[Context] = None) -> np.ndarray:
+    """cov(kernel, X1, X2) / cov(kernel, X) of GaussianProcesses (call sites src/hypotest_chi2.jl:38-39)."""
+    ctx = ctx or default_context()
+    spec = kernel_spec(kernel)
+    X1 = fmat(X1)
+    if X2 is None:
+        n = X1.shape[1]
+        K = np.empty((n, n), order="F")
+        ctx.check(ctx.lib.geordd_cov_sym(ctx._h, C.byref(spec), dptr(X1), X1.shape[0], n, float(diag_add), dptr(K)))
+        return K
+    X2 = fmat(X2)
+    K = np.empty((X1.shape[1], X2.shape[1]), order="F")
+    ctx.check(ctx.lib.geordd_cov_cross(ctx._h, C.byref(spec), dptr(X1), X1.shape[1], dptr(X2), X2.shape[1], X1.shape[0],
+                                       dptr(K)))
+    return K
+
+
+# ----------------------------------------------------------------------------------------------
+# GPE
+# ----------------------------------------------------------------------------------------------
+class Normal:
+    """Distributions.Normal(mu, sigma) with the cdf/ccdf/quantile GeoRDD uses."""
+
+    def __init__(self, mu: float, sigma: float):
+        self.mu, self.sigma = float(mu), float(sigma)
+
+    def cdf(self, x):
+        return math.erfc(-((x - self.mu) / self.sigma) * 0.7071067811865476) / 2.0
+
+    def ccdf(self, x):
+        return math.erfc(((x - self.mu) / self.sigma) * 0.7071067811865476) / 2.0
+
+    def quantile(self, p):
+        from scipy.special import erfcinv
+        return self.mu - self.sigma * math.sqrt(2.0) * float(erfcinv(2.0 * p))
+
+    def __repr__(self):
+        return f"Normal(mu={self.mu}, sigma={self.sigma})"
+
+
+class GPE:
+    """GPE(x, y, mean, kernel, logNoise) as GeoRDD constructs it (src/region_gp_fit.jl:3,12,28;
+    src/hypotest.jl:4): assembles K + (exp(2 logNoise) + eps) I, make_posdef!, alpha, mll -- on the GPU."""
+
+    def __init__(self, x, y, mean, kernel, logNoise: float, ctx: Optional[Context] = None, want_chol: bool = False):
+        self.ctx = ctx or default_context()
+        self.x = fmat(x)
+        self.y = np.array(y, dtype=np.float64)
+        self.mean, self.kernel, self.logNoise = mean, kernel, float(logNoise)
+        self.dim, self.nobs = self.x.shape
+        if self.y.shape[0] != self.nobs:
+            raise ValueError("ArgumentError: x and y have incompatible sizes")
+        spec = kernel_spec(kernel, mean)
+        self._h = C.c_void_p()
+        self.alpha = np.empty(self.nobs)
+        mll, jr = C.c_double(), C.c_int()
+        self.cholU = np.empty((self.nobs, self.nobs), order="F") if want_chol else None
+        rc = self.ctx.lib.geordd_gp_fit(self.ctx._h, C.byref(spec), dptr(self.x), self.dim, self.nobs, dptr(self.y),
+                                        self.logNoise, C.byref(self._h), dptr(self.alpha), C.byref(mll), dptr(self.cholU),
+                                        C.byref(jr))
+        self.ctx.check(rc)
+        self.mll = mll.value
+        self.jitter_rounds = jr.value
+
+    # GeoRDD.GPE(rd::RegionData, args...) (src/region_gp_fit.jl:3)
+    @classmethod
+    def from_region(cls, rd: "RegionData", mean, kernel, logNoise, **kw):
+        return cls(rd.x, rd.y, mean, kernel, logNoise, **kw)
+
+    def cK_mat(self) -> np.ndarray:
+        K = np.empty((self.nobs, self.nobs), order="F")
+        self.ctx.check(self.ctx.lib.geordd_gp_get_K(self._h, dptr(K)))
+        return K
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h:
+            self.ctx.lib.geordd_gp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def update_alpha(gp: GPE) -> None:
+    """update_alpha!(gp) (src/gp_utils.jl:15-18) -- also refreshes gp.mll like mll(gp) (:19-22)."""
+    mll = C.c_double()
+    gp.ctx.check(gp.ctx.lib.geordd_gp_set_y(gp._h, dptr(gp.y), dptr(gp.alpha), C.byref(mll)))
+    gp.mll = mll.value
+
+
+def mll(gp: GPE) -> float:
+    """mll(gp) (src/gp_utils.jl:19-22) for the current gp.y / gp.alpha."""
+    return gp.mll
+
+
+def modifiable(gp: GPE) -> GPE:
+    """modifiable(gp) (src/gp_utils.jl:10-14): a copy whose y may be changed.  The 8-argument GPE
+    constructor re-initialises (re-factors) the shared cK; so does this."""
+    return GPE(gp.x, gp.y.copy(), gp.mean, gp.kernel, gp.logNoise, ctx=gp.ctx)
+
+
+def predict_mu(gp: GPE, X, cK=None) -> np.ndarray:
+    """predict_mu(gp, X, cK) = mean(gp.mean, X) + cK*gp.alpha (src/gp_utils.jl:1-5); cK is recomputed on the
+    device from (kernel, X, gp.x), the argument is accepted for signature compatibility."""
+    X = fmat(X)
+    mu = np.empty(X.shape[1])
+    gp.ctx.check(gp.ctx.lib.geordd_gp_predict_mu(gp._h, dptr(X), X.shape[1], dptr(mu)))
+    return mu
+
+
+def prior_rand(gp: GPE, nsim: int = 1, *, seed: int = 0, draw0: int = 0, Z=None) -> np.ndarray:
+    """prior_rand(gp) (src/hypotest.jl:13-18) for nsim draws: columns of m + L z."""
+    Zf = fmat(Z) if Z is not None else None
+    if Zf is not None:
+        nsim = Zf.shape[1] if Zf.ndim == 2 else 1
+    Y = np.empty((gp.nobs, nsim), order="F")
+    gp.ctx.check(gp.ctx.lib.geordd_gp_prior_rand(gp._h, nsim, seed, draw0, dptr(Zf), dptr(Y)))
+    return Y
+
+
+# ----------------------------------------------------------------------------------------------
+# cliff face and LATE reducers
+# ----------------------------------------------------------------------------------------------
+def cliff_face(gpT: GPE, gpC: GPE, sentinels):
+    """cliff_face(gpT, gpC, sentinels) -> (mu_posterior, Sigma_posterior) (src/cliff_face.jl:3-9)."""
+    Xb = fmat(sentinels)
+    nb = Xb.shape[1]
+    mu, S = np.empty(nb), np.empty((nb, nb), order="F")
+    gpT.ctx.check(gpT.ctx.lib.geordd_cliff_face(gpT._h, gpC._h, dptr(Xb), nb, dptr(mu), dptr(S)))
+    return mu, S
+
+
+def add_nugget(A, nugget):
+    """src/average_treatment_effect.jl:1-2."""
+    return A + nugget * np.eye(A.shape[0])
+
+
+def inverse_variance(mu, Sigma, nugget: float = 1e-10, ctx: Optional[Context] = None) -> Normal:
+    """inverse_variance(mu, Sigma; nugget) (src/average_treatment_effect.jl:3-11)."""
+    ctx = ctx or default_context()
+    mu = np.ascontiguousarray(mu, dtype=np.float64)
+    S = fmat(Sigma)
+    tau, var = C.c_double(), C.c_double()
+    ctx.check(ctx.lib.geordd_inverse_variance(ctx._h, dptr(mu), dptr(S), mu.shape[0], float(nugget), C.byref(tau),
+                                              C.byref(var)))
+    return Normal(tau.value, math.sqrt(var.value))
+
+
+def unweighted_mean(mu, Sigma) -> Normal:
+    """src/average_treatment_effect.jl:13-22 (O(nb^2) host reduction of an nb x nb result)."""
+    n = len(mu)
+    return Normal(float(np.mean(mu)), math.sqrt(float(np.sum(Sigma)) / n ** 2))
+
+
+def weighted_mean(mu, Sigma, w) -> Normal:
+    """src/average_treatment_effect.jl:24-29."""
+    w = np.asarray(w, dtype=np.float64)
+    sw = float(np.sum(w))
+    return Normal(float(np.sum(mu * w)) / sw, math.sqrt(float(w @ (np.asarray(Sigma) @ w)) / sw ** 2))
+
+
+def weight_at_units(gp: GPE, sentinels, weights) -> np.ndarray:
+    """weight_at_units(gp, sentinels, weights) (src/weight_at_units.jl:12-18)."""
+    Xb = fmat(sentinels)
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    assert Xb.shape[1] == w.shape[0]
+    out = np.empty(gp.nobs)
+    gp.ctx.check(gp.ctx.lib.geordd_weight_at_units(gp._h, dptr(Xb), Xb.shape[1], dptr(w), dptr(out)))
+    return out
+
+
+def weights_unif(gpT: GPE, gpC: GPE, Xb):
+    """weights_unif with the sentinels already placed (src/weight_at_units.jl:23-28)."""
+    nb = np.asarray(Xb).shape[1]
+    wb = np.ones(nb)
+    return Xb, wb, np.concatenate([weight_at_units(gpT, Xb, wb), -weight_at_units(gpC, Xb, wb)])
+
+
+def generic_solve(A, B, ctx: Optional[Context] = None) -> np.ndarray:
+    """Julia's `A \\ B` on a square dense Matrix (lu with partial pivoting) on the device."""
+    ctx = ctx or default_context()
+    A = fmat(np.array(A, dtype=np.float64))
+    Bm = fmat(np.array(B, dtype=np.float64).reshape(A.shape[0], -1))
+    ctx.check(ctx.lib.geordd_solve_general(ctx._h, dptr(A), A.shape[0], dptr(Bm), Bm.shape[1]))
+    return Bm.reshape(np.shape(B))
+
+
+def weights_invvar(gpT: GPE, gpC: GPE, Xb):
+    """weights_invvar (src/weight_at_units.jl:33-39) with the sentinels already placed:
+    w_border = Sigma_post \\ ones(nb)."""
+    _, S = cliff_face(gpT, gpC, Xb)
+    wb = generic_solve(S, np.ones(S.shape[0]), ctx=gpT.ctx)
+    return Xb, wb, np.concatenate([weight_at_units(gpT, Xb, wb), -weight_at_units(gpC, Xb, wb)])
+
+
+# ----------------------------------------------------------------------------------------------
+# Null handle: make_null + draw-independent setup, and the Monte-Carlo tests
+# ----------------------------------------------------------------------------------------------
+class NullGPE:
+    """make_null(gpT, gpC) (src/hypotest.jl:1-12): the pooled GP, plus -- once sentinels are attached -- the
+    draw-independent state of nsim_chi / nsim_invvar_pval_uncalib / nsim_power."""
+
+    def __init__(self, gpT: GPE, gpC: GPE, Xb=None, nugget: float = 0.0):
+        self.ctx = gpT.ctx
+        self.gpT, self.gpC = gpT, gpC     # keep alive: the handle borrows them
+        self._h = C.c_void_p()
+        self.Xb = fmat(Xb) if Xb is not None else None
+        nb = self.Xb.shape[1] if self.Xb is not None else 0
+        jr, m = C.c_int(), C.c_double()
+        rc = self.ctx.lib.geordd_null_prepare(gpT._h, gpC._h, dptr(self.Xb), nb, float(nugget), C.byref(self._h),
+                                              C.byref(jr), C.byref(m))
+        self.ctx.check(rc)
+        self.jitter_rounds = jr.value
+        self.mll = m.value
+        self.nobs = gpT.nobs + gpC.nobs
+        self.nugget = nugget
+        self.y = np.concatenate([gpT.y, gpC.y])
+        self.alpha = None
+
+    def set_sentinels(self, Xb, nugget: float = 0.0) -> None:
+        self.Xb = fmat(Xb)
+        jr = C.c_int()
+        self.ctx.check(self.ctx.lib.geordd_null_set_sentinels(self._h, dptr(self.Xb), self.Xb.shape[1], float(nugget),
+                                                              C.byref(jr)))
+        self.jitter_rounds = jr.value
+        self.nugget = nugget
+
+    def _ensure(self, Xb, nugget):
+        Xb = fmat(Xb)
+        if self.Xb is None or self.Xb.shape != Xb.shape or not np.array_equal(self.Xb, Xb) or self.nugget != nugget:
+            self.set_sentinels(Xb, nugget)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h:
+            self.ctx.lib.geordd_null_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def make_null(gpT: GPE, gpC: GPE) -> NullGPE:
+    """make_null(gpT, gpC): pooled null GP with T's kernel, mean and noise (src/hypotest.jl:6-12)."""
+    return NullGPE(gpT, gpC)
+
+
+def _zarg(Z, n):
+    if Z is None:
+        return None, None
+    Zf = fmat(Z)
+    assert Zf.shape[0] == n, "Z must be n x nsim (column s = randn(n) of draw s)"
+    return Zf, Zf.shape[1]
+
+
+def chistat(gpT: GPE, gpC: GPE, Xb) -> float:
+    """chistat(gpT, gpC, Xb) observed (src/hypotest_chi2.jl:4-10; generic `\\` = LU on the raw Sigma)."""
+    Xb = fmat(Xb)
+    out = C.c_double()
+    gpT.ctx.check(gpT.ctx.lib.geordd_chistat_obs(gpT._h, gpC._h, dptr(Xb), Xb.shape[1], C.byref(out)))
+    return out.value
+
+
+def nsim_chi(gpT: GPE, gpC: GPE, gpNull: NullGPE, Xb, nsim: int, *, seed: int = 0, draw0: int = 0, Z=None,
+             chi_obs: float = math.inf, return_count: bool = False):
+    """nsim_chi(gpT, gpC, gpNull, Xb, nsim) (src/hypotest_chi2.jl:33-52): vector of nsim chi2 null draws."""
+    gpNull._ensure(Xb, 0.0)
+    Zf, nz = _zarg(Z, gpNull.nobs)
+    nsim = nz if nz is not None else int(nsim)
+    stats = np.empty(nsim)
+    cnt = C.c_longlong()
+    gpT.ctx.check(gpT.ctx.lib.geordd_null_chi2(gpNull._h, nsim, seed, draw0, dptr(Zf), float(chi_obs), dptr(stats),
+                                               C.byref(cnt)))
+    return (stats, cnt.value) if return_count else stats
+
+
+def boot_chi2test(gpT: GPE, gpC: GPE, Xb, nsim: int, **kw) -> float:
+    """boot_chi2test(gpT, gpC, Xb, nsim) (src/hypotest_chi2.jl:54-59): mean(chi_sims .> chi_obs)."""
+    gpNull = make_null(gpT, gpC)
+    chi_obs = chistat(gpT, gpC, Xb)
+    sims, cnt = nsim_chi(gpT, gpC, gpNull, Xb, nsim, chi_obs=chi_obs, return_count=True, **kw)
+    return cnt / sims.shape[0]
+
+
+def pval_invvar_uncalib(gpT: GPE, gpC: GPE, Xb, nugget: float = 1e-10) -> float:
+    """pval_invvar_uncalib(gpT, gpC, Xb; nugget) observed (src/hypotest_invvar.jl:1-6)."""
+    Xb = fmat(Xb)
+    tau, var, p = C.c_double(), C.c_double(), C.c_double()
+    gpT.ctx.check(gpT.ctx.lib.geordd_invvar_obs(gpT._h, gpC._h, dptr(Xb), Xb.shape[1], float(nugget), C.byref(tau),
+                                                C.byref(var), C.byref(p)))
+    return p.value
+
+
+def nsim_invvar_pval_uncalib(gpT: GPE, gpC: GPE, Xb, nsim: int, nugget: float = 1e-10, *, seed: int = 0,
+                             draw0: int = 0, Z=None, pval_obs: float = -1.0, return_count: bool = False,
+                             gpNull: Optional[NullGPE] = None):
+    """nsim_invvar_pval_uncalib(gpT, gpC, Xb, nsim; nugget) (src/hypotest_invvar.jl:48-63)."""
+    gpNull = gpNull or make_null(gpT, gpC)
+    gpNull._ensure(Xb, nugget)
+    Zf, nz = _zarg(Z, gpNull.nobs)
+    nsim = nz if nz is not None else int(nsim)
+    pv = np.empty(nsim)
+    cnt = C.c_longlong()
+    gpT.ctx.check(gpT.ctx.lib.geordd_null_invvar(gpNull._h, nsim, seed, draw0, dptr(Zf), float(pval_obs), dptr(pv),
+                                                 C.byref(cnt)))
+    return (pv, cnt.value) if return_count else pv
+
+
+def boot_invvar(gpT: GPE, gpC: GPE, Xb, nsim: int, nugget: float = 1e-10, **kw) -> float:
+    """boot_invvar (src/hypotest_invvar.jl:65-69): mean(pval_sims .< pval_obs)."""
+    pobs = pval_invvar_uncalib(gpT, gpC, Xb, nugget)
+    sims, cnt = nsim_invvar_pval_uncalib(gpT, gpC, Xb, nsim, nugget, pval_obs=pobs, return_count=True, **kw)
+    return cnt / sims.shape[0]
+
+
+def pval_invvar_calib(gpT: GPE, gpC: GPE, Xb, nugget: float = 1e-10) -> float:
+    """pval_invvar_calib(gpT, gpC, Xb; nugget) analytic (src/hypotest_invvar.jl:74-105)."""
+    Xb = fmat(Xb)
+    p = C.c_double()
+    gpT.ctx.check(gpT.ctx.lib.geordd_invvar_calib(gpT._h, gpC._h, dptr(Xb), Xb.shape[1], float(nugget), C.byref(p)))
+    return p.value
+
+
+def nsim_logP(gpT: GPE, gpC: GPE, gpNull: NullGPE, nsim: int, *, seed: int = 0, draw0: int = 0, Z=None,
+              dmll_obs: float = math.inf, return_count: bool = False):
+    """nsim_logP(gpT, gpC, gpNull, nsim) (src/hypotest_mll.jl:21-30): list of (mll_null, mll_alt).
+    Like the reference it leaves gpNull.y / .alpha / .mll at the last draw (:6,10,14)."""
+    Zf, nz = _zarg(Z, gpNull.nobs)
+    nsim = nz if nz is not None else int(nsim)
+    mnull, malt = np.empty(nsim), np.empty(nsim)
+    last_y, last_a = np.empty(gpNull.nobs), np.empty(gpNull.nobs)
+    cnt = C.c_longlong()
+    gpT.ctx.check(gpT.ctx.lib.geordd_null_mll(gpNull._h, nsim, seed, draw0, dptr(Zf), float(dmll_obs), dptr(mnull),
+                                              dptr(malt), C.byref(cnt), dptr(last_y), dptr(last_a)))
+    gpNull.y, gpNull.alpha, gpNull.mll = last_y, last_a, float(mnull[-1])
+    sims = list(zip(mnull.tolist(), malt.tolist()))
+    return (sims, cnt.value, mnull, malt) if return_count else sims
+
+
+def boot_mlltest(gpT: GPE, gpC: GPE, nsim: int, **kw) -> float:
+    """boot_mlltest(gpT, gpC, nsim) (src/hypotest_mll.jl:32-45): mean(dmll_sim .> dmll_obs)."""
+    mll_alt = gpT.mll + gpC.mll
+    gpNull = make_null(gpT, gpC)
+    d_obs = mll_alt - gpNull.mll
+    _, cnt, mnull, _ = nsim_logP(gpT, gpC, gpNull, nsim, dmll_obs=d_obs, return_count=True, **kw)
+    return cnt / mnull.shape[0]
+
+
+def nsim_power(gpT: GPE, gpC: GPE, tau: float, Xb, chi_null, mll_null, pval_invvar_null, nsim: int, *,
+               seed: int = 0, draw0: int = 0, Z=None, compat_calib_bug: bool = False) -> np.ndarray:
+    """nsim_power (src/power.jl:46-73): nsim x 5 array of (pval_mll, pval_chi2, pval_invvar_obs,
+    invvar_bootcalib, invvar_calib).  compat_calib_bug reproduces the as-shipped missing '+' of the
+    7-argument pval_invvar_calib (src/hypotest_invvar.jl:125-128); default is the corrected formula."""
+    gpNull = NullGPE(gpT, gpC, Xb, 0.0)
+    Zf, nz = _zarg(Z, gpNull.nobs)
+    nsim = nz if nz is not None else int(nsim)
+    chi_null = np.ascontiguousarray(chi_null, dtype=np.float64)
+    mll_null = np.ascontiguousarray(mll_null, dtype=np.float64)
+    pinv = np.ascontiguousarray(pval_invvar_null, dtype=np.float64)
+    assert chi_null.shape == mll_null.shape == pinv.shape
+    out = np.empty((5, nsim), order="F")
+    gpT.ctx.check(gpT.ctx.lib.geordd_power(gpNull._h, float(tau), nsim, seed, draw0, dptr(Zf), dptr(chi_null),
+                                           dptr(mll_null), dptr(pinv), chi_null.shape[0], 1 if compat_calib_bug else 0,
+                                           dptr(out)))
+    return np.ascontiguousarray(out.T)
+
+
+# ----------------------------------------------------------------------------------------------
+# RegionData, MultiGPCovars, GPRealisations
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class RegionData:
+    """src/regiondata.jl:1-9 (shape omitted: geometry stays on the CPU side of the boundary)."""
+    x: np.ndarray
+    y: np.ndarray
+    D: np.ndarray
+
+
+def residuals_data(rd: RegionData, beta) -> RegionData:
+    """residuals_data(rd, beta) (src/regiondata.jl:11-17): y - D'beta with empty covariates."""
+    return RegionData(rd.x, rd.y - rd.D.T @ np.asarray(beta), np.empty((0, rd.y.shape[0])))
+
+
+class MultiGPCovars:
+    """MultiGPCovars(rdict, groupKeys, spkern, betakern, logNoise, mean) (src/region_gp_fit.jl:5-21 ->
+    src/GPrealisationsCovars.jl:31-95): joint GP over all regions with a LinIso kernel on the covariates."""
+
+    def __init__(self, rdict: Dict[Hashable, RegionData], spkern, betakern: LinIso, logNoise: float, mean=None,
+                 groupKeys: Optional[Sequence[Hashable]] = None, ctx: Optional[Context] = None):
+        self.ctx = ctx or default_context()
+        self.groupKeys = list(groupKeys) if groupKeys is not None else list(rdict.keys())
+        if not isinstance(betakern, LinIso):
+            raise ValueError("ArgumentError: the covariate kernel must be LinIso")
+        self.kernel, self.betakern, self.logNoise = spkern, betakern, float(logNoise)
+        self.mean = mean if mean is not None else MeanZero()
+        xs, ys, Ds, off = [], [], [], [0]
+        self.groupIndices = {}
+        for key in self.groupKeys:
+            rd = rdict[key]
+            if rd.y.shape[0] == 0:
+                raise ValueError("empty group")
+            self.groupIndices[key] = range(off[-1], off[-1] + rd.y.shape[0])
+            xs.append(fmat(rd.x)); ys.append(np.asarray(rd.y, dtype=np.float64)); Ds.append(fmat(rd.D))
+            off.append(off[-1] + rd.y.shape[0])
+        self.x = fmat(np.concatenate(xs, axis=1))
+        self.y = np.concatenate(ys)
+        self.D = fmat(np.concatenate(Ds, axis=1))
+        self.p, self.nobs = self.D.shape
+        self.dim = self.x.shape[0]
+        if self.D.shape[1] != self.y.shape[0]:
+            raise ValueError("incompatible dimensions of covariates matrix and gaussian processes")
+        self._off = np.array(off, dtype=np.int32)
+        self._h = C.c_void_p()
+        rc = self.ctx.lib.geordd_multigp_create(self.ctx._h, dptr(self.D), self.p, dptr(self.x), self.dim,
+                                                self._off.ctypes.data_as(capi.c_int_p), len(self.groupKeys), dptr(self.y),
+                                                C.byref(self._h))
+        self.ctx.check(rc)
+        self.alpha = np.empty(self.nobs)
+        self.mll = float("nan")
+        self.dmll = None
+        self.jitter_rounds = 0
+        update_mll(self)      # initialise_mll! (:127-142)
+
+    def _spec(self):
+        return kernel_spec(self.kernel, self.mean)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h:
+            self.ctx.lib.geordd_multigp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def update_mll(obj):
+    """update_mll!(mgpcv) (src/GPrealisationsCovars.jl:110-125) / update_mll!(gpreals) (src/GPrealisations.jl:101-109)."""
+    if isinstance(obj, GPRealisations):
+        obj.mll = float(sum(gp.mll for gp in obj.mgp.values()))
+        return obj.mll
+    spec = obj._spec()
+    m, jr = C.c_double(), C.c_int()
+    obj.ctx.check(obj.ctx.lib.geordd_multigp_mll(obj._h, C.byref(spec), obj.betakern.ell2, obj.logNoise, dptr(obj.alpha),
+                                                 C.byref(m), C.byref(jr)))
+    obj.mll, obj.jitter_rounds = m.value, jr.value
+    return obj.mll
+
+
+def update_mll_and_dmll(mgpcv: MultiGPCovars, noise=True, domean=True, kern=True, beta=True) -> np.ndarray:
+    """update_mll_and_dmll!(mgpcv, buf; noise, domean, kern, beta) (src/GPrealisationsCovars.jl:145-193)."""
+    spec = mgpcv._spec()
+    m, nd = C.c_double(), C.c_int()
+    buf = np.empty(8)
+    nfix = 0 if not isinstance(mgpcv.kernel, (FixedKernel,)) else 0
+    mgpcv.ctx.check(mgpcv.ctx.lib.geordd_multigp_mll_grad(mgpcv._h, C.byref(spec), mgpcv.betakern.ell2, mgpcv.logNoise,
+                                                          int(noise), int(domean), int(kern), int(beta), C.byref(m),
+                                                          dptr(buf), C.byref(nd)))
+    mgpcv.mll = m.value
+    g = buf[: nd.value].copy()
+    # hide fixed sub-kernel parameters (fix(Const)) exactly like get_params does
+    if kern:
+        g = _drop_fixed_kernel_grads(mgpcv, g, noise, domean, beta)
+    mgpcv.dmll = g
+    return g
+
+
+def _kernel_param_mask(kernel) -> List[bool]:
+    """True for each device-reported kernel gradient entry that get_params exposes."""
+    k = kernel
+    if isinstance(k, FixedKernel):
+        inner = _kernel_param_mask(k.kernel)
+        return [False] * len(inner)
+    if isinstance(k, SumKernel):
+        a, b = k.kleft, k.kright
+        ma, mb = _kernel_param_mask(a), _kernel_param_mask(b)
+        # device order is always [spatial..., const]
+        if isinstance(_unfix(a), Const):
+            return mb + ma
+        return ma + mb
+    if isinstance(k, Const):
+        return [True]
+    return [True, True]
+
+
+def _drop_fixed_kernel_grads(mgpcv, g, noise, domean, beta):
+    start = (1 if noise else 0) + (1 if (domean and isinstance(mgpcv.mean, MeanConst) and mgpcv.mean.beta != 0.0) else 0)
+    mask = _kernel_param_mask(mgpcv.kernel)
+    nk = len(mask)
+    kg = [g[start + i] for i in range(nk) if mask[i]]
+    # reorder to get_params order if Const is on the left
+    k = mgpcv.kernel
+    if isinstance(k, SumKernel) and isinstance(_unfix(k.kleft), Const) and len(kg) == 3:
+        kg = [kg[2], kg[0], kg[1]]
+    return np.concatenate([g[:start], kg, g[start + nk:]])
+
+
+def mgp_get_params(mgpcv: MultiGPCovars, noise=True, domean=True, kern=True, beta=True) -> np.ndarray:
+    """get_params(mgpcv; ...) (src/GPrealisationsCovars.jl:194-201)."""
+    p: List[float] = []
+    if noise:
+        p.append(mgpcv.logNoise)
+    if domean and isinstance(mgpcv.mean, MeanConst):
+        p.append(mgpcv.mean.beta)
+    if kern:
+        p.extend(get_params(mgpcv.kernel))
+    if beta:
+        p.extend(get_params(mgpcv.betakern))
+    return np.array(p)
+
+
+def mgp_set_params(mgpcv: MultiGPCovars, hyp, noise=True, domean=True, kern=True, beta=True) -> None:
+    """set_params!(mgpcv, hyp; ...) (src/GPrealisationsCovars.jl:202-222)."""
+    i = 0
+    if noise:
+        mgpcv.logNoise = float(hyp[i]); i += 1
+    if domean and isinstance(mgpcv.mean, MeanConst):
+        mgpcv.mean.beta = float(hyp[i]); i += 1
+    if kern:
+        nk = len(get_params(mgpcv.kernel))
+        set_params(mgpcv.kernel, hyp[i:i + nk]); i += nk
+    if beta:
+        set_params(mgpcv.betakern, hyp[i:i + 1]); i += 1
+
+
+def optimize(mgpcv: MultiGPCovars, noise=True, domean=True, kern=True, beta=True, method="CG", options=None):
+    """optimize!(mgpcv; ...) (src/GPrealisationsCovars.jl:224-279).  The optimiser loop stays on the host
+    (Optim.jl in Julia; SciPy's nonlinear CG here); every objective / gradient evaluation is one ABI call.
+    Non-finite parameters, ArgumentError and PosDefException evaluate to +Inf exactly as :232-245."""
+    from scipy.optimize import minimize
+    kw = dict(noise=noise, domean=domean, kern=kern, beta=beta)
+
+    def fg(hyp):
+        try:
+            if not np.all(np.isfinite(hyp)):
+                raise ValueError("non-finite hyper-parameters")
+            mgp_set_params(mgpcv, hyp, **kw)
+            g = update_mll_and_dmll(mgpcv, **kw)
+            return -mgpcv.mll, -g
+        except (ValueError, PosDefException, OverflowError) as err:
+            print(err)
+            return math.inf, np.zeros_like(hyp)
+
+    init = mgp_get_params(mgpcv, **kw)
+    res = minimize(fg, init, jac=True, method=method, options=options or {})
+    mgp_set_params(mgpcv, res.x, **kw)
+    update_mll(mgpcv)
+    return res
+
+
+def postmean_beta(mgpcv: MultiGPCovars) -> np.ndarray:
+    """postmean_beta(mgpcv) (src/GPrealisationsCovars.jl:335-344)."""
+    spec = mgpcv._spec()
+    out = np.empty(mgpcv.p)
+    mgpcv.ctx.check(mgpcv.ctx.lib.geordd_multigp_postmean_beta(mgpcv._h, C.byref(spec), mgpcv.betakern.ell2,
+                                                               mgpcv.logNoise, dptr(out)))
+    return out
+
+
+class GPRealisations:
+    """GPRealisations(rdict, groupKeys, spkern, logNoise, mean) (src/region_gp_fit.jl:23-37 ->
+    src/GPrealisations.jl:10-55): one fitted GPE per region sharing (kernel, logNoise).  'Realisations'
+    are regions, not random draws."""
+
+    def __init__(self, rdict: Dict[Hashable, RegionData], spkern, logNoise: float, mean=None,
+                 groupKeys: Optional[Sequence[Hashable]] = None, ctx: Optional[Context] = None):
+        self.groupKeys = list(groupKeys) if groupKeys is not None else list(rdict.keys())
+        self.kernel, self.logNoise = spkern, float(logNoise)
+        self.mean = mean if mean is not None else MeanZero()
+        self.mgp: Dict[Hashable, GPE] = {}
+        nobs = 0
+        for key in self.groupKeys:
+            rd = rdict[key]
+            if rd.y.shape[0] == 0:
+                raise ValueError("empty group")
+            self.mgp[key] = GPE(rd.x, rd.y, self.mean, spkern, logNoise, ctx=ctx)
+            nobs += rd.y.shape[0]
+        self.nobs = nobs
+        self.mll = 0.0
+        update_mll(self)
+
+    def __getitem__(self, key) -> GPE:
+        return self.mgp[key]
+
+    def keys(self):
+        return self.groupKeys
+
+    def values(self):
+        return self.mgp.values()
+
+
+# ----------------------------------------------------------------------------------------------
+# Placebo drivers (src/placebo_geometry.jl + src/hypotest_*.jl placebo_*): O(n) host geometry feeding the
+# GPU tests.  Thin wrappers, SURVEY §8 a15.
+# ----------------------------------------------------------------------------------------------
+def _tand(a):
+    return math.tan(math.radians(a))
+
+
+def left_points(angle: float, shift: float, X) -> np.ndarray:
+    """left_points(angle, shift, X) (src/placebo_geometry.jl:8-32)."""
+    X = np.asarray(X)
+    dydx = _tand(angle)
+    meanx, meany = float(np.mean(X[0])), float(np.mean(X[1]))
+    direction = np.sign(math.cos(math.radians(angle + 90)))
+    if direction == 0.0:
+        direction = 1.0
+    sx = shift * math.cos(math.radians(angle + 90)) * direction
+    sy = shift * math.sin(math.radians(angle + 90)) * direction
+    ax, ay = meanx + sx, meany + sy
+    if abs(dydx) < 1.0:
+        dx, dy = 1.0, dydx
+    else:
+        dx, dy = 1.0 / dydx, 1.0
+    bx, by = meanx + sx + dx, meany + dy + sy
+    return ((bx - ax) * (X[1] - ay) - (by - ay) * (X[0] - ax)) > 0
+
+
+def shift_for_even_split(angle: float, X, tol: float = 1e-5, maxiter: int = 100) -> float:
+    """shift_for_even_split(angle, X) (src/placebo_geometry.jl:131-136): bisection (tol 1e-5) on
+    prop_left(angle, shift, X) - 0.5 over [-maxdistance, maxdistance] (:112-129)."""
+    X = np.asarray(X)
+    maxd = float(math.hypot(np.ptp(X[1]), np.ptp(X[0])))
+    f = lambda sh: float(np.mean(left_points(angle, sh, X))) - 0.5
+    a, b = -maxd, maxd
+    fa = f(a)
+    if fa * f(b) > 0:
+        raise ValueError("No real root in [a,b]")
+    c = 0.5 * (a + b)
+    for it in range(1, maxiter + 1):
+        if b - a <= tol:
+            break
+        if it == maxiter:
+            raise RuntimeError("Max iteration exceeded")
+        c = 0.5 * (a + b)
+        fc = f(c)
+        if fc == 0:
+            break
+        if fa * fc > 0:
+            a, fa = c, fc
+        else:
+            b = c
+    return c
+
+
+def placebo_sentinels(angle: float, shift: float, X, npoints: int) -> np.ndarray:
+    """placebo_sentinels(angle, shift, X, npoints) (src/placebo_geometry.jl:60-101): npoints equally spaced
+    between the two intersections of the placebo line with the data's bounding box."""
+    X = np.asarray(X)
+    meanx, meany = float(np.mean(X[0])), float(np.mean(X[1]))
+    minx, maxx = float(X[0].min()), float(X[0].max())
+    miny, maxy = float(X[1].min()), float(X[1].max())
+    dydx = _tand(angle)
+    direction = np.sign(math.cos(math.radians(angle + 90))) or 1.0
+    cx = meanx + shift * math.cos(math.radians(angle + 90)) * direction
+    cy = meany + shift * math.sin(math.radians(angle + 90)) * direction
+    ext = []
+    y0, y1 = cy + dydx * (minx - cx), cy + dydx * (maxx - cx)
+    if miny < y0 < maxy:
+        ext.append((minx, y0))
+    if miny < y1 < maxy:
+        ext.append((maxx, y1))
+    if dydx != 0.0:
+        x0, x1 = cx + (miny - cy) / dydx, cx + (maxy - cy) / dydx
+        if minx < x0 < maxx:
+            ext.append((x0, miny))
+        if minx < x1 < maxx:
+            ext.append((x1, maxy))
+    assert len(ext) == 2, "placebo line must cross the bounding box twice"
+    return fmat(np.vstack([np.linspace(ext[0][0], ext[1][0], npoints), np.linspace(ext[0][1], ext[1][1], npoints)]))
+
+
+def _placebo_split(angle, X, Y, kern, mean, logNoise):
+    X = fmat(X)
+    Y = np.asarray(Y, dtype=np.float64)
+    shift = shift_for_even_split(angle, X)
+    left = left_points(angle, shift, X)
+    gl = GPE(X[:, left], Y[left], mean, kern, logNoise)
+    gr = GPE(X[:, ~left], Y[~left], mean, kern, logNoise)
+    return shift, gl, gr
+
+
+def placebo_chi(angle: float, X, Y, kern, mean, logNoise: float, nsim: int, **kw) -> float:
+    """placebo_chi (src/hypotest_chi2.jl:62-76)."""
+    shift, gl, gr = _placebo_split(angle, X, Y, kern, mean, logNoise)
+    Xb = placebo_sentinels(angle, shift, X, 100)
+    return boot_chi2test(gl, gr, Xb, nsim, **kw)
+
+
+def placebo_invvar(angle: float, X, Y, kern, mean, logNoise: float) -> float:
+    """placebo_invvar (src/hypotest_invvar.jl:162-175)."""
+    shift, gl, gr = _placebo_split(angle, X, Y, kern, mean, logNoise)
+    Xb = placebo_sentinels(angle, shift, X, 100)
+    return pval_invvar_calib(gl, gr, Xb)
+
+
+def placebo_mll(angle: float, X, Y, kern, mean, logNoise: float, nsim: int, **kw) -> float:
+    """placebo_mll (src/hypotest_mll.jl:47-60)."""
+    _, gl, gr = _placebo_split(angle, X, Y, kern, mean, logNoise)
+    return boot_mlltest(gl, gr, nsim, **kw)

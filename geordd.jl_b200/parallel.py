@@ -1,0 +1,45 @@
+"""Multi-GPU host logic: the ONLY parallel structure of the hot path is the embarrassingly parallel
+Monte-Carlo draw loop (`[sim...() for _ in 1:nsim]`, src/hypotest_chi2.jl:49-50, src/hypotest_mll.jl:27-28,
+src/hypotest_invvar.jl:60-61, src/power.jl:67-71).  One process per GPU; draw indices are sharded
+contiguously; each draw depends only on (seed, draw index), so results are invariant to the GPU count;
+the exceedance tallies (a few int64) are summed with ONE all-reduce (NCCL over NVLink on GPUs, gloo in the
+CPU tests).  Single fits and cliff faces stay on one GPU (BASELINE north_star)."""
+from __future__ import annotations
+
+from typing import Sequence, Tuple
+
+
+def shard_draws(nsim: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous shard [draw0, draw0 + count) of draw indices 0..nsim-1 for `rank`."""
+    if world <= 0 or not (0 <= rank < world) or nsim < 0:
+        raise ValueError("bad shard request")
+    lo = (nsim * rank) // world
+    hi = (nsim * (rank + 1)) // world
+    return lo, hi - lo
+
+
+def allreduce_tallies(counts: Sequence[int], device=None):
+    """Sum integer tallies over all ranks (torch.distributed; backend chosen by the caller's init)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(counts), dtype=torch.int64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [int(v) for v in t.cpu().tolist()]
+
+
+def gather_stats(local, nsim: int, device=None):
+    """All-gather the per-draw statistics (8*S bytes) when the caller wants the full vector (`nsim_*`)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return np.asarray(local)
+    world = dist.get_world_size()
+    sizes = [shard_draws(nsim, r, world)[1] for r in range(world)]
+    mx = max(sizes)
+    buf = torch.zeros(mx, dtype=torch.float64, device=device)
+    buf[: len(local)] = torch.as_tensor(np.asarray(local), dtype=torch.float64)
+    out = [torch.zeros(mx, dtype=torch.float64, device=device) for _ in range(world)]
+    dist.all_gather(out, buf)
+    return np.concatenate([o[:s].cpu().numpy() for o, s in zip(out, sizes)])

@@ -102,6 +102,9 @@ GEORDD_API int geordd_cliff_face(geordd_gp* T, geordd_gp* C, const double* Xb, i
  * Sigma a plain Matrix => + nugget*I and LU solves.  Also unweighted/weighted means (:13-29). */
 GEORDD_API int geordd_inverse_variance(geordd_ctx* ctx, const double* mu, const double* Sigma, int nb, double nugget,
                             double* tau_hat, double* var_tau);
+/* Julia's generic `A \\ B` on a dense square Matrix = lu(A) \\ B (partial pivoting; hit at
+ * src/weight_at_units.jl:36, src/hypotest_chi2.jl:9).  A is n x n, B (n x nrhs) is overwritten by the solution. */
+GEORDD_API int geordd_solve_general(geordd_ctx* ctx, const double* A, int n, double* B, int nrhs);
 /* weight_at_units(gp, sentinels, weights) (src/weight_at_units.jl:12-18): w_unit (n). */
 GEORDD_API int geordd_weight_at_units(geordd_gp* gp, const double* Xb, int nb, const double* w_border, double* w_unit);
 

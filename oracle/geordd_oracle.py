@@ -88,7 +88,7 @@ def _sqdist(X1: np.ndarray, X2: np.ndarray, method: str = "direct") -> np.ndarra
 def kernel_of_r2(spec: KernelSpec, r2: np.ndarray) -> np.ndarray:
     """k(r) for the four isotropic kernels + Const (App. A.1)."""
     if spec.kind == SE_ISO:
-        k = spec.sigma2 * np.exp(-r2 / (2.0 * spec.ell * spec.ell))
+        k = spec.sigma2 * np.exp(-0.5 * r2 / (spec.ell * spec.ell))   # se.s2*exp(-0.5*r/se.l2)
     else:
         r = np.sqrt(r2)
         if spec.kind == MAT12:
@@ -484,13 +484,22 @@ def pval_invvar_calib(gpT: GP, gpC: GP, Xb: np.ndarray, nugget: float = 1e-10) -
     return 2.0 * Normal(0.0, math.sqrt(cov_mt)).ccdf(abs(num))
 
 
-def pval_invvar_calib_pre(ns: NullSetup, KCT: np.ndarray, as_shipped: bool = False) -> float:
-    """src/hypotest_invvar.jl:106-137 (7-argument variant used by sim_power!, src/power.jl:41).
-    as_shipped=True reproduces the missing-'+' defect."""
-    mub = predict_mu(ns.gpT, ns.Xb, ns.cK_T) - predict_mu(ns.gpC, ns.Xb, ns.cK_C)
-    n = mub.shape[0]
+def calib_cov_mu_tau(ns: NullSetup, KCT: np.ndarray, as_shipped: bool = False) -> float:
+    """The draw-independent part of the 7-argument pval_invvar_calib (src/hypotest_invvar.jl:111-131):
+    cov_mu_tau = sum((Sigma \\ cov_mu_delta) * (Sigma \\ ones)).  The reference recomputes it for every
+    draw; it does not depend on y, so computing it once gives bit-identical values."""
+    n = ns.Sraw.shape[0]
     cmd = _calib_cov_mu_delta(ns.gpT, ns.gpC, ns.cK_T, ns.cK_C, KCT, as_shipped)
-    cov_mt = float(np.sum(pd_solve(ns.US, cmd) @ pd_solve(ns.US, np.ones(n))))
+    return float(np.sum(pd_solve(ns.US, cmd) @ pd_solve(ns.US, np.ones(n))))
+
+
+def pval_invvar_calib_pre(ns: NullSetup, KCT: np.ndarray, as_shipped: bool = False,
+                          cov_mt: Optional[float] = None) -> float:
+    """src/hypotest_invvar.jl:106-137 (7-argument variant used by sim_power!, src/power.jl:41).
+    as_shipped=True reproduces the missing-'+' defect.  cov_mt: pass calib_cov_mu_tau(...) to hoist."""
+    mub = predict_mu(ns.gpT, ns.Xb, ns.cK_T) - predict_mu(ns.gpC, ns.Xb, ns.cK_C)
+    if cov_mt is None:
+        cov_mt = calib_cov_mu_tau(ns, KCT, as_shipped)
     num = float(np.sum(pd_solve(ns.US, mub)))
     return 2.0 * Normal(0.0, math.sqrt(cov_mt)).ccdf(abs(num))
 
@@ -537,6 +546,7 @@ def nsim_power(gpT: GP, gpC: GP, tau: float, Xb: np.ndarray, chi_null: np.ndarra
     invvar_bootcalib, invvar_calib)."""
     ns = null_setup(gpT, gpC, Xb, 0.0)   # make_posdef!(copy(Sigma_cliff)), src/power.jl:57-59
     KCT = cov_cross(gpC.spec, gpC.x, gpT.x)
+    cov_mt = calib_cov_mu_tau(ns, KCT, as_shipped_calib)   # hoisted: draw-independent
     S = Z.shape[1]
     out = np.empty((S, 5))
     for s in range(S):
@@ -551,7 +561,7 @@ def nsim_power(gpT: GP, gpC: GP, tau: float, Xb: np.ndarray, chi_null: np.ndarra
         pobs = pval_invvar_uncalib_pre(ns)
         out[s, 2] = pobs
         out[s, 3] = np.mean(pval_invvar_null < pobs)
-        out[s, 4] = pval_invvar_calib_pre(ns, KCT, as_shipped_calib)
+        out[s, 4] = pval_invvar_calib_pre(ns, KCT, as_shipped_calib, cov_mt)
     return out
 
 
@@ -584,8 +594,8 @@ def _kernel_param_grads(spec: KernelSpec, r2: np.ndarray):
     [log ell, log sigma, (log sigma_const)]  (App. A.1)."""
     grads = []
     if spec.kind == SE_ISO:
-        k = spec.sigma2 * np.exp(-r2 / (2.0 * spec.ell ** 2))
-        grads.append(k * r2 / spec.ell ** 2)
+        k = spec.sigma2 * np.exp(-0.5 * r2 / (spec.ell * spec.ell))
+        grads.append(k * r2 / (spec.ell * spec.ell))
     else:
         r = np.sqrt(r2)
         if spec.kind == MAT12:

@@ -1,0 +1,245 @@
+"""CPU tests of the oracle (oracle/geordd_oracle.py).  The reference ships no golden vectors for the hot
+path, so the oracle is pinned by: a 50-digit mpmath restatement, algebraic identities,
+the reference's own test styles (gradient vs finite differences, test/test_gprealisations.jl:12-40;
+statistical acceptance, test/test_simulated.jl:53-71), the published Mississippi size table
+(notebooks/Mississippi_sharp_null_sims.ipynb cell 28) and Random123's Philox known-answer vectors."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+
+def _small(O, m=14, nb=5, kind=None, seed=3):
+    d = O.synth_two_region(m, nb, seed=seed)
+    spec = O.KernelSpec(O.MAT32 if kind is None else kind, 0.3, 1.0, 4.0, 0.0)
+    gT = O.gp_fit(spec, d["XT"], d["YT"], math.log(0.3))
+    gC = O.gp_fit(spec, d["XC"], d["YC"], math.log(0.3))
+    return d, spec, gT, gC
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+def test_kernels_direct_vs_gram_and_symmetry(O, kind):
+    rng = np.random.default_rng(0)
+    X = rng.random((2, 60))
+    spec = O.KernelSpec(kind, 0.37, 1.3, 0.5, 0.0)
+    Kd = O.cov_cross(spec, X, X, "direct")
+    Kg = O.cov_cross(spec, X, X, "gram")
+    off = ~np.eye(60, dtype=bool)
+    # the Gram trick loses ~sqrt(eps) on near-zero distances for the non-smooth Matern-1/2 kernel
+    assert np.max(np.abs(Kd - Kg)[off]) < (1e-6 if kind == 1 else 1e-12)
+    Ks = O.cov_sym(spec, X, 0.09)
+    assert np.array_equal(Ks, Ks.T)
+    assert np.allclose(np.diag(Ks), spec.sigma2 + spec.const_sigma2 + 0.09, rtol=0, atol=1e-15)
+
+
+def test_mpmath_crosscheck(O):
+    """50-digit restatement of fit + cliff face + chi2 on a small well-conditioned problem."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 50
+    d, spec, gT, gC = _small(O, m=9, nb=4)
+
+    def kfun(x1, x2):
+        r = mp.sqrt(sum((mp.mpf(float(a)) - mp.mpf(float(b))) ** 2 for a, b in zip(x1, x2)))
+        s = mp.sqrt(3) * r / mp.mpf(spec.ell)
+        return mp.mpf(spec.sigma2) * (1 + s) * mp.e ** (-s) + mp.mpf(spec.const_sigma2)
+
+    def fit(X, y):
+        n = X.shape[1]
+        K = mp.matrix(n, n)
+        for i in range(n):
+            for j in range(n):
+                K[i, j] = kfun(X[:, i], X[:, j])
+            K[i, i] += mp.e ** (2 * mp.log(mp.mpf("0.3"))) + mp.mpf(float(O.EPS))
+        L = mp.cholesky(K)
+        yv = mp.matrix([mp.mpf(float(v)) for v in y])
+        alpha = mp.lu_solve(K, yv)
+        logdet = 2 * sum(mp.log(L[i, i]) for i in range(n))
+        mll = -(yv.T * alpha)[0] / 2 - logdet / 2 - n * mp.log(2 * mp.pi) / 2
+        return K, alpha, mll
+
+    def pred(X, K, alpha, Xb):
+        n, nb = X.shape[1], Xb.shape[1]
+        Kxb = mp.matrix(n, nb)
+        for i in range(n):
+            for j in range(nb):
+                Kxb[i, j] = kfun(X[:, i], Xb[:, j])
+        Kbb = mp.matrix(nb, nb)
+        for i in range(nb):
+            for j in range(nb):
+                Kbb[i, j] = kfun(Xb[:, i], Xb[:, j])
+        mu = Kxb.T * alpha
+        S = Kbb - Kxb.T * (mp.inverse(K) * Kxb)
+        return mu, S
+
+    KT, aT, mllT = fit(d["XT"], d["YT"])
+    KC, aC, mllC = fit(d["XC"], d["YC"])
+    muT, ST = pred(d["XT"], KT, aT, d["Xb"])
+    muC, SC = pred(d["XC"], KC, aC, d["Xb"])
+    mu_hp = np.array([float(muT[i] - muC[i]) for i in range(4)])
+    S_hp = np.array([[float(ST[i, j] + SC[i, j]) for j in range(4)] for i in range(4)])
+    chi_hp = float(((muT - muC).T * mp.lu_solve(ST + SC, muT - muC))[0])
+    mu, S = O.cliff_face(gT, gC, d["Xb"])
+    assert relerr(gT.alpha, [float(v) for v in aT]) < 1e-11
+    assert abs(gT.mll - float(mllT)) < 1e-10 * abs(float(mllT))
+    assert relerr(mu, mu_hp) < 1e-10
+    assert relerr(S, S_hp) < 1e-10
+    assert abs(O.chistat_obs(gT, gC, d["Xb"]) - chi_hp) < 1e-8 * abs(chi_hp)
+
+
+def test_identity_quadratic_form(O):
+    """y = L z  =>  y' K^-1 y = z' z: pins prior_rand + update_alpha! + the factor convention."""
+    d, spec, gT, gC = _small(O, m=40, nb=5)
+    gN = O.make_null(gT, gC)
+    z = np.random.default_rng(5).standard_normal(gN.nobs)
+    y = O.prior_rand(gN, z)
+    gN.y = y
+    O.update_alpha(gN)
+    assert abs(float(y @ gN.alpha) - float(z @ z)) < 1e-9 * float(z @ z)
+    assert np.allclose(gN.U.T @ gN.U, gN.K, rtol=1e-12, atol=1e-12)      # upper factor: U'U = K
+    assert np.allclose(y, gN.U.T @ z)
+
+
+def test_make_posdef_semantics(O):
+    """App. A.5: eps = 1e-6 tr(M)/n recomputed on the already-jittered matrix; rounds counted."""
+    v = np.ones((6, 1))
+    M = v @ v.T - 2.5e-6 * np.eye(6)          # eigenvalues 6 - 2.5e-6 and -2.5e-6 (x5): needs 3 jitter rounds
+    Mj, U, rounds = O.make_posdef(M)
+    assert rounds == 3
+    d, tot = M.copy(), 0.0
+    for _ in range(3):                         # eps compounds on the jittered trace
+        eps = 1e-6 * np.trace(d) / 6
+        d[np.diag_indices(6)] += eps
+        tot += eps
+    assert Mj[1, 1] == d[1, 1]
+    assert np.allclose(U.T @ U, Mj, atol=1e-12)
+    with pytest.raises(O.PosDefException):
+        O.make_posdef(-np.eye(4))
+
+
+def test_gradient_matches_finite_differences(O):
+    """The reference's own test (test/test_gprealisations.jl:12-40) restated on the oracle: n = 100,
+    SEIso(log .5, log 1) + Const(log 20), LinIso(log 1), logNoise 1.0; atol 1e-3 there, 1e-5 here."""
+    d = O.synth_two_region(50, 10, seed=1)
+    off = [0, 50, 100]
+
+    def make(th):
+        spec = O.KernelSpec(O.SE_ISO, math.exp(th[1]), math.exp(2 * th[2]), math.exp(2 * th[3]))
+        return O.MultiGP(D=d["D"], y=d["Y"], X=d["X"], group_off=off, spec=spec, lin_ell2=math.exp(2 * th[4]),
+                         log_noise=th[0])
+
+    th0 = np.array([1.0, math.log(0.5), 0.0, math.log(20.0), 0.0])
+    g = O.multigp_update_mll_and_dmll(make(th0), domean=False)
+    num = np.array([(O.multigp_update_mll(make(th0 + 1e-5 * e)) - O.multigp_update_mll(make(th0 - 1e-5 * e))) / 2e-5
+                    for e in np.eye(5)])
+    assert np.allclose(g, num, atol=1e-5)
+
+
+def test_simulated_acceptance(O):
+    """test/test_simulated.jl:11-71 on the oracle with NumPy-seeded data (n = 600 to keep the CPU suite
+    short): tau inside the central 99.8 % interval of the inverse-variance LATE, calibrated p < 0.05."""
+    from scipy.optimize import minimize
+    tau = 0.3
+    d = O.synth_two_region(300, 100, seed=1, tau=tau)
+    off = [0, 300, 600]
+
+    def make(th):
+        spec = O.KernelSpec(O.SE_ISO, math.exp(th[1]), math.exp(2 * th[2]), 400.0)
+        return O.MultiGP(D=d["D"], y=d["Y"], X=d["X"], group_off=off, spec=spec, lin_ell2=math.exp(2 * th[3]),
+                         log_noise=th[0])
+
+    def fg(th):
+        try:
+            mg = make(th)
+            g = O.multigp_update_mll_and_dmll(mg, domean=False)
+            g = np.array([g[0], g[1], g[2], g[4]])     # Const is fixed here to keep the problem 4-d
+            return -mg.mll, -g
+        except O.PosDefException:
+            return np.inf, np.zeros(4)
+
+    res = minimize(fg, np.array([1.0, math.log(0.3), 0.0, 0.0]), jac=True, method="CG", options={"maxiter": 60})
+    mg = make(res.x)
+    O.multigp_update_mll(mg)
+    beta = O.multigp_postmean_beta(mg)
+    rT, rC = O.residuals(d["YT"], d["D"][:, :300], beta), O.residuals(d["YC"], d["D"][:, 300:], beta)
+    gps, _ = O.gp_realisations(mg.spec, [d["XT"], d["XC"]], [rT, rC], mg.log_noise)
+    mu, S = O.cliff_face(gps[0], gps[1], d["Xb"])
+    tau_inv = O.inverse_variance(mu, S)
+    assert tau > tau_inv.quantile(0.001) and tau < tau_inv.quantile(0.999)
+    assert O.pval_invvar_calib(gps[0], gps[1], d["Xb"]) < 0.05
+
+
+def test_calib_as_shipped_differs(O):
+    d, spec, gT, gC = _small(O, m=30, nb=8)
+    ns = O.null_setup(gT, gC, d["Xb"], 0.0)
+    KCT = O.cov_cross(gC.spec, gC.x, gT.x)
+    ok = O.pval_invvar_calib_pre(ns, KCT, as_shipped=False)
+    bug = O.pval_invvar_calib_pre(ns, KCT, as_shipped=True)
+    ref3 = O.pval_invvar_calib(gT, gC, d["Xb"], nugget=0.0)
+    assert abs(ok - ref3) < 1e-6          # corrected 7-arg variant agrees with the 3-arg formula
+    assert abs(bug - ok) > 1e-6           # the missing '+' changes the answer
+
+
+def test_philox_known_answers(O):
+    """Random123 kat_vectors for philox4x32-10."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, exp in kat:
+        out = O.philox4x32_10(*[np.array([c], dtype=np.uint32) for c in ctr], key[0], key[1])
+        assert tuple(int(o[0]) for o in out) == exp
+
+
+def test_philox_normals_moments_and_invariance(O):
+    Z = O.philox_normals(1, 0, 400, 501)
+    assert abs(Z.mean()) < 0.01 and abs(Z.std() - 1.0) < 0.01
+    assert np.array_equal(O.philox_normals(1, 100, 50, 501), Z[:, 100:150])     # keyed by draw index only
+    assert not np.array_equal(O.philox_normals(2, 0, 4, 501), Z[:, :4])
+
+
+def test_golden_oracle_small(O, golden):
+    """Drift detection of the oracle against its own committed outputs (tests/golden/make_golden.py)."""
+    g = golden["small"]
+    for tag in ("mat32", "se"):
+        kind, ell, s2, c2, mc, ln = g[f"{tag}_spec"]
+        spec = O.KernelSpec(int(kind), ell, s2, c2, mc)
+        gT = O.gp_fit(spec, g[f"{tag}_XT"], g[f"{tag}_YT"], ln)
+        gC = O.gp_fit(spec, g[f"{tag}_XC"], g[f"{tag}_YC"], ln)
+        mu, S = O.cliff_face(gT, gC, g[f"{tag}_Xb"])
+        assert relerr(gT.alpha, g[f"{tag}_alphaT"]) < 1e-9
+        assert relerr(mu, g[f"{tag}_mu"]) < 1e-9 and relerr(S, g[f"{tag}_Sigma"]) < 1e-9
+        Z = g[f"{tag}_Z"][:, :24]
+        gN = O.make_null(gT, gC)
+        sims = O.nsim_chi(gT, gC, gN, g[f"{tag}_Xb"], Z)
+        tol = 1e-7 if tag == "mat32" else 1e-3      # SE cliff covariance is ill-conditioned (SURVEY §7 hard part 1)
+        assert relerr(sims, g[f"{tag}_chi_sims"][:24]) < tol
+        mnull, malt = O.nsim_logP(gT, gC, gN, Z)
+        assert relerr(malt - mnull, g[f"{tag}_dmll_sims"][:24]) < 1e-8
+
+
+def test_mississippi_size_table(O, golden):
+    """Statistical pin from the reference's own fixture and published table
+    (notebooks/Mississippi_sharp_null_sims.ipynb cells 7-11, 19-28): under tau = 0 the bootstrap tests have
+    size 0.05 at alpha = 0.05, the uncalibrated inverse-variance test is over-sized (0.09)."""
+    ms = golden["mississippi"]
+    spec = O.KernelSpec(O.SE_ISO, 100e3, 1.0, 100.0 ** 2, 0.0)
+    nT, nC = ms["X_MS"].shape[1], ms["X_LA"].shape[1]
+    gT = O.gp_fit(spec, ms["X_MS"], np.zeros(nT), 0.0)
+    gC = O.gp_fit(spec, ms["X_LA"], np.zeros(nC), 0.0)
+    Xb = ms["sentinels"]
+    rng = np.random.default_rng(4)
+    S_null, S_pow = 1500, 1500
+    Zn = rng.standard_normal((nT + nC, S_null))
+    gN = O.make_null(gT, gC)
+    chi_null = O.nsim_chi(gT, gC, gN, Xb, Zn)
+    mnull, malt = O.nsim_logP(gT, gC, O.make_null(gT, gC), Zn)
+    pinv_null = O.nsim_invvar_pval_uncalib(gT, gC, Xb, Zn)
+    Zp = rng.standard_normal((nT + nC, S_pow))
+    out = O.nsim_power(gT, gC, 0.0, Xb, chi_null, malt - mnull, pinv_null, Zp)
+    size = (out < 0.05).mean(axis=0)
+    se = 3.5 * math.sqrt(0.05 * 0.95 / S_pow) + 3.5 * math.sqrt(0.05 * 0.95 / S_null)
+    assert abs(size[0] - 0.05) < se and abs(size[1] - 0.05) < se and abs(size[3] - 0.05) < se
+    assert abs(size[4] - 0.05) < se                      # corrected analytic calibration
+    assert 0.06 < size[2] < 0.13                         # published 0.09
