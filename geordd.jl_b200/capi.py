@@ -43,6 +43,7 @@ class PosDefException(ArithmeticError):
 # name -> (restype, argtypes)
 _SIGS = {
     "geordd_version": (C.c_int, []),
+    "geordd_launch_count": (C.c_longlong, []),
     "geordd_ctx_create": (C.c_int, [c_void_pp, C.c_int]),
     "geordd_ctx_destroy": (C.c_int, [C.c_void_p]),
     "geordd_last_error": (C.c_char_p, [C.c_void_p]),

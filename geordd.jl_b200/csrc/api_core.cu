@@ -4,6 +4,8 @@
 
 namespace geordd {
 
+long long g_kernel_launches = 0;
+
 const char* const kProfNames[PC_COUNT] = {"cov", "potrf", "solve_fwd", "solve_bwd", "trmm",
                                           "gemm", "rng", "finish", "lu", "misc"};
 
@@ -262,6 +264,8 @@ using namespace geordd;
 extern "C" {
 
 int geordd_version(void) { return 100; }
+
+long long geordd_launch_count(void) { return geordd::g_kernel_launches; }
 
 int geordd_ctx_create(geordd_ctx** out, int device) {
     if (!out) return GEORDD_ERR_ARG;

@@ -134,7 +134,7 @@ static int mg_update_mll(geordd_multigp* h, const geordd_kernel* k, double lin_e
     geordd_ctx* c = h->ctx;
     const int n = h->n, np = h->npad;
     const long tot = (long)np * np;
-    scale_div_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(tot, h->dG, lin_ell2, h->dK);   // cov!(cK, LinIso, D)
+    scale_div_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(tot, h->dG, lin_ell2, h->dK); ++g_kernel_launches;   // cov!(cK, LinIso, D)
     add_spatial_blocks(h, k, h->dK);                                                                        // addcov!
     launch_add_diag(c->stream, h->dK, np, n, std::max(std::exp(2.0 * log_noise), 1e-8));                    // add_diag!
     if (np > n) launch_add_diag(c->stream, h->dK + (size_t)n * np + n, np, np - n, 1.0);
@@ -274,9 +274,9 @@ int geordd_multigp_mll_grad(geordd_multigp* h, const geordd_kernel* k, double li
         for (int g = 0; g < ngroups; ++g) {
             const int a = h->group_off[g], ng = h->group_off[g + 1] - a;
             grad_reduce_kernel<<<blk_off[g + 1] - blk_off[g], 256, 0, st>>>(to_dev(*k), h->dX, h->dim, a, ng, h->dAlpha, h->dB,
-                                                                           h->dG, np, part + (size_t)blk_off[g] * 4);
+                                                                           h->dG, np, part + (size_t)blk_off[g] * 4); ++g_kernel_launches;
         }
-        beta_reduce_kernel<<<n, 256, 0, st>>>(n, h->dAlpha, h->dB, h->dG, np, part + (size_t)nblk * 4);
+        beta_reduce_kernel<<<n, 256, 0, st>>>(n, h->dAlpha, h->dB, h->dG, np, part + (size_t)nblk * 4); ++g_kernel_launches;
         launch_reduce(st, 1, h->dAlpha, nullptr, 0, n, 0, c__->d_scal + 3);
         GD_CUDA(cudaMemcpyAsync(hp.data(), part, hp.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
         check_abort(c__);

@@ -37,11 +37,11 @@ int geordd_bench_dmma_peak(geordd_ctx* c, double* tflops) {
         const int iters = 4096, ctas = c->sched.num_sms * 4;
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
-        dmma_peak_kernel<<<ctas, 256, 0, c->stream>>>(64, c->d_scal + 8);
+        dmma_peak_kernel<<<ctas, 256, 0, c->stream>>>(64, c->d_scal + 8); ++g_kernel_launches;
         float best = 1e30f;
         for (int r = 0; r < 5; ++r) {
             cudaEventRecord(e0, c->stream);
-            dmma_peak_kernel<<<ctas, 256, 0, c->stream>>>(iters, c->d_scal + 8);
+            dmma_peak_kernel<<<ctas, 256, 0, c->stream>>>(iters, c->d_scal + 8); ++g_kernel_launches;
             cudaEventRecord(e1, c->stream);
             GD_CUDA(cudaStreamSynchronize(c->stream));
             float ms = 0.f;

@@ -122,10 +122,10 @@ void launch_cov(cudaStream_t st, const KernelSpecDev& spec, const double* X1, in
     int tb1 = (n1p + CT - 1) / CT, tb2 = (n2p + CT - 1) / CT;
     if (sym) {
         int nt = tb1 * (tb1 + 1) / 2;
-        cov_kernel<<<nt, 256, 0, st>>>(p);
+        cov_kernel<<<nt, 256, 0, st>>>(p); ++g_kernel_launches;
     } else {
         dim3 grid(tb1, tb2);
-        cov_kernel<<<grid, 256, 0, st>>>(p);
+        cov_kernel<<<grid, 256, 0, st>>>(p); ++g_kernel_launches;
     }
 }
 

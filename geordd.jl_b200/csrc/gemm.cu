@@ -75,11 +75,11 @@ static void launch_t(cudaStream_t st, int M, int N, int K, double alpha, const d
     dim3 grid(M / TILE, N / 64, splitk);
     long ws_stride = (long)ldc * N;
     gemm_kernel<A_MC, B_NC><<<grid, NTHREADS, ML::SMEM_BYTES, st>>>(K, alpha, A, lda, B, ldb, beta, C, ldc, splitk, ws,
-                                                                   ws_stride);
+                                                                   ws_stride); ++g_kernel_launches;
     if (splitk > 1) {
         long tot = (long)M * N;
         splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(M, N, alpha, beta, C, ldc, splitk, ws,
-                                                                          ws_stride);
+                                                                          ws_stride); ++g_kernel_launches;
     }
 }
 

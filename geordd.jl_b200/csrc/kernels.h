@@ -27,6 +27,9 @@ struct Sched {
     int num_sms;
 };
 
+// Number of kernels this library has launched (bench.py reports it as gpu_launches).
+extern long long g_kernel_launches;
+
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // ---- cov.cu ---------------------------------------------------------------------------------------

@@ -151,7 +151,7 @@ void launch_potrf(cudaStream_t st, Sched& sched, const double* A, double* L, lon
     sched.epoch++;
     int grid = njobs < sched.num_sms ? njobs : sched.num_sms;
     potrf_dataflow_kernel<<<grid, NTHREADS, POTRF_SMEM, st>>>(A, L, ld, T, sched.jobs, njobs, sched.flags, sched.epoch,
-                                                              sched.counter, sched.abort_word);
+                                                              sched.counter, sched.abort_word); ++g_kernel_launches;
 }
 
 __global__ void logdiag_sum_kernel(const double* __restrict__ L, long ld, int n, double* out) {
@@ -169,7 +169,7 @@ __global__ void logdiag_sum_kernel(const double* __restrict__ L, long ld, int n,
 }
 
 void launch_logdiag_sum(cudaStream_t st, const double* L, long ld, int n, double* out) {
-    logdiag_sum_kernel<<<1, 1024, 0, st>>>(L, ld, n, out);
+    logdiag_sum_kernel<<<1, 1024, 0, st>>>(L, ld, n, out); ++g_kernel_launches;
 }
 
 }  // namespace geordd

@@ -57,7 +57,7 @@ __global__ void philox_normals_kernel(unsigned long long seed, unsigned long lon
 void launch_philox_normals(cudaStream_t st, unsigned long long seed, unsigned long long draw0, int ndraws, int n,
                            double* Z, long ldz, int npad) {
     long tot = (long)(npad / 2) * ndraws;
-    philox_normals_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(seed, draw0, ndraws, n, Z, ldz, npad);
+    philox_normals_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(seed, draw0, ndraws, n, Z, ldz, npad); ++g_kernel_launches;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -99,7 +99,7 @@ __global__ void finish_mll_kernel(FinishMll f) {
     block_tally(hit, f.tally);
 }
 void launch_finish_mll(cudaStream_t st, const FinishMll& f) {
-    finish_mll_kernel<<<(unsigned)((f.ndraws + 255) / 256), 256, 0, st>>>(f);
+    finish_mll_kernel<<<(unsigned)((f.ndraws + 255) / 256), 256, 0, st>>>(f); ++g_kernel_launches;
 }
 
 // chi2 = dot(mu, Sigma \ mu) (src/hypotest_chi2.jl:16); invvar: tau = sum(Sigma\mu)/denom,
@@ -131,7 +131,7 @@ __global__ void finish_cliff_kernel(FinishCliff f) {
     if (f.part_num) block_tally(hit_inv, f.tally_inv);
 }
 void launch_finish_cliff(cudaStream_t st, const FinishCliff& f) {
-    finish_cliff_kernel<<<(unsigned)((f.ndraws + 255) / 256), 256, 0, st>>>(f);
+    finish_cliff_kernel<<<(unsigned)((f.ndraws + 255) / 256), 256, 0, st>>>(f); ++g_kernel_launches;
 }
 
 // out[s] = mean(ref .> x[s]) (greater != 0) or mean(ref .< x[s])   (src/power.jl:31,35,40)
@@ -151,7 +151,7 @@ __global__ void frac_compare_kernel(const double* ref, long nref, const double* 
 }
 void launch_frac_compare(cudaStream_t st, const double* ref, long nref, const double* x, long n, bool greater,
                          double* out) {
-    if (n > 0) frac_compare_kernel<<<(unsigned)n, 256, 0, st>>>(ref, nref, x, n, greater ? 1 : 0, out);
+    if (n > 0) frac_compare_kernel<<<(unsigned)n, 256, 0, st>>>(ref, nref, x, n, greater ? 1 : 0, out); ++g_kernel_launches;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(1024) lu_solve_kernel(double* A, long lda, int
 }
 void launch_lu_solve(cudaStream_t st, double* A, long lda, int n, double* B, long ldb, int nrhs, int* info) {
     cudaMemsetAsync(info, 0, sizeof(int), st);
-    lu_solve_kernel<<<1, 1024, 0, st>>>(A, lda, n, B, ldb, nrhs, info);
+    lu_solve_kernel<<<1, 1024, 0, st>>>(A, lda, n, B, ldb, nrhs, info); ++g_kernel_launches;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -254,7 +254,7 @@ __global__ void fill_kernel(double* p, long n, double v) {
     if (i < n) p[i] = v;
 }
 void launch_fill(cudaStream_t st, double* p, long n, double v) {
-    if (n > 0) fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, v);
+    if (n > 0) fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, v); ++g_kernel_launches;
 }
 
 // dst(r, c) = src(r, c) for r < rows, c < cols; optional transpose of the source.
@@ -283,7 +283,7 @@ void launch_copy2d(cudaStream_t st, double* dst, long ldd, const double* src, lo
                    bool trans) {
     if (rows <= 0 || cols <= 0) return;
     dim3 grid((rows + 31) / 32, (cols + 31) / 32), block(32, 8);
-    copy2d_kernel<<<grid, block, 0, st>>>(dst, ldd, src, lds, rows, cols, trans ? 1 : 0);
+    copy2d_kernel<<<grid, block, 0, st>>>(dst, ldd, src, lds, rows, cols, trans ? 1 : 0); ++g_kernel_launches;
 }
 
 // A(i,i) += v for i < n
@@ -292,7 +292,7 @@ __global__ void add_diag_kernel(double* A, long ld, int n, double v) {
     if (i < n) A[(long)i * ld + i] += v;
 }
 void launch_add_diag(cudaStream_t st, double* A, long ld, int n, double v) {
-    if (n > 0) add_diag_kernel<<<(n + 255) / 256, 256, 0, st>>>(A, ld, n, v);
+    if (n > 0) add_diag_kernel<<<(n + 255) / 256, 256, 0, st>>>(A, ld, n, v); ++g_kernel_launches;
 }
 
 // Single-block reductions: mode 0 trace(A), 1 sum(x), 2 dot(x,y), 3 sum of all entries of A (n x n2)
@@ -313,7 +313,7 @@ __global__ void reduce_kernel(int mode, const double* x, const double* y, long l
     }
 }
 void launch_reduce(cudaStream_t st, int mode, const double* x, const double* y, long ld, long n, long n2, double* out) {
-    reduce_kernel<<<1, 1024, 0, st>>>(mode, x, y, ld, n, n2, out);
+    reduce_kernel<<<1, 1024, 0, st>>>(mode, x, y, ld, n, n2, out); ++g_kernel_launches;
 }
 
 // M(r, c) += v for r < rows, c < cols
@@ -324,7 +324,7 @@ __global__ void add_const_kernel(double* M, long ld, int rows, long cols, double
 }
 void launch_add_const(cudaStream_t st, double* M, long ld, int rows, long cols, double v) {
     long tot = (long)rows * cols;
-    if (tot > 0 && v != 0.0) add_const_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(M, ld, rows, cols, v);
+    if (tot > 0 && v != 0.0) add_const_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(M, ld, rows, cols, v); ++g_kernel_launches;
 }
 
 // y = a*x + b*y elementwise over n
@@ -333,7 +333,7 @@ __global__ void axpby_kernel(long n, double a, const double* x, double b, double
     if (i < n) y[i] = a * x[i] + (b != 0.0 ? b * y[i] : 0.0);
 }
 void launch_axpby(cudaStream_t st, long n, double a, const double* x, double b, double* y) {
-    if (n > 0) axpby_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, a, x, b, y);
+    if (n > 0) axpby_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, a, x, b, y); ++g_kernel_launches;
 }
 
 // Mirror the lower triangle of an n x n matrix into the upper (copytri!)
@@ -345,7 +345,7 @@ __global__ void mirror_lower_kernel(double* A, long ld, int n) {
 }
 void launch_mirror_lower(cudaStream_t st, double* A, long ld, int n) {
     long tot = (long)n * n;
-    if (tot > 0) mirror_lower_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(A, ld, n);
+    if (tot > 0) mirror_lower_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(A, ld, n); ++g_kernel_launches;
 }
 
 }  // namespace geordd

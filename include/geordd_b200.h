@@ -54,6 +54,8 @@ typedef struct {
 } geordd_kernel;
 
 GEORDD_API int geordd_version(void);
+/* Total number of CUDA kernels this library has launched in this process. */
+GEORDD_API long long geordd_launch_count(void);
 
 /* ---- context ------------------------------------------------------------------------------- */
 GEORDD_API int geordd_ctx_create(geordd_ctx** out, int device);

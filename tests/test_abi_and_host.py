@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol(G):
     hdr = open(os.path.join(ROOT, "include", "geordd_b200.h")).read()
-    declared = set(re.findall(r"GEORDD_API\s+(?:const\s+char\s*\*|int)\s+(geordd_\w+)\s*\(", hdr))
+    declared = set(re.findall(r"GEORDD_API\s+(?:const\s+char\s*\*|int|long long)\s+(geordd_\w+)\s*\(", hdr))
     assert len(declared) >= 40
     lib = G.capi.load_library()
     for name in sorted(declared):
