@@ -43,7 +43,12 @@ static void prof_collect(geordd_ctx* c) {
 }
 
 // ---- small helpers ---------------------------------------------------------------------------------
-void ctx_use(geordd_ctx* c) { GD_CUDA(cudaSetDevice(c->device)); }
+static thread_local geordd_ctx* tl_ctx = nullptr;
+
+void ctx_use(geordd_ctx* c) {
+    GD_CUDA(cudaSetDevice(c->device));
+    tl_ctx = c;
+}
 
 int ctx_fail(geordd_ctx* c, const ApiError& e) {
     if (c) c->err = e.what();
@@ -78,13 +83,68 @@ void download2d(geordd_ctx* c, double* dst, long ldd, const double* src, long ld
                               cudaMemcpyDeviceToHost, c->stream));
 }
 
+static const size_t kPoolCapBytes = (size_t)64 << 30;
+
+static void pool_trim(geordd_ctx* c, size_t keep_bytes) {
+    while (c->pool_cached_bytes > keep_bytes && !c->pool_free.empty()) {
+        auto it = std::prev(c->pool_free.end());   // largest first
+        cudaFree(it->second);
+        c->pool_cached_bytes -= it->first;
+        c->pool_free.erase(it);
+    }
+}
+
 double* dalloc(size_t count, cudaStream_t st, bool zero) {
-    double* p = nullptr;
+    geordd_ctx* c = tl_ctx;
     if (count == 0) count = 1;
-    cudaError_t e = cudaMalloc(&p, count * sizeof(double));
-    if (e != cudaSuccess) throw ApiError(GEORDD_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    size_t bytes = (count * sizeof(double) + 511) / 512 * 512;
+    void* p = nullptr;
+    if (c) {
+        auto it = c->pool_free.lower_bound(bytes);
+        if (it != c->pool_free.end() && it->first <= bytes + bytes / 4 + (1u << 20)) {
+            p = it->second;
+            bytes = it->first;
+            c->pool_cached_bytes -= it->first;
+            c->pool_free.erase(it);
+        }
+    }
+    if (!p) {
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess && c) {   // give cached blocks back to the driver and retry once
+            cudaGetLastError();
+            cudaStreamSynchronize(c->stream);
+            pool_trim(c, 0);
+            e = cudaMalloc(&p, bytes);
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            throw ApiError(GEORDD_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        }
+    }
+    if (c) c->pool_live[p] = bytes;
     if (zero) GD_CUDA(cudaMemsetAsync(p, 0, count * sizeof(double), st));
-    return p;
+    return (double*)p;
+}
+
+// All work of a context is on one stream, so a block handed back here can be reused by later launches on that
+// stream without waiting for the earlier ones.
+void dfree(void* p) {
+    if (!p) return;
+    geordd_ctx* c = tl_ctx;
+    if (c) {
+        auto it = c->pool_live.find(p);
+        if (it != c->pool_live.end()) {
+            c->pool_free.emplace(it->second, p);
+            c->pool_cached_bytes += it->second;
+            c->pool_live.erase(it);
+            if (c->pool_cached_bytes > kPoolCapBytes) {
+                cudaStreamSynchronize(c->stream);
+                pool_trim(c, kPoolCapBytes / 2);
+            }
+            return;
+        }
+    }
+    cudaFree(p);
 }
 
 void ensure_ws(geordd_ctx* c, size_t count) { c->ws.ensure(count, c->stream, false); }
@@ -135,6 +195,8 @@ int make_posdef(geordd_ctx* c, double* K, double* L, long ld, int n, int npad, i
         if (info < 0) throw ApiError(GEORDD_ERR_WATCHDOG, "potrf watchdog fired");
         if (info == 0) {
             if (rounds) *rounds = nr;
+            ProfScope ps(c, PC_MISC);
+            launch_mirror_factor(c->stream, L, ld, npad);
             return 0;
         }
         if (attempt == 10) {
@@ -167,7 +229,7 @@ void pd_solve(geordd_ctx* c, const double* L, long ldl, int npad, double* B, lon
 // ---- GP ----------------------------------------------------------------------------------------------
 void gp_free(geordd_gp* gp) {
     if (!gp) return;
-    cudaFree(gp->dX); cudaFree(gp->dK); cudaFree(gp->dL); cudaFree(gp->dR); cudaFree(gp->dAlpha);
+    dfree(gp->dX); dfree(gp->dK); dfree(gp->dL); dfree(gp->dR); dfree(gp->dAlpha);
     delete gp;
 }
 
@@ -317,7 +379,12 @@ int geordd_ctx_destroy(geordd_ctx* c) {
     cudaFree(c->sched.counter); cudaFree(c->sched.flags); cudaFree(c->sched.abort_word); cudaFree(c->sched.jobs);
     cudaFree(c->d_scal); cudaFreeHost(c->h_scal); cudaFree(c->d_info); cudaFreeHost(c->h_info);
     cudaFree(c->d_tally); cudaFreeHost(c->h_tally);
+    tl_ctx = c;
     c->ws.release(); c->tmp0.release(); c->tmp1.release(); c->tmp2.release(); c->tmp3.release();
+    pool_trim(c, 0);
+    for (auto& kv : c->pool_live) cudaFree(kv.first);
+    c->pool_live.clear();
+    tl_ctx = nullptr;
     cudaStreamDestroy(c->own_stream);
     delete c;
     return 0;
@@ -385,10 +452,10 @@ int geordd_cov_sym(geordd_ctx* c, const geordd_kernel* k, const double* X, int d
         GD_CUDA(cudaMemcpyAsync(K, dK, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         GD_CUDA(cudaStreamSynchronize(c->stream));
     } catch (...) {
-        cudaFree(dX); cudaFree(dK);
+        dfree(dX); dfree(dK);
         throw;
     }
-    cudaFree(dX); cudaFree(dK);
+    dfree(dX); dfree(dK);
     API_END
 }
 
@@ -411,10 +478,10 @@ int geordd_cov_cross(geordd_ctx* c, const geordd_kernel* k, const double* X1, in
         GD_CUDA(cudaMemcpyAsync(K, dK, (size_t)n1 * n2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         GD_CUDA(cudaStreamSynchronize(c->stream));
     } catch (...) {
-        cudaFree(d1); cudaFree(d2); cudaFree(dK);
+        dfree(d1); dfree(d2); dfree(dK);
         throw;
     }
-    cudaFree(d1); cudaFree(d2); cudaFree(dK);
+    dfree(d1); dfree(d2); dfree(dK);
     API_END
 }
 
@@ -469,7 +536,7 @@ int geordd_gp_nobs(const geordd_gp* gp) { return gp ? gp->n : GEORDD_ERR_ARG; }
 
 int geordd_gp_destroy(geordd_gp* gp) {
     if (!gp) return 0;
-    cudaSetDevice(gp->ctx->device);
+    try { geordd::ctx_use(gp->ctx); } catch (...) { return GEORDD_ERR_CUDA; }
     cudaStreamSynchronize(gp->ctx->stream);
     gp_free(gp);
     return 0;
@@ -488,10 +555,10 @@ int geordd_dbg_normals(geordd_ctx* c, unsigned long long seed, unsigned long lon
         download2d(c, Z, n, dZ, npad, n, ndraws);
         GD_CUDA(cudaStreamSynchronize(c->stream));
     } catch (...) {
-        cudaFree(dZ);
+        dfree(dZ);
         throw;
     }
-    cudaFree(dZ);
+    dfree(dZ);
     API_END
 }
 
@@ -517,10 +584,10 @@ int geordd_dbg_gemm(geordd_ctx* c, int transa, int transb, int M, int N, int K, 
         GD_CUDA(cudaStreamSynchronize(c->stream));
         GD_CUDA(cudaGetLastError());
     } catch (...) {
-        cudaFree(dA); cudaFree(dB); cudaFree(dC);
+        dfree(dA); dfree(dB); dfree(dC);
         throw;
     }
-    cudaFree(dA); cudaFree(dB); cudaFree(dC);
+    dfree(dA); dfree(dB); dfree(dC);
     API_END
 }
 
@@ -563,10 +630,10 @@ int geordd_dbg_potrf(geordd_ctx* c, const double* A, int n, double* L, double* m
         for (int j = 0; j < n; ++j)
             for (int i = 0; i < n; ++i) L[(size_t)j * n + i] = (i >= j) ? tmp[(size_t)j * n + i] : 0.0;
     } catch (...) {
-        cudaFree(dA); cudaFree(dL);
+        dfree(dA); dfree(dL);
         throw;
     }
-    cudaFree(dA); cudaFree(dL);
+    dfree(dA); dfree(dL);
     if (info > 0) return info;
     API_END
 }
@@ -580,6 +647,7 @@ int geordd_dbg_trsm(geordd_ctx* c, int mode, const double* L, int n, double* B, 
         dL = dalloc((size_t)npad * npad, c->stream, false);
         dB = dalloc((size_t)npad * ncols, c->stream, true);
         upload_spd_padded(c, dL, npad, L, n);
+        launch_mirror_factor(c->stream, dL, npad, npad);
         upload2d(c, dB, npad, B, n, n, nrhs);
         SolveEpilogue epi;
         if (mode == 2) {
@@ -600,10 +668,10 @@ int geordd_dbg_trsm(geordd_ctx* c, int mode, const double* L, int n, double* B, 
         download2d(c, B, n, mode == 2 ? dO : dB, npad, n, nrhs);
         GD_CUDA(cudaStreamSynchronize(c->stream));
     } catch (...) {
-        cudaFree(dL); cudaFree(dB); cudaFree(dO);
+        dfree(dL); dfree(dB); dfree(dO);
         throw;
     }
-    cudaFree(dL); cudaFree(dB); cudaFree(dO);
+    dfree(dL); dfree(dB); dfree(dO);
     API_END
 }
 

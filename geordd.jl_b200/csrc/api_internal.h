@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <string>
 #include <vector>
+#include <map>
+#include <unordered_map>
 #include <stdexcept>
 #include <cstdio>
 #include <cstring>
@@ -28,23 +30,23 @@ struct ApiError : std::runtime_error {
             throw geordd::ApiError(GEORDD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
     } while (0)
 
+// Device memory comes from a per-context caching pool (api_core.cu): fits and null handles are created and
+// destroyed repeatedly by callers (placebo sweeps, boot_* drivers), cudaMalloc/cudaFree would serialise them.
+double* dalloc(size_t count, cudaStream_t st, bool zero);
+void dfree(void* p);
+
 struct DevBuf {
     double* p = nullptr;
     size_t n = 0;
     void ensure(size_t count, cudaStream_t st, bool zero) {
         if (count > n) {
             release();
-            cudaError_t e = cudaMalloc(&p, count * sizeof(double));
-            if (e != cudaSuccess) {
-                p = nullptr;
-                throw ApiError(GEORDD_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
-            }
+            p = dalloc(count, st, zero);
             n = count;
-            if (zero) GD_CUDA(cudaMemsetAsync(p, 0, count * sizeof(double), st));
         }
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) dfree(p);
         p = nullptr;
         n = 0;
     }
@@ -58,6 +60,10 @@ struct geordd_ctx {
     geordd::Sched sched{};
     std::string err;
     long max_batch = 0;
+    // caching device-memory pool
+    std::multimap<size_t, void*> pool_free;
+    std::unordered_map<void*, size_t> pool_live;
+    size_t pool_cached_bytes = 0;
     // small device / pinned-host scratch
     double* d_scal = nullptr;                 // 64 doubles
     double* h_scal = nullptr;                 // pinned
@@ -147,7 +153,6 @@ void check_abort(geordd_ctx* c);                   // sync + throw on watchdog
 double read_scalar(geordd_ctx* c, const double* d);   // sync D2H of one double
 void upload2d(geordd_ctx* c, double* dst, long ldd, const double* src, long lds, int rows, int cols);
 void download2d(geordd_ctx* c, double* dst, long ldd, const double* src, long lds, int rows, int cols);
-double* dalloc(size_t count, cudaStream_t st, bool zero);
 void ensure_ws(geordd_ctx* c, size_t count);
 
 KernelSpecDev to_dev(const geordd_kernel& k);

@@ -105,8 +105,8 @@ beta_reduce_kernel(int n, const double* __restrict__ alpha, const double* __rest
 
 static void mg_free(geordd_multigp* h) {
     if (!h) return;
-    cudaFree(h->dD); cudaFree(h->dX); cudaFree(h->dG); cudaFree(h->dK); cudaFree(h->dL); cudaFree(h->dB);
-    cudaFree(h->dY); cudaFree(h->dR); cudaFree(h->dAlpha);
+    dfree(h->dD); dfree(h->dX); dfree(h->dG); dfree(h->dK); dfree(h->dL); dfree(h->dB);
+    dfree(h->dY); dfree(h->dR); dfree(h->dAlpha);
     delete h;
 }
 
@@ -281,10 +281,10 @@ int geordd_multigp_mll_grad(geordd_multigp* h, const geordd_kernel* k, double li
         GD_CUDA(cudaMemcpyAsync(hp.data(), part, hp.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
         check_abort(c__);
     } catch (...) {
-        cudaFree(part);
+        dfree(part);
         throw;
     }
-    cudaFree(part);
+    dfree(part);
     const double sum_alpha = read_scalar(c__, c__->d_scal + 3);
     double sk[3] = {0, 0, 0}, sG = 0.0, trB = 0.0;
     for (int b = 0; b < nblk; ++b)
@@ -332,6 +332,7 @@ int geordd_multigp_postmean_beta(geordd_multigp* h, const geordd_kernel* k, doub
         c__->err = "Sigma_Y|beta is not positive definite";
         return info;
     }
+    launch_mirror_factor(st, h->dL, np, np);
     double *W = nullptr, *prec = nullptr, *rhs = nullptr, *v = nullptr;
     try {
         // W = L^-1 D'  (n x p): X_invA_Xt(Sigma, D) = W'W   (:337)
@@ -370,16 +371,16 @@ int geordd_multigp_postmean_beta(geordd_multigp* h, const geordd_kernel* k, doub
         GD_CUDA(cudaMemcpyAsync(beta_hat, v, (size_t)p * sizeof(double), cudaMemcpyDeviceToHost, st));
         check_abort(c__);
     } catch (...) {
-        cudaFree(W); cudaFree(prec); cudaFree(rhs); cudaFree(v);
+        dfree(W); dfree(prec); dfree(rhs); dfree(v);
         throw;
     }
-    cudaFree(W); cudaFree(prec); cudaFree(rhs); cudaFree(v);
+    dfree(W); dfree(prec); dfree(rhs); dfree(v);
     API_END
 }
 
 int geordd_multigp_destroy(geordd_multigp* h) {
     if (!h) return 0;
-    cudaSetDevice(h->ctx->device);
+    try { geordd::ctx_use(h->ctx); } catch (...) { return GEORDD_ERR_CUDA; }
     cudaStreamSynchronize(h->ctx->stream);
     geordd::mg_free(h);
     return 0;

@@ -64,7 +64,7 @@ static void check_pair(geordd_gp* T, geordd_gp* C) {
 struct CliffTmp {
     double *dXb = nullptr, *dMu = nullptr, *dSig = nullptr;
     int nb = 0, nbp = 0;
-    ~CliffTmp() { cudaFree(dXb); cudaFree(dMu); cudaFree(dSig); }
+    ~CliffTmp() { dfree(dXb); dfree(dMu); dfree(dSig); }
 };
 static void cliff_tmp(geordd_gp* T, geordd_gp* C, const double* Xb, int nb, CliffTmp& t) {
     geordd_ctx* c = T->ctx;
@@ -140,17 +140,17 @@ static void calib_cov_mu_delta(geordd_gp* T, geordd_gp* C, const double* dXb, in
         }
         GD_CUDA(cudaStreamSynchronize(c->stream));
     } catch (...) {
-        cudaFree(WT); cudaFree(WC); cudaFree(P); cudaFree(KCT); cudaFree(E);
+        dfree(WT); dfree(WC); dfree(P); dfree(KCT); dfree(E);
         throw;
     }
-    cudaFree(WT); cudaFree(WC); cudaFree(P); cudaFree(KCT); cudaFree(E);
+    dfree(WT); dfree(WC); dfree(P); dfree(KCT); dfree(E);
 }
 
 // ---- null handle ---------------------------------------------------------------------------------------
 static void null_free(geordd_null* h) {
     if (!h) return;
     if (h->N) gp_free(h->N);
-    cudaFree(h->dXb); cudaFree(h->dKbT); cudaFree(h->dKbC); cudaFree(h->dSig); cudaFree(h->dLSig); cudaFree(h->dOnes);
+    dfree(h->dXb); dfree(h->dKbT); dfree(h->dKbC); dfree(h->dSig); dfree(h->dLSig); dfree(h->dOnes);
     h->Z.release(); h->RN.release(); h->AN.release(); h->AT.release(); h->AC.release(); h->M.release(); h->W.release();
     h->partN.release(); h->partT.release(); h->partC.release(); h->partChi.release(); h->partNum.release();
     h->oChi.release(); h->oPval.release(); h->oNum.release(); h->oNull.release(); h->oAlt.release();
@@ -350,12 +350,12 @@ static double null_cov_mu_tau(geordd_null* h, bool as_shipped) {
         gemm(c, true, false, nbp, 64, nbp, 1.0, cmd, nbp, one, nbp, 0.0, v, nbp, 1);
         launch_reduce(c->stream, 1, v, nullptr, 0, nb, 0, c->d_scal + 4);
         out = read_scalar(c, c->d_scal + 4);
-        cudaFree(v);
+        dfree(v);
     } catch (...) {
-        cudaFree(cmd); cudaFree(one);
+        dfree(cmd); dfree(one);
         throw;
     }
-    cudaFree(cmd); cudaFree(one);
+    dfree(cmd); dfree(one);
     h->cov_mu_tau[idx] = out;
     h->calib_ready[idx] = true;
     return out;
@@ -397,10 +397,10 @@ int geordd_gp_predict_mu(geordd_gp* gp, const double* Xb, int nb, double* mu) {
         GD_CUDA(cudaMemcpyAsync(mu, dMu, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, c__->stream));
         GD_CUDA(cudaStreamSynchronize(c__->stream));
     } catch (...) {
-        cudaFree(dXb); cudaFree(dMu);
+        dfree(dXb); dfree(dMu);
         throw;
     }
-    cudaFree(dXb); cudaFree(dMu);
+    dfree(dXb); dfree(dMu);
     API_END
 }
 
@@ -431,10 +431,10 @@ int geordd_chistat_obs(geordd_gp* T, geordd_gp* C, const double* Xb, int nb, dou
         check_abort(c__);
         *chi2 = read_scalar(c__, c__->d_scal);
     } catch (...) {
-        cudaFree(x);
+        dfree(x);
         throw;
     }
-    cudaFree(x);
+    dfree(x);
     API_END
 }
 
@@ -454,10 +454,10 @@ static void invvar_dev(geordd_ctx* c, double* dSig, const double* dMu, int nb, i
         *tau = num / denom;
         *var = 1.0 / denom;
     } catch (...) {
-        cudaFree(rhs);
+        dfree(rhs);
         throw;
     }
-    cudaFree(rhs);
+    dfree(rhs);
 }
 
 int geordd_invvar_obs(geordd_gp* T, geordd_gp* C, const double* Xb, int nb, double nugget, double* tau_hat,
@@ -488,10 +488,10 @@ int geordd_inverse_variance(geordd_ctx* c, const double* mu, const double* Sigma
         GD_CUDA(cudaMemcpyAsync(dM, mu, (size_t)nb * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         invvar_dev(c, dS, dM, nb, nbp, nugget, tau_hat, var_tau);
     } catch (...) {
-        cudaFree(dS); cudaFree(dM);
+        dfree(dS); dfree(dM);
         throw;
     }
-    cudaFree(dS); cudaFree(dM);
+    dfree(dS); dfree(dM);
     API_END
 }
 
@@ -514,10 +514,10 @@ int geordd_solve_general(geordd_ctx* c, const double* A, int n, double* B, int n
         GD_CUDA(cudaGetLastError());
         if (c->h_info[1] != 0) throw ApiError(GEORDD_ERR_ARG, "solve_general: matrix is singular");   // SingularException
     } catch (...) {
-        cudaFree(dA); cudaFree(dB);
+        dfree(dA); dfree(dB);
         throw;
     }
-    cudaFree(dA); cudaFree(dB);
+    dfree(dA); dfree(dB);
     API_END
 }
 
@@ -546,10 +546,10 @@ int geordd_weight_at_units(geordd_gp* gp, const double* Xb, int nb, const double
         GD_CUDA(cudaMemcpyAsync(w_unit, out, (size_t)gp->n * sizeof(double), cudaMemcpyDeviceToHost, c__->stream));
         check_abort(c__);
     } catch (...) {
-        cudaFree(dXb); cudaFree(KXb); cudaFree(w); cudaFree(out);
+        dfree(dXb); dfree(KXb); dfree(w); dfree(out);
         throw;
     }
-    cudaFree(dXb); cudaFree(KXb); cudaFree(w); cudaFree(out);
+    dfree(dXb); dfree(KXb); dfree(w); dfree(out);
     API_END
 }
 
@@ -585,10 +585,10 @@ int geordd_invvar_calib(geordd_gp* T, geordd_gp* C, const double* Xb, int nb, do
         double z = std::fabs(num) / std::sqrt(cov_mt);
         *pval = 2.0 * (std::erfc(z * 0.7071067811865476) / 2.0);
     } catch (...) {
-        cudaFree(rhs);
+        dfree(rhs);
         throw;
     }
-    cudaFree(rhs);
+    dfree(rhs);
     API_END
 }
 
@@ -597,7 +597,7 @@ static int null_set_sentinels(geordd_null* h, const double* Xb, int nb, double n
     geordd_gp *T = h->T, *C = h->C;
     check_pair(T, C);
     if (!Xb || nb <= 0) throw ApiError(GEORDD_ERR_ARG, "sentinels missing");
-    cudaFree(h->dXb); cudaFree(h->dKbT); cudaFree(h->dKbC); cudaFree(h->dSig); cudaFree(h->dLSig); cudaFree(h->dOnes);
+    dfree(h->dXb); dfree(h->dKbT); dfree(h->dKbC); dfree(h->dSig); dfree(h->dLSig); dfree(h->dOnes);
     h->dXb = h->dKbT = h->dKbC = h->dSig = h->dLSig = h->dOnes = nullptr;
     if (round_up(nb, TILE) != h->nbp) {   // sentinel-sized simulation buffers must be re-made
         h->M.release(); h->W.release(); h->partChi.release(); h->partNum.release();
@@ -616,10 +616,10 @@ static int null_set_sentinels(geordd_null* h, const double* Xb, int nb, double n
     try {
         cliff_face_dev(T, C, h->dXb, nb, nbp, mu, h->dSig);
     } catch (...) {
-        cudaFree(mu);
+        dfree(mu);
         throw;
     }
-    cudaFree(mu);
+    dfree(mu);
     if (nugget != 0.0) launch_add_diag(c->stream, h->dSig, nbp, nb, nugget);
     int info = make_posdef(c, h->dSig, h->dLSig, nbp, nb, nbp, &h->jitter_rounds);
     if (info != 0) {
@@ -645,10 +645,10 @@ static int null_set_sentinels(geordd_null* h, const double* Xb, int nb, double n
         check_abort(c);
         h->denom = read_scalar(c, c->d_scal + 2);
     } catch (...) {
-        cudaFree(slab);
+        dfree(slab);
         throw;
     }
-    cudaFree(slab);
+    dfree(slab);
     h->nb = nb;
     return 0;
 }
@@ -739,10 +739,10 @@ int geordd_gp_prior_rand(geordd_gp* gp, long nsim, unsigned long long seed, unsi
         download2d(c__, Y, n, dY, np, n, (int)nsim);
         check_abort(c__);
     } catch (...) {
-        cudaFree(dZ); cudaFree(dY);
+        dfree(dZ); dfree(dY);
         throw;
     }
-    cudaFree(dZ); cudaFree(dY);
+    dfree(dZ); dfree(dY);
     API_END
 }
 
@@ -837,16 +837,16 @@ int geordd_power(geordd_null* h, double tau, long nsim, unsigned long long seed,
             out5[5 * s + 4] = 2.0 * (std::erfc(z * 0.7071067811865476) / 2.0);
         }
     } catch (...) {
-        cudaFree(ref); cudaFree(dm); cudaFree(o);
+        dfree(ref); dfree(dm); dfree(o);
         throw;
     }
-    cudaFree(ref); cudaFree(dm); cudaFree(o);
+    dfree(ref); dfree(dm); dfree(o);
     API_END
 }
 
 int geordd_null_destroy(geordd_null* h) {
     if (!h) return 0;
-    cudaSetDevice(h->ctx->device);
+    try { geordd::ctx_use(h->ctx); } catch (...) { return GEORDD_ERR_CUDA; }
     cudaStreamSynchronize(h->ctx->stream);
     geordd::null_free(h);
     return 0;

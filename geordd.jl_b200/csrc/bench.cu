@@ -101,10 +101,10 @@ int geordd_bench_potrf(geordd_ctx* c, int n, int reps, double* ms_best, double* 
         if (ms_best) *ms_best = best;
         if (ms_mean) *ms_mean = sum / reps;
     } catch (const ApiError& e) {
-        cudaFree(dX); cudaFree(dK); cudaFree(dL);
+        dfree(dX); dfree(dK); dfree(dL);
         return ctx_fail(c, e);
     }
-    cudaFree(dX); cudaFree(dK); cudaFree(dL);
+    dfree(dX); dfree(dK); dfree(dL);
     return 0;
 }
 

@@ -43,10 +43,8 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
 __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ int ld_volatile_int(const int* p) {
-    int v;
-    asm volatile("ld.volatile.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ int ld_volatile_int(const int* p) {   // generic address (global or shared)
+    return *reinterpret_cast<const volatile int*>(p);
 }
 
 // Spin (one thread) until *flag == epoch.  A watchdog turns a scheduling bug into an error code
@@ -69,5 +67,57 @@ __device__ __forceinline__ bool wait_flag(const unsigned* flag, unsigned epoch, 
 }
 
 __device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }
+
+// ---- mbarrier + bulk async copy (TMA unit, SASS UBLKCP) ---------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+// Orders generic-proxy accesses (ld/st, flag acquire) before subsequent async-proxy (bulk copy) accesses.
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
+    unsigned done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+// Wait for the phase with the given parity.  Polls the abort word so that an error / watchdog anywhere
+// releases every waiter (returns false).
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, unsigned parity, int* abort_word) {
+    if (mbar_try_wait(bar, parity)) return true;
+    long long t0 = clock64();
+    unsigned spins = 0;
+    while (true) {
+        if (mbar_try_wait(bar, parity)) return true;
+        if ((++spins & 15u) == 0) {
+            if (ld_volatile_int(abort_word) != 0) return false;
+            if (clock64() - t0 > WATCHDOG_CYCLES) {
+                atomicCAS(abort_word, 0, -9);
+                return false;
+            }
+        }
+    }
+}
+// Contiguous global -> shared copy by the TMA unit; completion is signalled on `bar` (complete_tx).
+// dst, src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 }  // namespace geordd

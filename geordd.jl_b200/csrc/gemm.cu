@@ -14,6 +14,10 @@ gemm_kernel(int K, double alpha, const double* __restrict__ A, long lda, const d
             double beta, double* __restrict__ C, long ldc, int splitk, double* __restrict__ ws, long ws_stride) {
     using ML = Mainloop<64, A_MC, B_NC, 3>;
     extern __shared__ __align__(16) double smem[];
+    __shared__ int sh_abort;   // never set: plain GEMM has no dataflow waits, only the ring watchdog
+    if (threadIdx.x == 0) sh_abort = 0;
+    Ring ring;
+    ML::ring_init(ring, reinterpret_cast<uint64_t*>(smem + ML::RING_ELEMS), &sh_abort);
     const int mt = blockIdx.x, nt = blockIdx.y, z = blockIdx.z;
     const int kchunks_total = K / BK;
     const int per = (kchunks_total + splitk - 1) / splitk;
@@ -31,7 +35,7 @@ gemm_kernel(int K, double alpha, const double* __restrict__ A, long lda, const d
     src.b_step = B_NC ? (long)BK * ldb : BK;
     typename ML::Acc acc;
     ML::zero(acc);
-    ML::run(smem, nch, src, acc);
+    ML::run(smem, ring, nch, src, acc);
 #pragma unroll
     for (int a = 0; a < ML::MI; ++a)
 #pragma unroll
@@ -69,12 +73,13 @@ static void launch_t(cudaStream_t st, int M, int N, int K, double alpha, const d
     using ML = Mainloop<64, A_MC, B_NC, 3>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(gemm_kernel<A_MC, B_NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ML::SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_kernel<A_MC, B_NC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(ML::SMEM_BYTES + ML::BAR_WORDS * 8));
         attr_set = true;
     }
     dim3 grid(M / TILE, N / 64, splitk);
     long ws_stride = (long)ldc * N;
-    gemm_kernel<A_MC, B_NC><<<grid, NTHREADS, ML::SMEM_BYTES, st>>>(K, alpha, A, lda, B, ldb, beta, C, ldc, splitk, ws,
+    gemm_kernel<A_MC, B_NC><<<grid, NTHREADS, ML::SMEM_BYTES + ML::BAR_WORDS * 8, st>>>(K, alpha, A, lda, B, ldb, beta, C, ldc, splitk, ws,
                                                                    ws_stride); ++g_kernel_launches;
     if (splitk > 1) {
         long tot = (long)M * N;

@@ -46,6 +46,8 @@ void launch_cov(cudaStream_t st, const KernelSpecDev& spec, const double* X1, in
 // upper triangle of the diagonal tiles of L is zeroed, upper tiles are not touched.
 // Result code is left in sched.abort_word (0 ok, k>0: pivot k non-positive, <0 watchdog).
 void launch_potrf(cudaStream_t st, Sched& sched, const double* A, double* L, long ld, int npad);
+// Mirror L' into the tiles above the diagonal (needed before any SOLVE_BWD against this factor).
+void launch_mirror_factor(cudaStream_t st, double* L, long ld, int npad);
 // out[0] = sum_i log L(i,i) for i < n
 void launch_logdiag_sum(cudaStream_t st, const double* L, long ld, int n, double* out);
 
@@ -54,6 +56,7 @@ enum SolveMode { SOLVE_FWD = 0, SOLVE_BWD = 1, SOLVE_TRMM = 2 };
 // In-place triangular solve / multiply against lower factor L (npad x npad) for ncols right-hand
 // sides (ncols multiple of 64): B (npad x ncols, ldb) is overwritten.
 //   FWD:  B <- L^-1 B      BWD: B <- L^-T B      TRMM: Bout <- L * B (out of place, needs Bout)
+// BWD requires launch_mirror_factor to have been applied to L.
 struct SolveEpilogue {
     // FWD/BWD: fused statistic partials, written per row block (deterministic; reduced later):
     //   dot0[rb*ncols + c] = sum_{r in block rb} (wmat(r,c) + (r < wrows ? wshift : 0)) * X(r,c)

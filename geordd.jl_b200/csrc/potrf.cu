@@ -32,21 +32,16 @@ struct PotrfSrc {
     __device__ __forceinline__ const double* b_ptr(int c) const {
         return L + (long)(c * BK) * ldb + (long)j * TILE;
     }
-    __device__ __forceinline__ bool ready(int c) const {
+    __device__ __forceinline__ bool ready(int c) const {   // warp level
         if (c % CHUNKS_PER_TILE != 0) return true;
         int kt = c / CHUNKS_PER_TILE;
-        int ok = 1;
-        if (threadIdx.x == 0) {
-            ok = wait_flag(flags + (long)i * T + kt, epoch, abort_word) &&
-                 wait_flag(flags + (long)j * T + kt, epoch, abort_word);
-        }
-        return __syncthreads_and(ok);
+        return warp_wait_flags(flags + (long)i * T + kt, i != j ? flags + (long)j * T + kt : nullptr, epoch, abort_word);
     }
 };
 
 constexpr int POTRF_CS_ELEMS = TILE * SC;
 constexpr int POTRF_LP_ELEMS = NB * SC;
-constexpr size_t POTRF_SMEM = (size_t)(POTRF_CS_ELEMS + POTRF_LP_ELEMS + TILE) * sizeof(double);
+constexpr size_t POTRF_SMEM = (size_t)(POTRF_CS_ELEMS + POTRF_LP_ELEMS + TILE + PotrfML::BAR_WORDS) * sizeof(double);
 static_assert(PotrfML::SMEM_BYTES <= POTRF_CS_ELEMS * sizeof(double), "stage ring must fit under the C tile");
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -59,6 +54,8 @@ potrf_dataflow_kernel(const double* __restrict__ A, double* __restrict__ L, long
     __shared__ int sh_job;
     __shared__ int sh_info;
     const int tid = threadIdx.x;
+    Ring ring;
+    PotrfML::ring_init(ring, reinterpret_cast<uint64_t*>(invd + TILE), abort_word);
 
     while (true) {
         if (tid == 0) {
@@ -85,8 +82,8 @@ potrf_dataflow_kernel(const double* __restrict__ A, double* __restrict__ L, long
                         acc.v[a][b][e] = -ldcg(Aij + (long)PotrfML::acc_col(b, e) * ld + PotrfML::acc_row(a));
         }
         PotrfSrc src{L, ld, ld, i, j, T, flags, epoch, abort_word};
-        bool ok = PotrfML::run(smem, j * CHUNKS_PER_TILE, src, acc);
-        if (!ok) break;
+        bool ok = PotrfML::run(smem, ring, j * CHUNKS_PER_TILE, src, acc);
+        if (__syncthreads_or(!ok)) break;   // also: every warp is done reading the ring before Cs overwrites it
 #pragma unroll
         for (int a = 0; a < PotrfML::MI; ++a)
 #pragma unroll
@@ -119,6 +116,7 @@ potrf_dataflow_kernel(const double* __restrict__ A, double* __restrict__ L, long
             }
         }
         __threadfence();
+        fence_proxy_async();   // generic smem accesses of the finalize step before the next job's bulk copies
         __syncthreads();
         if (tid == 0) st_release(flags + (long)i * T + j, epoch);
     }
@@ -152,6 +150,27 @@ void launch_potrf(cudaStream_t st, Sched& sched, const double* A, double* L, lon
     int grid = njobs < sched.num_sms ? njobs : sched.num_sms;
     potrf_dataflow_kernel<<<grid, NTHREADS, POTRF_SMEM, st>>>(A, L, ld, T, sched.jobs, njobs, sched.flags, sched.epoch,
                                                               sched.counter, sched.abort_word); ++g_kernel_launches;
+}
+
+// After the factorisation: store L' in the (otherwise unused) tiles above the diagonal, M(j-block, i-block) =
+// L(i-block, j-block)' for i > j, so that backward solves read both L and L' with the row index contiguous.
+// Diagonal tiles keep their explicit zeros above the diagonal (the TRMM path relies on them).
+__global__ void __launch_bounds__(256) mirror_factor_kernel(double* __restrict__ L, long ld, int T) {
+    __shared__ double t[64][65];
+    // 64x64 sub-tiles of the strictly-lower 128-tiles
+    const int S = 2 * T;
+    int bi = blockIdx.x % S, bj = blockIdx.x / S;          // 64-block row / col
+    if (bi / 2 <= bj / 2) return;                           // only tiles strictly below the 128-diagonal
+    const int tx = threadIdx.x % 64, ty0 = threadIdx.x / 64;
+    for (int c = ty0; c < 64; c += 4) t[c][tx] = L[(long)(bj * 64 + c) * ld + bi * 64 + tx];
+    __syncthreads();
+    for (int c = ty0; c < 64; c += 4) L[(long)(bi * 64 + c) * ld + bj * 64 + tx] = t[tx][c];
+}
+
+void launch_mirror_factor(cudaStream_t st, double* L, long ld, int npad) {
+    const int T = npad / TILE;
+    if (T < 2) return;
+    mirror_factor_kernel<<<4 * T * T, 256, 0, st>>>(L, ld, T); ++g_kernel_launches;
 }
 
 __global__ void logdiag_sum_kernel(const double* __restrict__ L, long ld, int n, double* out) {

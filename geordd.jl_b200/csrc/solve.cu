@@ -24,10 +24,11 @@ namespace geordd {
 constexpr int SLAB = 64;
 constexpr int CHUNKS_PER_TILE_S = TILE / BK;
 
+// All three modes read the factor with the row index contiguous: forward / TRMM from the lower tiles of L,
+// backward from the mirrored upper tiles (L' stored above the diagonal by launch_mirror_factor).
 template <int MODE>
 struct SolveCfg {
-    static constexpr bool A_MC = (MODE != SOLVE_BWD);
-    using ML = Mainloop<SLAB, A_MC, /*B_NC=*/false, 3>;
+    using ML = Mainloop<SLAB, /*A_MC=*/true, /*B_NC=*/false, 4>;
 };
 
 template <int MODE>
@@ -44,20 +45,18 @@ struct SolveSrc {
     }
     __device__ __forceinline__ const double* a_ptr(int c) const {
         int kt = ktile(c), kk = (c % CHUNKS_PER_TILE_S) * BK;
-        if (MODE == SOLVE_BWD)   // A(m,k) = L(kt*128+kk+k, rb*128+m): k contiguous
-            return L + (long)rb * TILE * lda + (long)kt * TILE + kk;
-        return L + ((long)kt * TILE + kk) * lda + (long)rb * TILE;   // A(m,k) = L(rb*128+m, kt*128+kk+k)
+        // A(m,k) = M(rb*128+m, kt*128+kk+k), m contiguous.  kt < rb: lower tile of L; kt > rb (backward): the
+        // mirrored tile holding L(kt-block, rb-block)'.
+        return L + ((long)kt * TILE + kk) * lda + (long)rb * TILE;
     }
     __device__ __forceinline__ const double* b_ptr(int c) const {
         int kt = ktile(c), kk = (c % CHUNKS_PER_TILE_S) * BK;
         return X + (long)kt * TILE + kk;   // B(k,n) = X(kt*128+kk+k, n): k contiguous
     }
-    __device__ __forceinline__ bool ready(int c) const {
+    __device__ __forceinline__ bool ready(int c) const {   // warp level
         if (MODE == SOLVE_TRMM) return true;
         if (c % CHUNKS_PER_TILE_S != 0) return true;
-        int ok = 1;
-        if (threadIdx.x == 0) ok = wait_flag(flags + (long)ktile(c) * nslabs + s, epoch, abort_word);
-        return __syncthreads_and(ok);
+        return warp_wait_flags(flags + (long)ktile(c) * nslabs + s, nullptr, epoch, abort_word);
     }
 };
 
@@ -77,19 +76,23 @@ struct SolveParams {
 
 constexpr int SOLVE_CS_ELEMS = SLAB * SC;                       // 8448
 constexpr int SOLVE_PANEL_ELEMS = TILE * LRS;                   // 4608 >= NB*SC = 4224
-constexpr int SOLVE_SMEM_ELEMS = SOLVE_CS_ELEMS + SOLVE_PANEL_ELEMS + NB;
+constexpr int SOLVE_RING_ELEMS = SolveCfg<0>::ML::RING_ELEMS;
+constexpr int SOLVE_WORK_ELEMS = SOLVE_CS_ELEMS + SOLVE_PANEL_ELEMS + NB;
+constexpr int SOLVE_SMEM_ELEMS = (SOLVE_RING_ELEMS > SOLVE_WORK_ELEMS ? SOLVE_RING_ELEMS : SOLVE_WORK_ELEMS) + SolveCfg<0>::ML::BAR_WORDS;
 constexpr size_t SOLVE_SMEM = (size_t)SOLVE_SMEM_ELEMS * sizeof(double);
 
 template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 2) solve_dataflow_kernel(SolveParams p) {
     using ML = typename SolveCfg<MODE>::ML;
-    static_assert(ML::SMEM_BYTES <= SOLVE_SMEM, "stage ring must fit");
+    static_assert(ML::SMEM_BYTES + ML::BAR_WORDS * 8 <= SOLVE_SMEM, "stage ring must fit");
     extern __shared__ __align__(16) double smem[];
     double* Cs = smem;
     double* Lp = smem + SOLVE_CS_ELEMS;
     double* invd = Lp + SOLVE_PANEL_ELEMS;
     __shared__ int sh_job;
     const int tid = threadIdx.x;
+    Ring ring;
+    ML::ring_init(ring, reinterpret_cast<uint64_t*>(smem + SOLVE_SMEM_ELEMS - ML::BAR_WORDS), p.abort_word);
     const int njobs = p.T * p.nslabs;
     const long ncols = (long)p.nslabs * SLAB;
 
@@ -123,8 +126,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) solve_dataflow_kernel(SolveParams
         int nchunks = (MODE == SOLVE_FWD) ? rb * CHUNKS_PER_TILE_S
                     : (MODE == SOLVE_BWD) ? (p.T - 1 - rb) * CHUNKS_PER_TILE_S
                                           : (rb + 1) * CHUNKS_PER_TILE_S;
-        bool ok = ML::run(smem, nchunks, src, acc);
-        if (!ok) break;
+        bool ok = ML::run(smem, ring, nchunks, src, acc);
+        if (__syncthreads_or(!ok)) break;   // also: every warp is done reading the ring before Cs overwrites it
         const double sgn = (MODE == SOLVE_TRMM) ? 1.0 : -1.0;
 #pragma unroll
         for (int a = 0; a < ML::MI; ++a)
@@ -191,6 +194,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) solve_dataflow_kernel(SolveParams
             }
             __threadfence();
         }
+        fence_proxy_async();   // generic smem accesses of this job before the next job's bulk copies
         __syncthreads();
         if (MODE != SOLVE_TRMM && tid == 0) st_release(p.flags + (long)rb * p.nslabs + s, p.epoch);
     }
