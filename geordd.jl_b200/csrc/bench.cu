@@ -58,6 +58,34 @@ int geordd_bench_dmma_peak(geordd_ctx* c, double* tflops) {
     return 0;
 }
 
+// DMMA issue-rate probe: `threads` per CTA, `ctas` CTAs in total, 16 independent accumulators per warp.
+int geordd_bench_dmma(geordd_ctx* c, int threads, int ctas, int iters, double* tflops) {
+    if (!c || !tflops || threads <= 0 || threads > 1024 || threads % 32 || ctas <= 0 || iters <= 0) return GEORDD_ERR_ARG;
+    try {
+        ctx_use(c);
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        dmma_peak_kernel<<<ctas, threads, 0, c->stream>>>(16, c->d_scal + 8); ++g_kernel_launches;
+        float best = 1e30f;
+        for (int r = 0; r < 3; ++r) {
+            cudaEventRecord(e0, c->stream);
+            dmma_peak_kernel<<<ctas, threads, 0, c->stream>>>(iters, c->d_scal + 8); ++g_kernel_launches;
+            cudaEventRecord(e1, c->stream);
+            GD_CUDA(cudaStreamSynchronize(c->stream));
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            best = std::min(best, ms);
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        GD_CUDA(cudaGetLastError());
+        double flops = 2.0 * 256.0 * 16.0 * (double)iters * (threads / 32) * (double)ctas;
+        *tflops = flops / (best * 1e-3) / 1e12;
+    } catch (const ApiError& e) {
+        return ctx_fail(c, e);
+    }
+    return 0;
+}
+
 int geordd_bench_potrf(geordd_ctx* c, int n, int reps, double* ms_best, double* ms_mean) {
     if (!c || n <= 0 || reps <= 0) return GEORDD_ERR_ARG;
     double *dX = nullptr, *dK = nullptr, *dL = nullptr;

@@ -193,6 +193,7 @@ GEORDD_API int geordd_dbg_trsm(geordd_ctx* ctx, int mode, const double* L, int n
 /* Device-resident micro-benchmarks (synthetic SPD matrix built on device): times in ms. */
 GEORDD_API int geordd_bench_potrf(geordd_ctx* ctx, int n, int reps, double* ms_best, double* ms_mean);
 GEORDD_API int geordd_bench_dmma_peak(geordd_ctx* ctx, double* tflops);
+GEORDD_API int geordd_bench_dmma(geordd_ctx* ctx, int threads_per_cta, int ctas, int iters, double* tflops);
 
 #ifdef __cplusplus
 }
