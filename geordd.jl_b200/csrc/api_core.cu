@@ -196,7 +196,7 @@ int make_posdef(geordd_ctx* c, double* K, double* L, long ld, int n, int npad, i
         if (info == 0) {
             if (rounds) *rounds = nr;
             ProfScope ps(c, PC_MISC);
-            launch_mirror_factor(c->stream, L, ld, npad);
+            launch_mirror_factor(c->stream, L, npad);
             return 0;
         }
         if (attempt == 10) {
@@ -213,16 +213,15 @@ int make_posdef(geordd_ctx* c, double* K, double* L, long ld, int n, int npad, i
     return -1;
 }
 
-void pd_solve(geordd_ctx* c, const double* L, long ldl, int npad, double* B, long ldb, int ncols,
-              const SolveEpilogue& epi_bwd) {
+void pd_solve(geordd_ctx* c, const double* L, int npad, double* B, long ldb, int ncols, const SolveEpilogue& epi_bwd) {
     SolveEpilogue none;
     {
         ProfScope ps(c, PC_FWD);
-        launch_solve(c->stream, c->sched, SOLVE_FWD, L, ldl, npad, B, ldb, ncols, none);
+        launch_solve(c->stream, c->sched, SOLVE_FWD, L, npad, B, ldb, ncols, none);
     }
     {
         ProfScope ps(c, PC_BWD);
-        launch_solve(c->stream, c->sched, SOLVE_BWD, L, ldl, npad, B, ldb, ncols, epi_bwd);
+        launch_solve(c->stream, c->sched, SOLVE_BWD, L, npad, B, ldb, ncols, epi_bwd);
     }
 }
 
@@ -240,7 +239,7 @@ void gp_update_alpha(geordd_gp* gp) {
     GD_CUDA(cudaMemsetAsync(gp->dAlpha, 0, (size_t)npad * 64 * sizeof(double), c->stream));
     GD_CUDA(cudaMemcpyAsync(gp->dAlpha, gp->dR, (size_t)npad * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     SolveEpilogue none;
-    pd_solve(c, gp->dL, npad, npad, gp->dAlpha, npad, 64, none);
+    pd_solve(c, gp->dL, npad, gp->dAlpha, npad, 64, none);
     launch_reduce(c->stream, 2, gp->dR, gp->dAlpha, 0, gp->n, 0, c->d_scal);
     check_abort(c);
     double quad = read_scalar(c, c->d_scal);
@@ -268,7 +267,7 @@ geordd_gp* gp_create(geordd_ctx* c, const geordd_kernel* k, const double* X, int
         gp->X.assign(X, X + (size_t)dim * n);
         gp->dX = dalloc((size_t)dim * n, c->stream, false);
         gp->dK = dalloc(np * np, c->stream, false);
-        gp->dL = dalloc(np * np, c->stream, false);
+        gp->dL = dalloc(factor_elems(gp->npad), c->stream, false);
         gp->dR = dalloc(np, c->stream, true);
         gp->dAlpha = dalloc(np * 64, c->stream, true);
         GD_CUDA(cudaMemcpyAsync(gp->dX, X, (size_t)dim * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -502,7 +501,7 @@ int geordd_gp_fit(geordd_ctx* c, const geordd_kernel* k, const double* X, int di
     if (cholU) {
         // U = L' : transpose-copy the logical n x n block through scratch
         c->tmp0.ensure((size_t)n * n, c->stream, false);
-        launch_copy2d(c->stream, c->tmp0.p, n, gp->dL, gp->npad, n, n, true);
+        launch_factor_unpack(c->stream, gp->dL, gp->npad, c->tmp0.p, n, n, true);
         GD_CUDA(cudaMemcpyAsync(cholU, c->tmp0.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     }
     GD_CUDA(cudaStreamSynchronize(c->stream));
@@ -605,7 +604,7 @@ int geordd_dbg_potrf(geordd_ctx* c, const double* A, int n, double* L, double* m
     int info = 0;
     try {
         dA = dalloc((size_t)npad * npad, c->stream, false);
-        dL = dalloc((size_t)npad * npad, c->stream, true);
+        dL = dalloc(factor_elems(npad), c->stream, true);
         upload_spd_padded(c, dA, npad, A, n);
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -623,12 +622,9 @@ int geordd_dbg_potrf(geordd_ctx* c, const double* A, int n, double* L, double* m
         info = c->h_info[0];
         GD_CUDA(cudaMemsetAsync(c->sched.abort_word, 0, sizeof(int), c->stream));
         if (info < 0) throw ApiError(GEORDD_ERR_WATCHDOG, "potrf watchdog fired");
-        // zero the strictly-upper tiles for the copy-out (they are never written by the kernel)
-        std::vector<double> tmp((size_t)n * n);
-        download2d(c, tmp.data(), n, dL, npad, n, n);
+        launch_factor_unpack(c->stream, dL, npad, dA, n, n, false);   // dense lower factor (reuse dA as staging)
+        GD_CUDA(cudaMemcpyAsync(L, dA, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         GD_CUDA(cudaStreamSynchronize(c->stream));
-        for (int j = 0; j < n; ++j)
-            for (int i = 0; i < n; ++i) L[(size_t)j * n + i] = (i >= j) ? tmp[(size_t)j * n + i] : 0.0;
     } catch (...) {
         dfree(dA); dfree(dL);
         throw;
@@ -638,16 +634,19 @@ int geordd_dbg_potrf(geordd_ctx* c, const double* A, int n, double* L, double* m
     API_END
 }
 
+
 int geordd_dbg_trsm(geordd_ctx* c, int mode, const double* L, int n, double* B, int nrhs, double* ms) {
     API_BEGIN(c)
     if (!L || !B || n <= 0 || nrhs <= 0 || mode < 0 || mode > 2) throw ApiError(GEORDD_ERR_ARG, "dbg_trsm: bad arguments");
     const int npad = round_up(n, TILE), ncols = round_up(nrhs, 64);
     double *dL = nullptr, *dB = nullptr, *dO = nullptr;
     try {
-        dL = dalloc((size_t)npad * npad, c->stream, false);
+        dL = dalloc(factor_elems(npad), c->stream, false);
         dB = dalloc((size_t)npad * ncols, c->stream, true);
-        upload_spd_padded(c, dL, npad, L, n);
-        launch_mirror_factor(c->stream, dL, npad, npad);
+        c->tmp0.ensure((size_t)n * n, c->stream, false);
+        GD_CUDA(cudaMemcpyAsync(c->tmp0.p, L, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        launch_factor_pack(c->stream, c->tmp0.p, n, n, dL, npad);
+        launch_mirror_factor(c->stream, dL, npad);
         upload2d(c, dB, npad, B, n, n, nrhs);
         SolveEpilogue epi;
         if (mode == 2) {
@@ -658,7 +657,7 @@ int geordd_dbg_trsm(geordd_ctx* c, int mode, const double* L, int n, double* B, 
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         GD_CUDA(cudaStreamSynchronize(c->stream));
         cudaEventRecord(e0, c->stream);
-        launch_solve(c->stream, c->sched, (SolveMode)mode, dL, npad, npad, dB, npad, ncols, epi);
+        launch_solve(c->stream, c->sched, (SolveMode)mode, dL, npad, dB, npad, ncols, epi);
         cudaEventRecord(e1, c->stream);
         check_abort(c);
         float t = 0.f;

@@ -89,7 +89,7 @@ struct geordd_gp {
     int n = 0, npad = 0, dim = 0;
     double* dX = nullptr;       // dim x n
     double* dK = nullptr;       // npad x npad  (cK.mat, lower tiles; full once mirrored)
-    double* dL = nullptr;       // npad x npad  lower Cholesky factor (= U')
+    double* dL = nullptr;       // lower Cholesky factor (= U') in TBP storage, factor_elems(npad) doubles
     double* dR = nullptr;       // npad         y - m (zero padded)
     double* dAlpha = nullptr;   // npad x 64 slab, column 0 = alpha
     bool k_full = false;
@@ -160,8 +160,7 @@ KernelSpecDev to_dev(const geordd_kernel& k);
 // place.  Returns 0 or the LAPACK info after the 11th failed attempt.
 int make_posdef(geordd_ctx* c, double* K, double* L, long ld, int n, int npad, int* rounds);
 // B <- L^-T L^-1 B (ncols multiple of 64) with optional fused epilogue on the backward pass.
-void pd_solve(geordd_ctx* c, const double* L, long ldl, int npad, double* B, long ldb, int ncols,
-              const SolveEpilogue& epi_bwd);
+void pd_solve(geordd_ctx* c, const double* L, int npad, double* B, long ldb, int ncols, const SolveEpilogue& epi_bwd);
 void gemm(geordd_ctx* c, bool a_mc, bool b_nc, int M, int N, int K, double alpha, const double* A, long lda,
           const double* B, long ldb, double beta, double* C, long ldc, int splitk);
 int pick_splitk(geordd_ctx* c, int M, int N, int K);

@@ -150,7 +150,7 @@ static int mg_update_mll(geordd_multigp* h, const geordd_kernel* k, double lin_e
     GD_CUDA(cudaMemsetAsync(h->dAlpha, 0, (size_t)np * 64 * sizeof(double), c->stream));
     GD_CUDA(cudaMemcpyAsync(h->dAlpha, h->dR, (size_t)np * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     SolveEpilogue none;
-    pd_solve(c, h->dL, np, np, h->dAlpha, np, 64, none);
+    pd_solve(c, h->dL, np, h->dAlpha, np, 64, none);
     launch_reduce(c->stream, 2, h->dR, h->dAlpha, 0, n, 0, c->d_scal);
     check_abort(c);
     double quad = read_scalar(c, c->d_scal);
@@ -199,7 +199,7 @@ int geordd_multigp_create(geordd_ctx* c, const double* D, int p, const double* X
         h->dX = dalloc((size_t)dim * n, c->stream, false);
         h->dG = dalloc(np * np, c->stream, false);
         h->dK = dalloc(np * np, c->stream, false);
-        h->dL = dalloc(np * np, c->stream, false);
+        h->dL = dalloc(factor_elems(h->npad), c->stream, false);
         h->dY = dalloc(np, c->stream, true);
         h->dR = dalloc(np, c->stream, true);
         h->dAlpha = dalloc(np * 64, c->stream, true);
@@ -258,7 +258,7 @@ int geordd_multigp_mll_grad(geordd_multigp* h, const geordd_kernel* k, double li
     GD_CUDA(cudaMemsetAsync(h->dB, 0, (size_t)np * np * sizeof(double), st));
     launch_add_diag(st, h->dB, np, np, 1.0);
     SolveEpilogue none;
-    pd_solve(c__, h->dL, np, np, h->dB, np, np, none);
+    pd_solve(c__, h->dL, np, h->dB, np, np, none);
     // reductions
     const int ngroups = (int)h->group_off.size() - 1;
     std::vector<int> blk_off(ngroups + 1, 0);
@@ -332,7 +332,7 @@ int geordd_multigp_postmean_beta(geordd_multigp* h, const geordd_kernel* k, doub
         c__->err = "Sigma_Y|beta is not positive definite";
         return info;
     }
-    launch_mirror_factor(st, h->dL, np, np);
+    launch_mirror_factor(st, h->dL, np);
     double *W = nullptr, *prec = nullptr, *rhs = nullptr, *v = nullptr;
     try {
         // W = L^-1 D'  (n x p): X_invA_Xt(Sigma, D) = W'W   (:337)
@@ -347,7 +347,7 @@ int geordd_multigp_postmean_beta(geordd_multigp* h, const geordd_kernel* k, doub
         {
             ProfScope ps(c__, PC_FWD);
             SolveEpilogue none;
-            launch_solve(st, c__->sched, SOLVE_FWD, h->dL, np, np, W, np, pp, none);
+            launch_solve(st, c__->sched, SOLVE_FWD, h->dL, np, W, np, pp, none);
         }
         prec = dalloc((size_t)pp * pp, st, true);
         gemm(c__, false, false, pp, pp, np, 1.0, W, np, W, np, 0.0, prec, pp, 0);
@@ -357,7 +357,7 @@ int geordd_multigp_postmean_beta(geordd_multigp* h, const geordd_kernel* k, doub
         launch_axpby(st, n, 1.0, h->dY, 0.0, rhs);
         launch_add_const(st, rhs, np, n, 1, -k->mean_const);
         SolveEpilogue none;
-        pd_solve(c__, h->dL, np, np, rhs, np, 64, none);
+        pd_solve(c__, h->dL, np, rhs, np, 64, none);
         // beta = precision \ (D * rhs)    [== (precision \ D) * rhs, :342]
         v = dalloc((size_t)pp * 64, st, true);
         // D (p x n) stored ppad x np column-major: A(m,k) = D(m,k) at k*ppad + m -> a_mc with M = pp needs ld >= pp: use Dt'

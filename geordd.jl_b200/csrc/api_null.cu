@@ -32,7 +32,7 @@ void cliff_face_dev(geordd_gp* T, geordd_gp* C, const double* dXb, int nb, int n
         {
             ProfScope ps(c, PC_FWD);
             SolveEpilogue none;
-            launch_solve(c->stream, c->sched, SOLVE_FWD, gp->dL, mp, mp, Kxb, mp, nbp, none);
+            launch_solve(c->stream, c->sched, SOLVE_FWD, gp->dL, mp, Kxb, mp, nbp, none);
         }
         gemm(c, false, false, nbp, nbp, mp, -1.0, Kxb, mp, Kxb, mp, 1.0, dSigma, nbp, 0);
     }
@@ -110,7 +110,7 @@ static void calib_cov_mu_delta(geordd_gp* T, geordd_gp* C, const double* dXb, in
             ProfScope ps(c, PC_COV);
             launch_cov(c->stream, to_dev(T->k), T->dX, mT, dXb, nb, 2, false, false, 0.0, WT, mTp, mTp, nbp, false);
         }
-        pd_solve(c, T->dL, mTp, mTp, WT, mTp, nbp, none);
+        pd_solve(c, T->dL, mTp, WT, mTp, nbp, none);
         P = dalloc((size_t)std::max(mTp, mCp) * nbp, c->stream, false);
         // P = KTT * WT_c ; out = WT_c' P
         gemm(c, true, false, mTp, nbp, mTp, 1.0, T->dK, mTp, WT, mTp, 0.0, P, mTp, 0);
@@ -121,7 +121,7 @@ static void calib_cov_mu_delta(geordd_gp* T, geordd_gp* C, const double* dXb, in
                 ProfScope ps(c, PC_COV);
                 launch_cov(c->stream, to_dev(C->k), C->dX, mC, dXb, nb, 2, false, false, 0.0, WC, mCp, mCp, nbp, false);
             }
-            pd_solve(c, C->dL, mCp, mCp, WC, mCp, nbp, none);
+            pd_solve(c, C->dL, mCp, WC, mCp, nbp, none);
             gemm(c, true, false, mCp, nbp, mCp, 1.0, C->dK, mCp, WC, mCp, 0.0, P, mCp, 0);
             gemm(c, false, false, nbp, nbp, mCp, 1.0, WC, mCp, P, mCp, 1.0, dOut, nbp, 0);
             // KCT = cov(kernel_C, X_C, X_T) (mCp x mTp); P = KCT * WT_c (mCp x nbp); E = WC_c' P ; out -= E + E'
@@ -252,7 +252,7 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
             e.outT = h->AT.p; e.ldT = mTp; e.sub_T = mTc;
             e.outC = h->AC.p; e.ldC = mCp; e.sub_C = mCc;
             ProfScope ps(c, PC_TRMM);
-            launch_solve(st, c->sched, SOLVE_TRMM, N->dL, npN, npN, h->Z.p, npN, ncols, e);
+            launch_solve(st, c->sched, SOLVE_TRMM, N->dL, npN, h->Z.p, npN, ncols, e);
         }
         // 3. update_alpha! on T, C (and N), with the (y - m)' alpha quadratic forms fused into the solves
         {
@@ -261,12 +261,12 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
                 eT.wmat = h->RN.p; eT.ldw = ldN; eT.wshift = mN - mTc; eT.wrows = mT; eT.dot0 = h->partT.p;
                 eC.wmat = h->RN.p + mT; eC.ldw = ldN; eC.wshift = mN - mCc; eC.wrows = mC; eC.dot0 = h->partC.p;
             }
-            pd_solve(c, T->dL, mTp, mTp, h->AT.p, mTp, ncols, eT);
-            pd_solve(c, C->dL, mCp, mCp, h->AC.p, mCp, ncols, eC);
+            pd_solve(c, T->dL, mTp, h->AT.p, mTp, ncols, eT);
+            pd_solve(c, C->dL, mCp, h->AC.p, mCp, ncols, eC);
             if (rq.want_mll) {
                 SolveEpilogue eN;
                 eN.wmat = h->RN.p; eN.ldw = ldN; eN.dot0 = h->partN.p;
-                pd_solve(c, N->dL, npN, npN, h->AN.p, ldN, ncols, eN);
+                pd_solve(c, N->dL, npN, h->AN.p, ldN, ncols, eN);
             }
         }
         // Partials of dead columns in the last slab are garbage-free (zero inputs) and ignored.
@@ -290,7 +290,7 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
             SolveEpilogue e;
             e.wmat = h->M.p; e.ldw = nbp; e.dot0 = h->partChi.p;
             e.wvec = h->dOnes; e.dot1 = h->partNum.p;
-            pd_solve(c, h->dLSig, nbp, nbp, h->W.p, nbp, ncols, e);
+            pd_solve(c, h->dLSig, nbp, h->W.p, nbp, ncols, e);
             FinishCliff f{};
             f.part_chi = h->partChi.p; f.part_num = h->partNum.p; f.nb = TS; f.ncols = ncols; f.ndraws = live;
             f.chi_obs = rq.chi_obs; f.denom = h->denom; f.pval_obs = rq.pval_obs;
@@ -341,10 +341,10 @@ static double null_cov_mu_tau(geordd_null* h, bool as_shipped) {
         calib_cov_mu_delta(h->T, h->C, h->dXb, nb, nbp, as_shipped, cmd);
         // cov_mu_tau = sum((Sigma \ cmd) * (Sigma \ 1))
         SolveEpilogue none;
-        pd_solve(c, h->dLSig, nbp, nbp, cmd, nbp, nbp, none);
+        pd_solve(c, h->dLSig, nbp, cmd, nbp, nbp, none);
         one = dalloc((size_t)nbp * 64, c->stream, true);
         GD_CUDA(cudaMemcpyAsync(one, h->dOnes, (size_t)nbp * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-        pd_solve(c, h->dLSig, nbp, nbp, one, nbp, 64, none);
+        pd_solve(c, h->dLSig, nbp, one, nbp, 64, none);
         // v = (Sigma\cmd) * s  then sum(v)  == sum over all entries of (Sigma\cmd)(i,j) * s(j)
         double* v = dalloc((size_t)nbp * 64, c->stream, true);
         gemm(c, true, false, nbp, 64, nbp, 1.0, cmd, nbp, one, nbp, 0.0, v, nbp, 1);
@@ -541,7 +541,7 @@ int geordd_weight_at_units(geordd_gp* gp, const double* Xb, int nb, const double
             launch_cov(c__->stream, to_dev(gp->k), gp->dX, gp->n, dXb, nb, gp->dim, false, false, 0.0, KXb, mp, mp, nbp, false);
         }
         SolveEpilogue none;
-        pd_solve(c__, gp->dL, mp, mp, KXb, mp, nbp, none);          // K_XX \ K_Xb
+        pd_solve(c__, gp->dL, mp, KXb, mp, nbp, none);          // K_XX \ K_Xb
         gemm(c__, true, false, mp, 64, nbp, 1.0 / sw, KXb, mp, w, nbp, 0.0, out, mp, 1);
         GD_CUDA(cudaMemcpyAsync(w_unit, out, (size_t)gp->n * sizeof(double), cudaMemcpyDeviceToHost, c__->stream));
         check_abort(c__);
@@ -611,7 +611,7 @@ static int null_set_sentinels(geordd_null* h, const double* Xb, int nb, double n
     h->dXb = dalloc((size_t)2 * nb, c->stream, false);
     GD_CUDA(cudaMemcpyAsync(h->dXb, Xb, (size_t)2 * nb * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     h->dSig = dalloc((size_t)nbp * nbp, c->stream, true);
-    h->dLSig = dalloc((size_t)nbp * nbp, c->stream, true);
+    h->dLSig = dalloc(factor_elems(nbp), c->stream, true);
     double* mu = dalloc((size_t)nbp * 64, c->stream, true);
     try {
         cliff_face_dev(T, C, h->dXb, nb, nbp, mu, h->dSig);
@@ -640,7 +640,7 @@ static int null_set_sentinels(geordd_null* h, const double* Xb, int nb, double n
     try {
         GD_CUDA(cudaMemcpyAsync(slab, h->dOnes, (size_t)nbp * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         SolveEpilogue none;
-        pd_solve(c, h->dLSig, nbp, nbp, slab, nbp, 64, none);
+        pd_solve(c, h->dLSig, nbp, slab, nbp, 64, none);
         launch_reduce(c->stream, 1, slab, nullptr, 0, nb, 0, c->d_scal + 2);
         check_abort(c);
         h->denom = read_scalar(c, c->d_scal + 2);
@@ -734,7 +734,7 @@ int geordd_gp_prior_rand(geordd_gp* gp, long nsim, unsigned long long seed, unsi
         e.nrows = n; e.split = n; e.add_const = gp->k.mean_const; e.out0 = dY; e.ld0 = np;
         {
             ProfScope ps(c__, PC_TRMM);
-            launch_solve(c__->stream, c__->sched, SOLVE_TRMM, gp->dL, np, np, dZ, np, ncols, e);
+            launch_solve(c__->stream, c__->sched, SOLVE_TRMM, gp->dL, np, dZ, np, ncols, e);
         }
         download2d(c__, Y, n, dY, np, n, (int)nsim);
         check_abort(c__);

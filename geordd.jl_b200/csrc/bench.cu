@@ -98,7 +98,7 @@ int geordd_bench_potrf(geordd_ctx* c, int n, int reps, double* ms_best, double* 
         for (auto& v : X) v = U(rng);
         dX = dalloc((size_t)2 * n, c->stream, false);
         dK = dalloc((size_t)npad * npad, c->stream, false);
-        dL = dalloc((size_t)npad * npad, c->stream, false);
+        dL = dalloc(factor_elems(npad), c->stream, false);
         GD_CUDA(cudaMemcpyAsync(dX, X.data(), X.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         KernelSpecDev spec{2, 0.3, 1.0, 400.0};
         launch_cov(c->stream, spec, dX, n, dX, n, 2, true, false, 0.09, dK, npad, npad, npad, false);

@@ -68,6 +68,7 @@ __device__ __forceinline__ bool wait_flag(const unsigned* flag, unsigned epoch, 
 
 __device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }
 
+
 // ---- mbarrier + bulk async copy (TMA unit, SASS UBLKCP) ---------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -85,6 +86,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned by
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(smem_u32(bar)),
                  "r"(bytes)
                  : "memory");
+}
+// Raise the expected transaction bytes of the current phase without arriving.
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
     unsigned done;
@@ -111,6 +116,10 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, unsigned parity, int* a
             }
         }
     }
+}
+// Make the completion of all cp.async (LDGSTS) issued so far by this thread count as one (pre-counted) arrival.
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 // Contiguous global -> shared copy by the TMA unit; completion is signalled on `bar` (complete_tx).
 // dst, src 16-byte aligned, bytes a multiple of 16.

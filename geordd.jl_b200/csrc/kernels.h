@@ -9,6 +9,17 @@ namespace geordd {
 constexpr int TILE = 128;        // matrix tile edge: all device matrices are padded to multiples of TILE
 constexpr int BK = 16;           // K-chunk of the mainloop
 
+// Cholesky factors are stored TILE-BLOCKED AND PADDED ("TBP"): tile (I,J) of the npad x npad matrix is a
+// contiguous 128 x 132 column-major image (column stride TLD = 132, the same padded image the mainloop keeps in
+// shared memory), so a 16-column K-chunk of a tile is ONE contiguous 16.5 KB bulk copy.
+constexpr int TLD = TILE + 4;
+constexpr long TSZ = (long)TILE * TLD;
+inline size_t factor_elems(int npad) { size_t T = npad / TILE; return T * T * (size_t)TSZ; }
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline long tile_off(int I, int J, int T) { return ((long)J * T + I) * TSZ; }
+
 struct KernelSpecDev {
     int kind;            // 0 SE, 1 Mat12, 2 Mat32, 3 Mat52
     double ell, sigma2, const_sigma2;
@@ -42,14 +53,18 @@ void launch_cov(cudaStream_t st, const KernelSpecDev& spec, const double* X1, in
                 bool accumulate);
 
 // ---- potrf.cu -------------------------------------------------------------------------------------
-// L = chol(A) (lower), out of place, npad x npad, only the lower triangle of A is read; the strict
-// upper triangle of the diagonal tiles of L is zeroed, upper tiles are not touched.
+// L = chol(A) (lower), out of place.  A: npad x npad column-major (leading dimension ld), only its lower
+// triangle is read.  L: TBP storage (factor_elems(npad) doubles); the strict upper triangle of the diagonal
+// tiles is zeroed, upper tiles are written only by launch_mirror_factor.
 // Result code is left in sched.abort_word (0 ok, k>0: pivot k non-positive, <0 watchdog).
 void launch_potrf(cudaStream_t st, Sched& sched, const double* A, double* L, long ld, int npad);
+// dense (n x n column-major, ldd) lower triangle -> TBP factor with identity padding; and back (optionally transposed).
+void launch_factor_pack(cudaStream_t st, const double* dense, long ldd, int n, double* L, int npad);
+void launch_factor_unpack(cudaStream_t st, const double* L, int npad, double* dense, long ldd, int n, bool transpose);
 // Mirror L' into the tiles above the diagonal (needed before any SOLVE_BWD against this factor).
-void launch_mirror_factor(cudaStream_t st, double* L, long ld, int npad);
-// out[0] = sum_i log L(i,i) for i < n
-void launch_logdiag_sum(cudaStream_t st, const double* L, long ld, int n, double* out);
+void launch_mirror_factor(cudaStream_t st, double* L, int npad);
+// out[0] = sum_i log L(i,i) for i < n   (L in TBP storage)
+void launch_logdiag_sum(cudaStream_t st, const double* L, int npad, int n, double* out);
 
 // ---- solve.cu -------------------------------------------------------------------------------------
 enum SolveMode { SOLVE_FWD = 0, SOLVE_BWD = 1, SOLVE_TRMM = 2 };
@@ -77,8 +92,8 @@ struct SolveEpilogue {
     double add_const = 0.0, add_T = 0.0;
     double sub_0 = 0.0, sub_1 = 0.0, sub_T = 0.0, sub_C = 0.0;
 };
-void launch_solve(cudaStream_t st, Sched& sched, SolveMode mode, const double* L, long ldl, int npad, double* B,
-                  long ldb, int ncols, const SolveEpilogue& epi);
+void launch_solve(cudaStream_t st, Sched& sched, SolveMode mode, const double* L, int npad, double* B, long ldb,
+                  int ncols, const SolveEpilogue& epi);
 
 // ---- gemm.cu --------------------------------------------------------------------------------------
 // C(M x N) = alpha * op(A) * op(B) + beta * C.  M multiple of 128, N multiple of 64, K multiple of 16.

@@ -2,34 +2,53 @@
 //
 //   acc(128 x BN) += sum over K-chunks  A_chunk(128 x 16) * B_chunk(16 x BN)
 //
-// 256 threads = 8 warps, each both producer and consumer of a STAGES-deep shared-memory ring:
-//   * operand rows are moved global -> shared by the TMA unit with bulk async copies (SASS UBLKCP), one
-//     contiguous row per copy, landing in padded rows; a stage's arrival is tracked by an mbarrier
-//     (expect_tx / complete_tx), its release by a second mbarrier on which each warp arrives after its last
-//     fragment read.  There is NO CTA-wide barrier in the K loop: warps drift by up to STAGES-2 chunks.
-//   * fragments are read with conflict-free LDS.64 (row strides == 4 mod 16 doubles) and multiplied with
-//     mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4), 16-32 independent accumulators per warp.
+// 256 threads = 8 warps feed and drain a STAGES-deep shared-memory ring without any CTA-wide barrier in the
+// K loop: a stage's arrival is tracked by an mbarrier (`full`), its release by a second one (`empty`) on which
+// each warp arrives after its last fragment read, so warps drift by up to STAGES-2 chunks.
 //
-// Layout flags describe which index is contiguous in GLOBAL memory for a chunk:
+// How an operand chunk travels global -> shared is a per-operand template choice:
+//   ROWS_TMA  one bulk async copy (TMA unit, SASS UBLKCP) per contiguous row, landing in padded rows
+//   BLK_TMA   ONE bulk async copy per chunk: the global storage already is the padded shared-memory image
+//             (tile-blocked padded factor storage, kernels.h)
+//   ROWS_GEN / BLK_GEN   the same two shapes moved with 16-byte cp.async (LDGSTS) by all threads, completion
+//             signalled on the same mbarrier (cp.async.mbarrier.arrive.noinc)
+// RULE (empirical, round 1): the *_TMA modes are used only in kernels WITHOUT inter-CTA dataflow flags (the
+// triangular multiply, the plain GEMM).  The flagged kernels (Cholesky, forward/backward solves) move both
+// operands with the *_GEN modes.  With bulk copies in those kernels a stress test (20 000 right-hand sides
+// against SciPy, scripts/gpu_stress_solve.py) showed rare wrong accumulator tiles -- for the flag-published X
+// blocks AND for the kernel-constant factor tiles -- although the ring contents compared equal to global memory
+// at consume time and the same ring with bulk copies is exact in the flag-free triangular multiply, with injected
+// skew, acquire loads and fences.  The cause was not identified; the generic-proxy ring is exact in all tests.
+//
+// Fragments are read with conflict-free LDS.64 (row strides == 4 mod 16 doubles) and multiplied with
+// mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4), 16-32 independent accumulators per warp.
+//
+// Layout flags say which index is contiguous in a chunk:
 //   A_MC: A(m,k) at a[k*lda + m]  (column-major tile)      else  A(m,k) at a[m*lda + k]
 //   B_NC: B(k,n) at b[k*ldb + n]                            else  B(k,n) at b[n*ldb + k]
-// The chunk source `Src` supplies per-chunk base pointers (so a K loop can walk over many tiles of a big
-// matrix) and a warp-level `ready(chunk)` hook where dataflow kernels wait for producer tiles.
+// The chunk source `Src` supplies per-chunk base pointers (so a K loop can walk over many tiles of a big matrix)
+// and a warp-level `ready(chunk)` hook where dataflow kernels wait for producer tiles.
 #pragma once
 #include "common.cuh"
 
 namespace geordd {
 
+enum CopyMode { ROWS_TMA = 0, BLK_TMA = 1, ROWS_GEN = 2, BLK_GEN = 3 };
+__host__ __device__ constexpr bool copy_is_gen(int m) { return m == ROWS_GEN || m == BLK_GEN; }
+__host__ __device__ constexpr bool copy_is_blk(int m) { return m == BLK_TMA || m == BLK_GEN; }
+
 // Ring bookkeeping that persists across the jobs of a persistent kernel.
 struct Ring {
-    uint64_t* full;    // [STAGES] data landed   (1 arrival + tx bytes)
-    uint64_t* empty;   // [STAGES] stage free     (8 arrivals, one per warp)
+    uint64_t* full;    // [STAGES] data landed
+    uint64_t* empty;   // [STAGES] stage free (8 arrivals, one per warp)
     unsigned it;       // chunks pushed through the ring so far (same value in every thread)
     int* abort_word;
 };
 
-template <int BN_, bool A_MC_, bool B_NC_, int STAGES_>
+template <int BN_, bool A_MC_, bool B_NC_, int STAGES_, int A_MODE_ = ROWS_TMA, int B_MODE_ = ROWS_TMA>
 struct Mainloop {
+    static constexpr int A_MODE = A_MODE_, B_MODE = B_MODE_;
+    static_assert(!copy_is_blk(A_MODE_) || A_MC_, "block copies of A need the m-contiguous layout");
     static constexpr int BM = TILE;
     static constexpr int BN = BN_;
     static constexpr bool A_MC = A_MC_;
@@ -51,7 +70,16 @@ struct Mainloop {
     static constexpr int SB = B_RUN + PAD;
     static constexpr int B_ELEMS = B_ROWS * SB;
     static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
-    static constexpr unsigned STAGE_TX_BYTES = (unsigned)((A_ROWS * A_RUN + B_ROWS * B_RUN) * sizeof(double));
+    static constexpr unsigned bytes_of(int mode, int elems, int rows, int run) {
+        return copy_is_gen(mode) ? 0u : (unsigned)((copy_is_blk(mode) ? elems : rows * run) * sizeof(double));
+    }
+    // bytes moved by the TMA unit per stage, announced by thread 0 together with its arrival
+    static constexpr unsigned STAGE_TX_BYTES =
+        bytes_of(A_MODE_, A_ELEMS, A_ROWS, A_RUN) + bytes_of(B_MODE_, B_ELEMS, B_ROWS, B_RUN);
+    static constexpr bool ANY_GEN = copy_is_gen(A_MODE_) || copy_is_gen(B_MODE_);
+    static constexpr bool ANY_ROWS_TMA = A_MODE_ == ROWS_TMA || B_MODE_ == ROWS_TMA;
+    // only thread 0 has anything to do in produce(): warps 1..7 can skip it entirely
+    static constexpr bool SOLO = !ANY_GEN && !ANY_ROWS_TMA;
     static constexpr int RING_ELEMS = STAGES * STAGE_ELEMS;
     static constexpr size_t SMEM_BYTES = (size_t)RING_ELEMS * sizeof(double);
     static constexpr int BAR_WORDS = 2 * STAGES;    // uint64 barriers needed (full + empty)
@@ -68,7 +96,8 @@ struct Mainloop {
         ring.abort_word = abort_word;
         if (threadIdx.x == 0) {
             for (int s = 0; s < STAGES; ++s) {
-                mbar_init(ring.full + s, 1);
+                // thread 0's arrival (+ TMA bytes), plus one pre-counted cp.async arrival per thread in GEN modes
+                mbar_init(ring.full + s, 1 + (ANY_GEN ? NTHREADS : 0));
                 mbar_init(ring.empty + s, NTHREADS / 32);
             }
             fence_mbar_init();
@@ -93,9 +122,10 @@ struct Mainloop {
         return (warp % WARPS_N) * WN + j * 8 + 2 * (lane & 3) + e;
     }
 
-    // This warp's share of one operand tile: rows [warp*ROWS/8, (warp+1)*ROWS/8), one bulk copy per lane.
+    // ---- copy engines -------------------------------------------------------------------------------------
+    // TMA, one copy per row: this warp's share is rows [warp*ROWS/8, (warp+1)*ROWS/8), one copy per lane.
     template <int ROWS, int RUN, int STRIDE>
-    __device__ static __forceinline__ void issue_rows(double* s, const double* g, long ld, uint64_t* bar) {
+    __device__ static __forceinline__ void rows_tma(double* s, const double* g, long ld, uint64_t* bar) {
         constexpr int PER_WARP = ROWS / 8;
         static_assert(ROWS % 8 == 0 && PER_WARP <= 32, "row split");
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -104,18 +134,53 @@ struct Mainloop {
             bulk_g2s(s + r * STRIDE, g + (long)r * ld, RUN * (unsigned)sizeof(double), bar);
         }
     }
+    // generic proxy, padded rows
+    template <int ROWS, int RUN, int STRIDE>
+    __device__ static __forceinline__ void rows_gen(double* s, const double* g, long ld) {
+        constexpr int CH_PER_ROW = RUN / 2;
+        constexpr int TOTAL = ROWS * CH_PER_ROW;
+        static_assert(TOTAL % NTHREADS == 0, "tile copy must divide evenly");
+#pragma unroll
+        for (int t = 0; t < TOTAL / NTHREADS; ++t) {
+            int id = threadIdx.x + t * NTHREADS;
+            int r = id / CH_PER_ROW, c = (id % CH_PER_ROW) * 2;
+            cp_async16(s + r * STRIDE + c, g + (long)r * ld + c);
+        }
+    }
+    // generic proxy, contiguous padded image of ELEMS doubles
+    template <int ELEMS>
+    __device__ static __forceinline__ void blk_gen(double* s, const double* g) {
+        constexpr int TOTAL = ELEMS / 2;
+#pragma unroll
+        for (int t = 0; t < (TOTAL + NTHREADS - 1) / NTHREADS; ++t) {
+            int id = threadIdx.x + t * NTHREADS;
+            if (TOTAL % NTHREADS == 0 || id < TOTAL) cp_async16(s + 2 * id, g + 2 * id);
+        }
+    }
 
     template <class Src>
     __device__ static __forceinline__ bool produce(double* smem, Ring& ring, unsigned it_load, int chunk, Src& src) {
+        if (SOLO && threadIdx.x >= 32) return true;   // warp 0 alone feeds the ring
         const int s = it_load % STAGES;
         const unsigned ph = (it_load / STAGES) & 1u;
         if (!mbar_wait(ring.empty + s, ph ^ 1u, ring.abort_word)) return false;   // all warps done with this stage
         if (!src.ready(chunk)) return false;                                       // dataflow: operand tiles published
         double* As = smem + s * STAGE_ELEMS;
         double* Bs = As + A_ELEMS;
-        if (threadIdx.x == 0) mbar_arrive_expect_tx(ring.full + s, STAGE_TX_BYTES);
-        issue_rows<A_ROWS, A_RUN, SA>(As, src.a_ptr(chunk), src.lda, ring.full + s);
-        issue_rows<B_ROWS, B_RUN, SB>(Bs, src.b_ptr(chunk), src.ldb, ring.full + s);
+        uint64_t* bar = ring.full + s;
+        if (threadIdx.x == 0) {
+            if (STAGE_TX_BYTES) mbar_arrive_expect_tx(bar, STAGE_TX_BYTES);
+            else mbar_arrive(bar);
+            if (A_MODE == BLK_TMA) bulk_g2s(As, src.a_ptr(chunk), (unsigned)(A_ELEMS * sizeof(double)), bar);
+            if (B_MODE == BLK_TMA) bulk_g2s(Bs, src.b_ptr(chunk), (unsigned)(B_ELEMS * sizeof(double)), bar);
+        }
+        if (A_MODE == ROWS_TMA) rows_tma<A_ROWS, A_RUN, SA>(As, src.a_ptr(chunk), src.lda, bar);
+        if (B_MODE == ROWS_TMA) rows_tma<B_ROWS, B_RUN, SB>(Bs, src.b_ptr(chunk), src.ldb, bar);
+        if (A_MODE == ROWS_GEN) rows_gen<A_ROWS, A_RUN, SA>(As, src.a_ptr(chunk), src.lda);
+        if (B_MODE == ROWS_GEN) rows_gen<B_ROWS, B_RUN, SB>(Bs, src.b_ptr(chunk), src.ldb);
+        if (A_MODE == BLK_GEN) blk_gen<A_ELEMS>(As, src.a_ptr(chunk));
+        if (B_MODE == BLK_GEN) blk_gen<B_ELEMS>(Bs, src.b_ptr(chunk));
+        if (ANY_GEN) cp_async_mbar_arrive_noinc(bar);   // fires when this thread's cp.async of the stage have landed
         return true;
     }
 
@@ -187,8 +252,8 @@ struct PlainSrc {
     __device__ __forceinline__ bool ready(int) const { return true; }
 };
 
-// Warp-level wait for up to two dataflow flags (lane 0 polls, result broadcast), then order the async proxy
-// behind the acquire so the bulk copies that follow see the published tiles.
+// Warp-level wait for up to two dataflow flags: lane 0 polls with acquire loads, the result is broadcast, and
+// __syncwarp orders the other lanes' subsequent (generic-proxy) loads of the published tile behind the acquire.
 __device__ __forceinline__ bool warp_wait_flags(const unsigned* f0, const unsigned* f1, unsigned epoch, int* abort_word) {
     int ok = 1;
     if ((threadIdx.x & 31) == 0) {
@@ -196,8 +261,13 @@ __device__ __forceinline__ bool warp_wait_flags(const unsigned* f0, const unsign
         if (ok && f1) ok = wait_flag(f1, epoch, abort_word);
     }
     ok = __shfl_sync(0xffffffffu, ok, 0);
-    fence_proxy_async();
-    return ok != 0;
+    __syncwarp();
+    if (ok) {   // every lane performs its own acquire of the (already set) flags before it touches the tile
+        unsigned v = ld_acquire(f0);
+        if (f1) v &= ld_acquire(f1);
+        if (v != epoch) ok = 0;
+    }
+    return __all_sync(0xffffffffu, ok) != 0;
 }
 
 }  // namespace geordd

@@ -16,7 +16,8 @@
 
 namespace geordd {
 
-using PotrfML = Mainloop<128, /*A_MC=*/true, /*B_NC=*/true, 4>;
+// Flagged dataflow kernel: both operands are moved with generic-proxy block copies (mainloop.cuh RULE).
+using PotrfML = Mainloop<128, /*A_MC=*/true, /*B_NC=*/true, 4, BLK_GEN, BLK_GEN>;
 constexpr int CHUNKS_PER_TILE = TILE / BK;
 
 struct PotrfSrc {
@@ -26,11 +27,12 @@ struct PotrfSrc {
     const unsigned* flags;
     unsigned epoch;
     int* abort_word;
+    // chunk c = columns [16c, 16c+16) of block row i (A) / j (B): 16 consecutive columns of one TBP tile
     __device__ __forceinline__ const double* a_ptr(int c) const {
-        return L + (long)(c * BK) * lda + (long)i * TILE;
+        return L + tile_off(i, c / CHUNKS_PER_TILE, T) + (long)(c % CHUNKS_PER_TILE) * BK * TLD;
     }
     __device__ __forceinline__ const double* b_ptr(int c) const {
-        return L + (long)(c * BK) * ldb + (long)j * TILE;
+        return L + tile_off(j, c / CHUNKS_PER_TILE, T) + (long)(c % CHUNKS_PER_TILE) * BK * TLD;
     }
     __device__ __forceinline__ bool ready(int c) const {   // warp level
         if (c % CHUNKS_PER_TILE != 0) return true;
@@ -81,7 +83,7 @@ potrf_dataflow_kernel(const double* __restrict__ A, double* __restrict__ L, long
                     for (int e = 0; e < 2; ++e)
                         acc.v[a][b][e] = -ldcg(Aij + (long)PotrfML::acc_col(b, e) * ld + PotrfML::acc_row(a));
         }
-        PotrfSrc src{L, ld, ld, i, j, T, flags, epoch, abort_word};
+        PotrfSrc src{L, 0, 0, i, j, T, flags, epoch, abort_word};
         bool ok = PotrfML::run(smem, ring, j * CHUNKS_PER_TILE, src, acc);
         if (__syncthreads_or(!ok)) break;   // also: every warp is done reading the ring before Cs overwrites it
 #pragma unroll
@@ -93,7 +95,7 @@ potrf_dataflow_kernel(const double* __restrict__ A, double* __restrict__ L, long
                     Cs[PotrfML::acc_col(b, e) * SC + PotrfML::acc_row(a)] = -acc.v[a][b][e];
         __syncthreads();
 
-        double* Lij = L + (long)j * TILE * ld + (long)i * TILE;
+        double* Lij = L + tile_off(i, j, T);   // stored image: (m, n) at n * TLD + m, same as Cs (SC == TLD)
         if (i == j) {
             potrf_tile(Cs, invd, &sh_info);
             __syncthreads();
@@ -101,18 +103,18 @@ potrf_dataflow_kernel(const double* __restrict__ A, double* __restrict__ L, long
                 if (tid == 0) atomicCAS(abort_word, 0, j * TILE + sh_info);
                 break;
             }
-            for (int idx = tid; idx < TILE * TILE; idx += NTHREADS) {
-                int n = idx / TILE, m = idx % TILE;
-                Lij[(long)n * ld + m] = (m >= n) ? Cs[n * SC + m] : 0.0;
+            for (int idx = tid; idx < TILE * TLD; idx += NTHREADS) {
+                int n = idx / TLD, m = idx % TLD;
+                Lij[idx] = (m < TILE && m >= n) ? Cs[n * SC + m] : 0.0;
             }
         } else {
             int okf = 1;
             if (tid == 0) okf = wait_flag(flags + (long)j * T + j, epoch, abort_word);
             if (!__syncthreads_and(okf)) break;
-            trsm_right_tile(Cs, Lp, invd, L + (long)j * TILE * ld + (long)j * TILE, ld);
-            for (int idx = tid; idx < TILE * TILE; idx += NTHREADS) {
-                int n = idx / TILE, m = idx % TILE;
-                Lij[(long)n * ld + m] = Cs[n * SC + m];
+            trsm_right_tile(Cs, Lp, invd, L + tile_off(j, j, T), TLD);
+            for (int idx = tid; idx < TILE * TLD; idx += NTHREADS) {
+                int m = idx % TLD;
+                Lij[idx] = (m < TILE) ? Cs[idx] : 0.0;
             }
         }
         __threadfence();
@@ -155,28 +157,69 @@ void launch_potrf(cudaStream_t st, Sched& sched, const double* A, double* L, lon
 // After the factorisation: store L' in the (otherwise unused) tiles above the diagonal, M(j-block, i-block) =
 // L(i-block, j-block)' for i > j, so that backward solves read both L and L' with the row index contiguous.
 // Diagonal tiles keep their explicit zeros above the diagonal (the TRMM path relies on them).
-__global__ void __launch_bounds__(256) mirror_factor_kernel(double* __restrict__ L, long ld, int T) {
+__global__ void __launch_bounds__(256) mirror_factor_kernel(double* __restrict__ L, int T) {
     __shared__ double t[64][65];
-    // 64x64 sub-tiles of the strictly-lower 128-tiles
+    // 64x64 quarters of the tiles strictly below the block diagonal
     const int S = 2 * T;
     int bi = blockIdx.x % S, bj = blockIdx.x / S;          // 64-block row / col
-    if (bi / 2 <= bj / 2) return;                           // only tiles strictly below the 128-diagonal
+    const int I = bi / 2, J = bj / 2;
+    if (I <= J) return;
+    const double* src = L + tile_off(I, J, T) + (long)(bj % 2) * 64 * TLD + (bi % 2) * 64;
+    double* dst = L + tile_off(J, I, T) + (long)(bi % 2) * 64 * TLD + (bj % 2) * 64;
     const int tx = threadIdx.x % 64, ty0 = threadIdx.x / 64;
-    for (int c = ty0; c < 64; c += 4) t[c][tx] = L[(long)(bj * 64 + c) * ld + bi * 64 + tx];
+    for (int c = ty0; c < 64; c += 4) t[c][tx] = src[(long)c * TLD + tx];
     __syncthreads();
-    for (int c = ty0; c < 64; c += 4) L[(long)(bi * 64 + c) * ld + bj * 64 + tx] = t[tx][c];
+    for (int c = ty0; c < 64; c += 4) dst[(long)c * TLD + tx] = t[tx][c];
 }
 
-void launch_mirror_factor(cudaStream_t st, double* L, long ld, int npad) {
+void launch_mirror_factor(cudaStream_t st, double* L, int npad) {
     const int T = npad / TILE;
     if (T < 2) return;
-    mirror_factor_kernel<<<4 * T * T, 256, 0, st>>>(L, ld, T); ++g_kernel_launches;
+    mirror_factor_kernel<<<4 * T * T, 256, 0, st>>>(L, T); ++g_kernel_launches;
 }
 
-__global__ void logdiag_sum_kernel(const double* __restrict__ L, long ld, int n, double* out) {
+// dense lower triangle -> TBP factor ([L 0; 0 I] padding, explicit zeros above the diagonal of diagonal tiles)
+__global__ void factor_pack_kernel(const double* __restrict__ dense, long ldd, int n, double* __restrict__ L, int T) {
+    const int I = blockIdx.x % T, J = blockIdx.x / T;
+    if (I < J) return;
+    double* dst = L + tile_off(I, J, T);
+    for (int idx = threadIdx.x; idx < TILE * TLD; idx += blockDim.x) {
+        int c = idx / TLD, r = idx % TLD;
+        int gr = I * TILE + r, gc = J * TILE + c;
+        double v = 0.0;
+        if (r < TILE && gr >= gc) {
+            if (gr < n && gc < n) v = dense[(long)gc * ldd + gr];
+            else if (gr == gc) v = 1.0;
+        }
+        dst[idx] = v;
+    }
+}
+void launch_factor_pack(cudaStream_t st, const double* dense, long ldd, int n, double* L, int npad) {
+    const int T = npad / TILE;
+    factor_pack_kernel<<<T * T, 256, 0, st>>>(dense, ldd, n, L, T); ++g_kernel_launches;
+}
+
+// TBP lower factor -> dense n x n (strict upper zero); transpose = true writes U = L' (upper)
+__global__ void factor_unpack_kernel(const double* __restrict__ L, int T, double* __restrict__ dense, long ldd, int n,
+                                     int transpose) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)n * n) return;
+    int r = (int)(idx % n), c = (int)(idx / n);          // destination element (r, c), coalesced along r
+    int lr = transpose ? c : r, lc = transpose ? r : c;  // source element of L
+    double v = 0.0;
+    if (lr >= lc) v = L[tile_off(lr / TILE, lc / TILE, T) + (long)(lc % TILE) * TLD + lr % TILE];
+    dense[(long)c * ldd + r] = v;
+}
+void launch_factor_unpack(cudaStream_t st, const double* L, int npad, double* dense, long ldd, int n, bool transpose) {
+    long tot = (long)n * n;
+    factor_unpack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(L, npad / TILE, dense, ldd, n, transpose ? 1 : 0); ++g_kernel_launches;
+}
+
+__global__ void logdiag_sum_kernel(const double* __restrict__ L, int T, int n, double* out) {
     __shared__ double red[32];
     double s = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s += log(L[(long)i * ld + i]);
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        s += log(L[tile_off(i / TILE, i / TILE, T) + (long)(i % TILE) * TLD + i % TILE]);
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
     __syncthreads();
@@ -187,8 +230,8 @@ __global__ void logdiag_sum_kernel(const double* __restrict__ L, long ld, int n,
     }
 }
 
-void launch_logdiag_sum(cudaStream_t st, const double* L, long ld, int n, double* out) {
-    logdiag_sum_kernel<<<1, 1024, 0, st>>>(L, ld, n, out); ++g_kernel_launches;
+void launch_logdiag_sum(cudaStream_t st, const double* L, int npad, int n, double* out) {
+    logdiag_sum_kernel<<<1, 1024, 0, st>>>(L, npad / TILE, n, out); ++g_kernel_launches;
 }
 
 }  // namespace geordd

@@ -15,6 +15,7 @@
 // atomic counter; a job waits only on lower-index jobs of its own slab (acquire-polled flags).
 // With many slabs nobody ever waits; with few slabs (cliff face: nb = 100 sentinels) the row blocks
 // of one slab pipeline across CTAs instead of serialising on one SM.
+#include <cstdlib>
 #include "kernels.h"
 #include "mainloop.cuh"
 #include "tileops.cuh"
@@ -26,9 +27,12 @@ constexpr int CHUNKS_PER_TILE_S = TILE / BK;
 
 // All three modes read the factor with the row index contiguous: forward / TRMM from the lower tiles of L,
 // backward from the mirrored upper tiles (L' stored above the diagonal by launch_mirror_factor).
+// Triangular multiply (no flags): factor chunk = ONE TMA block copy, Z rows = TMA row copies.
+// Solves (flagged dataflow): both operands through the generic proxy (mainloop.cuh RULE).
 template <int MODE>
 struct SolveCfg {
-    using ML = Mainloop<SLAB, /*A_MC=*/true, /*B_NC=*/false, 4>;
+    using ML = Mainloop<SLAB, /*A_MC=*/true, /*B_NC=*/false, 4, MODE == SOLVE_TRMM ? BLK_TMA : BLK_GEN,
+                        MODE == SOLVE_TRMM ? ROWS_TMA : ROWS_GEN>;
 };
 
 template <int MODE>
@@ -45,9 +49,9 @@ struct SolveSrc {
     }
     __device__ __forceinline__ const double* a_ptr(int c) const {
         int kt = ktile(c), kk = (c % CHUNKS_PER_TILE_S) * BK;
-        // A(m,k) = M(rb*128+m, kt*128+kk+k), m contiguous.  kt < rb: lower tile of L; kt > rb (backward): the
-        // mirrored tile holding L(kt-block, rb-block)'.
-        return L + ((long)kt * TILE + kk) * lda + (long)rb * TILE;
+        // A(m,k) = M(rb*128+m, kt*128+kk+k): 16 consecutive columns of TBP tile (rb, kt).  kt < rb: lower tile of L;
+        // kt > rb (backward): the mirrored tile holding L(kt-block, rb-block)'.
+        return L + tile_off(rb, kt, T) + (long)kk * TLD;
     }
     __device__ __forceinline__ const double* b_ptr(int c) const {
         int kt = ktile(c), kk = (c % CHUNKS_PER_TILE_S) * BK;
@@ -61,8 +65,7 @@ struct SolveSrc {
 };
 
 struct SolveParams {
-    const double* L;
-    long ldl;
+    const double* L;   // TBP factor storage
     int T;
     double* B;         // FWD/BWD: in place.  TRMM: input Z
     long ldb;
@@ -76,7 +79,7 @@ struct SolveParams {
 
 constexpr int SOLVE_CS_ELEMS = SLAB * SC;                       // 8448
 constexpr int SOLVE_PANEL_ELEMS = TILE * LRS;                   // 4608 >= NB*SC = 4224
-constexpr int SOLVE_RING_ELEMS = SolveCfg<0>::ML::RING_ELEMS;
+constexpr int SOLVE_RING_ELEMS = SolveCfg<0>::ML::RING_ELEMS;   // identical for the three modes
 constexpr int SOLVE_WORK_ELEMS = SOLVE_CS_ELEMS + SOLVE_PANEL_ELEMS + NB;
 constexpr int SOLVE_SMEM_ELEMS = (SOLVE_RING_ELEMS > SOLVE_WORK_ELEMS ? SOLVE_RING_ELEMS : SOLVE_WORK_ELEMS) + SolveCfg<0>::ML::BAR_WORDS;
 constexpr size_t SOLVE_SMEM = (size_t)SOLVE_SMEM_ELEMS * sizeof(double);
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) solve_dataflow_kernel(SolveParams
                     for (int e = 0; e < 2; ++e)
                         acc.v[a][b][e] = -ldcg(Brb + (long)ML::acc_col(b, e) * p.ldb + ML::acc_row(a));
         }
-        SolveSrc<MODE> src{p.L, Bslab, p.ldl, p.ldb, rb, p.T, s, p.nslabs, p.flags, p.epoch, p.abort_word};
+        SolveSrc<MODE> src{p.L, Bslab, 0, p.ldb, rb, p.T, s, p.nslabs, p.flags, p.epoch, p.abort_word};
         int nchunks = (MODE == SOLVE_FWD) ? rb * CHUNKS_PER_TILE_S
                     : (MODE == SOLVE_BWD) ? (p.T - 1 - rb) * CHUNKS_PER_TILE_S
                                           : (rb + 1) * CHUNKS_PER_TILE_S;
@@ -137,9 +140,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) solve_dataflow_kernel(SolveParams
                 for (int e = 0; e < 2; ++e) Cs[ML::acc_col(b, e) * SC + ML::acc_row(a)] = sgn * acc.v[a][b][e];
         __syncthreads();
 
-        const double* Ldiag = p.L + (long)rb * TILE * p.ldl + (long)rb * TILE;
-        if (MODE == SOLVE_FWD) solve_fwd_tile(Cs, SLAB, Lp, invd, Ldiag, p.ldl);
-        if (MODE == SOLVE_BWD) solve_bwd_tile(Cs, SLAB, Lp, invd, Ldiag, p.ldl);
+        const double* Ldiag = p.L + tile_off(rb, rb, p.T);
+        if (MODE == SOLVE_FWD) solve_fwd_tile(Cs, SLAB, Lp, invd, Ldiag, TLD);
+        if (MODE == SOLVE_BWD) solve_bwd_tile(Cs, SLAB, Lp, invd, Ldiag, TLD);
 
         const SolveEpilogue& e = p.epi;
         if (MODE == SOLVE_TRMM) {
@@ -210,13 +213,15 @@ static void launch_mode(cudaStream_t st, Sched& sched, const SolveParams& p) {
     int njobs = p.T * p.nslabs;
     int grid = 2 * sched.num_sms;
     if (grid > njobs) grid = njobs;
+
     solve_dataflow_kernel<MODE><<<grid, NTHREADS, SOLVE_SMEM, st>>>(p); ++g_kernel_launches;
 }
 
-void launch_solve(cudaStream_t st, Sched& sched, SolveMode mode, const double* L, long ldl, int npad, double* B,
-                  long ldb, int ncols, const SolveEpilogue& epi) {
+
+void launch_solve(cudaStream_t st, Sched& sched, SolveMode mode, const double* L, int npad, double* B, long ldb,
+                  int ncols, const SolveEpilogue& epi) {
     SolveParams p;
-    p.L = L; p.ldl = ldl; p.T = npad / TILE; p.B = B; p.ldb = ldb; p.nslabs = ncols / SLAB;
+    p.L = L; p.T = npad / TILE; p.B = B; p.ldb = ldb; p.nslabs = ncols / SLAB;
     p.flags = sched.flags; p.counter = sched.counter; p.abort_word = sched.abort_word; p.epi = epi;
     cudaMemsetAsync(sched.counter, 0, sizeof(unsigned), st);
     sched.epoch++;
@@ -227,3 +232,4 @@ void launch_solve(cudaStream_t st, Sched& sched, SolveMode mode, const double* L
 }
 
 }  // namespace geordd
+

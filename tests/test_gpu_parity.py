@@ -426,3 +426,57 @@ def test_full_size_identities_c4(G, O, ctx):
     assert np.all(chi > 0) and np.all(np.isfinite(malt))
     # sanity against the null distribution: E[chi2] = rank-ish, well below nb + 6 sd
     assert 1.0 < chi.mean() < 100 + 6 * math.sqrt(200)
+
+
+# ---------------------------------------------------------------------------------------------
+# Stress: the batched dataflow solves with MANY right-hand sides (more jobs than resident CTAs, real flag
+# waits, persistent CTAs running many jobs).  Every column is checked -- this is the regime in which a ring fed
+# by bulk async copies produced rare wrong tiles during round 1 (scripts/gpu_stress_solve.py).
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,nrhs", [(1000, 20000), (700, 5632), (2000, 8192)])
+def test_many_rhs_triangular_ops_every_column(G, O, ctx, n, nrhs):
+    import ctypes as C
+    import scipy.linalg as sl
+    rng = np.random.default_rng(n)
+    X = rng.random((2, n))
+    K = O.cov_sym(O.KernelSpec(O.MAT32, 0.3, 1.0, 400.0), X, 0.09)
+    L = np.asfortranarray(np.linalg.cholesky(K))
+    B = np.asfortranarray(rng.standard_normal((n, nrhs)))
+    refs = {2: L @ B, 0: sl.solve_triangular(L, B, lower=True), 1: sl.solve_triangular(L.T, B, lower=False)}
+    for mode in (2, 0, 1):
+        for rep in range(2):
+            out = B.copy(order="F")
+            ctx.check(ctx.lib.geordd_dbg_trsm(ctx._h, mode, G.capi.dptr(L), n, G.capi.dptr(out), nrhs, None))
+            err = np.abs(out - refs[mode]).max(axis=0) / np.abs(refs[mode]).max()
+            assert int((err > 1e-10).sum()) == 0, (mode, rep, float(err.max()))
+
+
+@pytest.mark.parametrize("m", [1000, 2000])
+def test_null_identities_every_draw_at_scale(G, O, ctx, m):
+    """20 000 device draws: y = L_N z  =>  mll_null + z'z/2 is the same constant for EVERY draw (1e-9), the chi2
+    statistics are finite and distributed like a null (no outliers from corrupted tiles), and repeated runs are
+    bit-identical."""
+    d = O.synth_two_region(m, 100, seed=1)
+    k = G.Mat32Iso(math.log(0.3), 0.0) + G.Const(math.log(20.0))
+    ln = math.log(0.3)
+    gT, gC = G.GPE(d["XT"], d["YT"], G.MeanZero(), k, ln), G.GPE(d["XC"], d["YC"], G.MeanZero(), k, ln)
+    gN = G.NullGPE(gT, gC, d["Xb"], 0.0)
+    S = 20000
+    _, _, mnull, malt = G.nsim_logP(gT, gC, gN, S, seed=5, return_count=True)
+    Z = np.zeros((2 * m, S), order="F")
+    ctx.check(ctx.lib.geordd_dbg_normals(ctx._h, 5, 0, S, 2 * m, G.capi.dptr(Z)))
+    v = mnull + np.sum(Z * Z, axis=0) / 2.0
+    const = np.median(v)
+    assert np.max(np.abs(v - const)) < 1e-9 * abs(const)
+    chi = G.nsim_chi(gT, gC, gN, d["Xb"], S, seed=5)
+    chi2_ = G.nsim_chi(gT, gC, gN, d["Xb"], S, seed=5)
+    assert np.array_equal(chi, chi2_)
+    _, _, mnull2, malt2 = G.nsim_logP(gT, gC, gN, S, seed=5, return_count=True)
+    assert np.array_equal(mnull, mnull2) and np.array_equal(malt, malt2)
+    assert np.all(np.isfinite(chi)) and chi.max() < 20 * chi.mean() and 5.0 < chi.mean() < 60.0
+    # 16 draws against the CPU oracle
+    spec = O.KernelSpec(O.MAT32, 0.3, 1.0, 400.0)
+    oT, oC = O.gp_fit(spec, d["XT"], d["YT"], ln), O.gp_fit(spec, d["XC"], d["YC"], ln)
+    idx = np.array([0, 1, 63, 64, 4095, 4096, 9999, 10000, 12345, 15000, 16383, 16384, 19000, 19935, 19998, 19999])
+    so = O.nsim_chi(oT, oC, O.make_null(oT, oC), d["Xb"], Z[:, idx])
+    assert relerr(chi[idx], so) < 1e-8
