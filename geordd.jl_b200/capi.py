@@ -80,6 +80,7 @@ _SIGS = {
                                    c_double_p, c_ll_p]),
     "geordd_null_invvar": (C.c_int, [C.c_void_p, C.c_long, C.c_ulonglong, C.c_ulonglong, c_double_p, C.c_double,
                                      c_double_p, c_ll_p]),
+    "geordd_null_invvar_calib": (C.c_int, [C.c_void_p, C.c_long, C.c_ulonglong, C.c_ulonglong, c_double_p, c_double_p]),
     "geordd_null_mll": (C.c_int, [C.c_void_p, C.c_long, C.c_ulonglong, C.c_ulonglong, c_double_p, C.c_double,
                                   c_double_p, c_double_p, c_ll_p, c_double_p, c_double_p]),
     "geordd_null_all": (C.c_int, [C.c_void_p, C.c_long, C.c_ulonglong, C.c_ulonglong, c_double_p, C.c_double,

@@ -844,6 +844,22 @@ int geordd_power(geordd_null* h, double tau, long nsim, unsigned long long seed,
     API_END
 }
 
+int geordd_null_invvar_calib(geordd_null* h, long nsim, unsigned long long seed, unsigned long long draw0, const double* Z,
+                             double* pvals) {
+    if (!h) return GEORDD_ERR_ARG;
+    API_BEGIN(h->ctx)
+    if (!pvals) throw ApiError(GEORDD_ERR_ARG, "null_invvar_calib: output is NULL");
+    SimRequest rq;
+    rq.want_cliff = true; rq.nsim = nsim; rq.seed = seed; rq.draw0 = draw0; rq.Z = Z;
+    rq.chi_obs = INFINITY; rq.pval_obs = -1.0;
+    std::vector<double> num(nsim);
+    rq.num = num.data();
+    run_sims(h, rq);
+    const double sd = std::sqrt(null_cov_mu_tau(h, false));   // draw independent (hoisted)
+    for (long s = 0; s < nsim; ++s) pvals[s] = 2.0 * (std::erfc(std::fabs(num[s]) / sd * 0.7071067811865476) / 2.0);
+    API_END
+}
+
 int geordd_null_destroy(geordd_null* h) {
     if (!h) return 0;
     try { geordd::ctx_use(h->ctx); } catch (...) { return GEORDD_ERR_CUDA; }

@@ -584,6 +584,19 @@ def pval_invvar_calib(gpT: GPE, gpC: GPE, Xb, nugget: float = 1e-10) -> float:
     return p.value
 
 
+def nsim_invvar_calib(gpT: GPE, gpC: GPE, Xb, nsim: int, nugget: float = 1e-10, *, seed: int = 0, draw0: int = 0, Z=None,
+                      gpNull: Optional[NullGPE] = None) -> np.ndarray:
+    """nsim_invvar_calib(gpT, gpC, Xb, nsim) (src/hypotest_invvar.jl:138-160): the analytically calibrated p-value of
+    every null draw (the draw-independent covariance term is computed once)."""
+    gpNull = gpNull or make_null(gpT, gpC)
+    gpNull._ensure(Xb, nugget)
+    Zf, nz = _zarg(Z, gpNull.nobs)
+    nsim = nz if nz is not None else int(nsim)
+    pv = np.empty(nsim)
+    gpT.ctx.check(gpT.ctx.lib.geordd_null_invvar_calib(gpNull._h, nsim, seed, draw0, dptr(Zf), dptr(pv)))
+    return pv
+
+
 def nsim_logP(gpT: GPE, gpC: GPE, gpNull: NullGPE, nsim: int, *, seed: int = 0, draw0: int = 0, Z=None,
               dmll_obs: float = math.inf, return_count: bool = False):
     """nsim_logP(gpT, gpC, gpNull, nsim) (src/hypotest_mll.jl:21-30): list of (mll_null, mll_alt).

@@ -144,6 +144,11 @@ GEORDD_API int geordd_null_chi2(geordd_null* h, long nsim, unsigned long long se
 /* nsim_invvar_pval_uncalib / boot_invvar (src/hypotest_invvar.jl:11-69): pvals, n_below = #{p < pval_obs}. */
 GEORDD_API int geordd_null_invvar(geordd_null* h, long nsim, unsigned long long seed, unsigned long long draw0, const double* Z,
                        double pval_obs, double* pvals, long long* n_below);
+/* sim_invvar_calib! / nsim_invvar_calib (src/hypotest_invvar.jl:138-160): analytically calibrated p-value of every
+ * draw, 2 ccdf(Normal(0, sqrt(cov_mu_tau)), |sum(Sigma_b \ mu_b)|).  The draw-independent cov_mu_tau (:88-99) is
+ * computed once; Sigma_b is the handle's make_posdef!-factored (Sigma + nugget I) (prepare with nugget = 1e-10). */
+GEORDD_API int geordd_null_invvar_calib(geordd_null* h, long nsim, unsigned long long seed, unsigned long long draw0,
+                             const double* Z, double* pvals);
 /* sim_logP! / nsim_logP / boot_mlltest (src/hypotest_mll.jl:1-45): mll_null, mll_alt (nsim, nullable),
  * n_exceed = #{(alt - null) > dmll_obs}.  last_y / last_alpha (n, nullable) receive the pooled GP's y and
  * alpha after the final draw (the reference mutates gpNull, src/hypotest_mll.jl:6,10,14). */

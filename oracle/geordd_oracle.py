@@ -504,6 +504,21 @@ def pval_invvar_calib_pre(ns: NullSetup, KCT: np.ndarray, as_shipped: bool = Fal
     return 2.0 * Normal(0.0, math.sqrt(cov_mt)).ccdf(abs(num))
 
 
+def nsim_invvar_calib(gpT: GP, gpC: GP, Xb: np.ndarray, Z: np.ndarray) -> np.ndarray:
+    """src/hypotest_invvar.jl:138-160: per draw prior_rand -> update_alpha! x2 -> pval_invvar_calib(gpT, gpC, Xb)
+    (3-argument variant: cliff face recomputed, nugget 1e-10, LU)."""
+    gT, gC = modifiable(gpT), modifiable(gpC)
+    gN = make_null(gT, gC)
+    mT = gpT.nobs
+    out = np.empty(Z.shape[1])
+    for s in range(Z.shape[1]):
+        Ysim = prior_rand(gN, Z[:, s])
+        gT.y, gC.y = Ysim[:mT], Ysim[mT:]
+        update_alpha(gT); update_alpha(gC)
+        out[s] = pval_invvar_calib(gT, gC, Xb)
+    return out
+
+
 # ----------------------------------------------------------------------------
 # src/hypotest_mll.jl
 # ----------------------------------------------------------------------------

@@ -252,6 +252,18 @@ def test_nsim_power_matches_oracle(G, O, ctx):
         assert np.max(np.abs(pg[:, 4] - po[:, 4])) < 1e-7
 
 
+def test_nsim_invvar_calib(G, O, ctx):
+    """nsim_invvar_calib (src/hypotest_invvar.jl:138-160): per-draw analytic calibration; the GPU hoists the
+    draw-independent term and uses the Cholesky of Sigma + 1e-10 I where the reference uses LU (well-conditioned
+    Matern-3/2 case, so both agree to 1e-6)."""
+    d, (oT, oC), (gT, gC) = _pair(G, O, m=110, nb=24, kind=2)
+    Z = np.asfortranarray(np.random.default_rng(8).standard_normal((220, 24)))
+    po = O.nsim_invvar_calib(oT, oC, d["Xb"], Z)
+    pg = G.nsim_invvar_calib(gT, gC, d["Xb"], 24, Z=Z)
+    assert np.max(np.abs(pg - po)) < 1e-6
+    assert 0.0 < pg.min() and pg.max() <= 1.0
+
+
 def test_golden_fixtures(G, golden):
     """GPU path against the committed oracle outputs (tests/golden/oracle_small.npz)."""
     g = golden["small"]
