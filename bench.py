@@ -310,9 +310,17 @@ def main():
         solve_n = prof["solve_fwd"][1] + prof["solve_bwd"][1] + prof["trmm"][1]
         algo_flops_per_launch = flops_per_mll_draw(M_SIDE) * S * args.steps / max(solve_n, 1)
         achieved = flops_per_mll_draw(M_SIDE) * S * args.steps / (solve_ms * 1e-3) / 1e12
+        traffic = None
+        try:   # per-launch DRAM traffic of the dominant kernel family from the committed ncu capture (same draw count only)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01c_traffic.json")))
+            if tj.get("draws") == S:
+                traffic = tj["dram_gbytes_per_launch"] * 1e9
+        except Exception:
+            pass
         roofline = {"bound": "tensor", "kernel": "solve_dataflow_kernel<FWD|BWD|TRMM> (FP64 DMMA)",
                     "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak,
-                    "traffic": None, "launches": int(solve_n), "avg_launch_ms": solve_ms / max(solve_n, 1),
+                    "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read+write, avg over the 7 launches of a step)",
+                    "launches": int(solve_n), "avg_launch_ms": solve_ms / max(solve_n, 1),
                     "algorithmic_flops_per_launch": algo_flops_per_launch,
                     "peak_source": "measured live: register-resident mma.sync.m8n8k4.f64 loop (MEASURED_PEAKS.json has no FP64 figure)",
                     "share_of_step": solve_ms / ms}

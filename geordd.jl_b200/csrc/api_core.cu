@@ -549,7 +549,7 @@ int geordd_dbg_normals(geordd_ctx* c, unsigned long long seed, unsigned long lon
     try {
         {
             ProfScope ps(c, PC_RNG);
-            launch_philox_normals(c->stream, seed, draw0, ndraws, n, dZ, npad, npad);
+            launch_philox_normals(c->stream, seed, draw0, ndraws, n, dZ, npad, npad, false);
         }
         download2d(c, Z, n, dZ, npad, n, ndraws);
         GD_CUDA(cudaStreamSynchronize(c->stream));
@@ -649,15 +649,19 @@ int geordd_dbg_trsm(geordd_ctx* c, int mode, const double* L, int n, double* B, 
         launch_mirror_factor(c->stream, dL, npad);
         upload2d(c, dB, npad, B, n, n, nrhs);
         SolveEpilogue epi;
-        if (mode == 2) {
+        double* dIn = dB;
+        if (mode == 2) {   // triangular multiply reads its input in ZB storage
             dO = dalloc((size_t)npad * ncols, c->stream, true);
             epi.out0 = dO; epi.ld0 = npad; epi.nrows = n; epi.split = n;
+            c->tmp1.ensure(zb_elems(npad, ncols), c->stream, false);
+            launch_zb_pack(c->stream, dB, npad, n, nrhs, c->tmp1.p, npad, ncols);
+            dIn = c->tmp1.p;
         }
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         GD_CUDA(cudaStreamSynchronize(c->stream));
         cudaEventRecord(e0, c->stream);
-        launch_solve(c->stream, c->sched, (SolveMode)mode, dL, npad, dB, npad, ncols, epi);
+        launch_solve(c->stream, c->sched, (SolveMode)mode, dL, npad, dIn, npad, ncols, epi);
         cudaEventRecord(e1, c->stream);
         check_abort(c);
         float t = 0.f;

@@ -202,7 +202,7 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
         h->partN.release(); h->partT.release(); h->partC.release(); h->partChi.release(); h->partNum.release();
         h->cap_cols = 0;
     }
-    h->Z.ensure((size_t)npN * cap, st, true);
+    h->Z.ensure(zb_elems(npN, cap), st, true);   // ZB storage
     h->AT.ensure((size_t)mTp * cap, st, true);
     h->AC.ensure((size_t)mCp * cap, st, true);
     if (rq.want_mll) {
@@ -233,13 +233,14 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
         const long live = std::min(cap, rq.nsim - done);
         const int ncols = (int)((live + 63) / 64 * 64);
         // 1. standard normals (column s = draw done+s)
-        if (rq.Z) {
-            if (ncols > live)   // stale columns from a previous larger batch must not leak NaNs
-                GD_CUDA(cudaMemsetAsync(h->Z.p + (size_t)live * npN, 0, (size_t)(ncols - live) * npN * sizeof(double), st));
-            upload2d(c, h->Z.p, npN, rq.Z + (size_t)done * n, n, n, (int)live);
+        if (rq.Z) {   // host normals: stage compactly, then re-block on the device
+            c->tmp2.ensure((size_t)n * live, st, false);
+            GD_CUDA(cudaMemcpyAsync(c->tmp2.p, rq.Z + (size_t)done * n, (size_t)n * live * sizeof(double), cudaMemcpyHostToDevice, st));
+            ProfScope ps(c, PC_MISC);
+            launch_zb_pack(st, c->tmp2.p, n, n, live, h->Z.p, npN, ncols);
         } else {
             ProfScope ps(c, PC_RNG);
-            launch_philox_normals(st, rq.seed, rq.draw0 + (unsigned long long)done, ncols, n, h->Z.p, npN, npN);
+            launch_philox_normals(st, rq.seed, rq.draw0 + (unsigned long long)done, ncols, n, h->Z.p, 0, npN, true);
         }
         // 2. prior_rand: y = m_N + L_N z (+ tau on treated), scattered into residual buffers
         {
@@ -721,14 +722,17 @@ int geordd_gp_prior_rand(geordd_gp* gp, long nsim, unsigned long long seed, unsi
     if (!Y || nsim <= 0) throw ApiError(GEORDD_ERR_ARG, "prior_rand: bad arguments");
     const int n = gp->n, np = gp->npad;
     const int ncols = (int)((nsim + 63) / 64 * 64);
-    double* dZ = dalloc((size_t)np * ncols, c__->stream, true);
+    double* dZ = dalloc(zb_elems(np, ncols), c__->stream, true);
     double* dY = nullptr;
     try {
         dY = dalloc((size_t)np * ncols, c__->stream, true);
-        if (Z) upload2d(c__, dZ, np, Z, n, n, (int)nsim);
-        else {
+        if (Z) {
+            c__->tmp2.ensure((size_t)n * nsim, c__->stream, false);
+            GD_CUDA(cudaMemcpyAsync(c__->tmp2.p, Z, (size_t)n * nsim * sizeof(double), cudaMemcpyHostToDevice, c__->stream));
+            launch_zb_pack(c__->stream, c__->tmp2.p, n, n, nsim, dZ, np, ncols);
+        } else {
             ProfScope ps(c__, PC_RNG);
-            launch_philox_normals(c__->stream, seed, draw0, ncols, n, dZ, np, np);
+            launch_philox_normals(c__->stream, seed, draw0, ncols, n, dZ, 0, np, true);
         }
         SolveEpilogue e;
         e.nrows = n; e.split = n; e.add_const = gp->k.mean_const; e.out0 = dY; e.ld0 = np;

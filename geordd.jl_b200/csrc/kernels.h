@@ -20,6 +20,14 @@ __host__ __device__
 #endif
 inline long tile_off(int I, int J, int T) { return ((long)J * T + I) * TSZ; }
 
+// Standard-normal draws Z are stored SLAB-BLOCKED ("ZB"): for slab s (64 draws) and K-chunk c (16 rows) the block
+// [n = 0..63][k = 0..15 (+4 pad)] is a contiguous 64 x 20 image -- exactly the B stage of the mainloop -- so the
+// triangular multiply moves a chunk of Z with ONE bulk copy.  Element (row r, draw col):
+//   ((col/64) * (npad/16) + r/16) * ZB_ELEMS + (col%64) * ZB_LD + r%16
+constexpr int ZB_LD = BK + 4;
+constexpr int ZB_ELEMS = 64 * ZB_LD;
+inline size_t zb_elems(int npad, long ncols) { return (size_t)(ncols / 64) * (npad / BK) * ZB_ELEMS; }
+
 struct KernelSpecDev {
     int kind;            // 0 SE, 1 Mat12, 2 Mat32, 3 Mat52
     double ell, sigma2, const_sigma2;
@@ -70,7 +78,7 @@ void launch_logdiag_sum(cudaStream_t st, const double* L, int npad, int n, doubl
 enum SolveMode { SOLVE_FWD = 0, SOLVE_BWD = 1, SOLVE_TRMM = 2 };
 // In-place triangular solve / multiply against lower factor L (npad x npad) for ncols right-hand
 // sides (ncols multiple of 64): B (npad x ncols, ldb) is overwritten.
-//   FWD:  B <- L^-1 B      BWD: B <- L^-T B      TRMM: Bout <- L * B (out of place, needs Bout)
+//   FWD:  B <- L^-1 B      BWD: B <- L^-T B      TRMM: out <- L * Z, Z given in ZB storage (ldb ignored)
 // BWD requires launch_mirror_factor to have been applied to L.
 struct SolveEpilogue {
     // FWD/BWD: fused statistic partials, written per row block (deterministic; reduced later):
@@ -103,7 +111,10 @@ void launch_gemm(cudaStream_t st, bool a_mc, bool b_nc, int M, int N, int K, dou
                  const double* B, long ldb, double beta, double* C, long ldc, int splitk, double* ws);
 
 // ---- stats.cu -------------------------------------------------------------------------------------
+// blocked = false: Z is npad x ndraws column-major (ldz);  blocked = true: ZB storage (ndraws multiple of 64).
 void launch_philox_normals(cudaStream_t st, unsigned long long seed, unsigned long long draw0, int ndraws, int n,
-                           double* Z, long ldz, int npad);
+                           double* Z, long ldz, int npad, bool blocked);
+// dense (n x ncols_live, ldz) -> ZB storage for ncols (multiple of 64) draws, zero padded
+void launch_zb_pack(cudaStream_t st, const double* dense, long ldz, int n, long ncols_live, double* Zb, int npad, long ncols);
 
 }  // namespace geordd

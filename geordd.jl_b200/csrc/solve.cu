@@ -27,12 +27,12 @@ constexpr int CHUNKS_PER_TILE_S = TILE / BK;
 
 // All three modes read the factor with the row index contiguous: forward / TRMM from the lower tiles of L,
 // backward from the mirrored upper tiles (L' stored above the diagonal by launch_mirror_factor).
-// Triangular multiply (no flags): factor chunk = ONE TMA block copy, Z rows = TMA row copies.
-// Solves (flagged dataflow): both operands through the generic proxy (mainloop.cuh RULE).
+// Triangular multiply (no flags): factor chunk and Z chunk (ZB storage) are ONE TMA block copy each, issued by
+// thread 0.  Solves (flagged dataflow): both operands through the generic proxy (mainloop.cuh RULE).
 template <int MODE>
 struct SolveCfg {
     using ML = Mainloop<SLAB, /*A_MC=*/true, /*B_NC=*/false, 4, MODE == SOLVE_TRMM ? BLK_TMA : BLK_GEN,
-                        MODE == SOLVE_TRMM ? ROWS_TMA : ROWS_GEN>;
+                        MODE == SOLVE_TRMM ? BLK_TMA : ROWS_GEN>;
 };
 
 template <int MODE>
@@ -54,6 +54,7 @@ struct SolveSrc {
         return L + tile_off(rb, kt, T) + (long)kk * TLD;
     }
     __device__ __forceinline__ const double* b_ptr(int c) const {
+        if (MODE == SOLVE_TRMM) return X + (long)c * ZB_ELEMS;   // ZB storage: chunk c of this slab is one block
         int kt = ktile(c), kk = (c % CHUNKS_PER_TILE_S) * BK;
         return X + (long)kt * TILE + kk;   // B(k,n) = X(kt*128+kk+k, n): k contiguous
     }
@@ -110,7 +111,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) solve_dataflow_kernel(SolveParams
         if (job >= njobs) break;
         const int lvl = job / p.nslabs, s = job % p.nslabs;
         const int rb = (MODE == SOLVE_FWD) ? lvl : (p.T - 1 - lvl);
-        double* Bslab = p.B + (long)s * SLAB * p.ldb;
+        double* Bslab = (MODE == SOLVE_TRMM) ? p.B + (long)s * (p.T * CHUNKS_PER_TILE_S) * ZB_ELEMS   // ZB: slab s
+                                             : p.B + (long)s * SLAB * p.ldb;
 
         typename ML::Acc acc;
         if (MODE == SOLVE_TRMM) {

@@ -23,7 +23,7 @@ __device__ __forceinline__ void philox_round(unsigned& c0, unsigned& c1, unsigne
 }
 
 __global__ void philox_normals_kernel(unsigned long long seed, unsigned long long draw0, int ndraws, int n,
-                                      double* __restrict__ Z, long ldz, int npad) {
+                                      double* __restrict__ Z, long ldz, int npad, int blocked) {
     const int npairp = npad / 2;
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)npairp * ndraws) return;
@@ -50,14 +50,30 @@ __global__ void philox_normals_kernel(unsigned long long seed, unsigned long lon
         z0 = rad * cs;
         z1 = (2 * j + 1 < n) ? rad * sn : 0.0;
     }
-    double2* dst = reinterpret_cast<double2*>(Z + (long)s * ldz + 2 * j);
-    *dst = make_double2(z0, z1);
+    const int r = 2 * j;
+    long off = blocked ? ((long)(s / 64) * (npad / BK) + r / BK) * ZB_ELEMS + (long)(s % 64) * ZB_LD + r % BK
+                       : (long)s * ldz + r;
+    *reinterpret_cast<double2*>(Z + off) = make_double2(z0, z1);
 }
 
 void launch_philox_normals(cudaStream_t st, unsigned long long seed, unsigned long long draw0, int ndraws, int n,
-                           double* Z, long ldz, int npad) {
+                           double* Z, long ldz, int npad, bool blocked) {
     long tot = (long)(npad / 2) * ndraws;
-    philox_normals_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(seed, draw0, ndraws, n, Z, ldz, npad); ++g_kernel_launches;
+    philox_normals_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(seed, draw0, ndraws, n, Z, ldz, npad, blocked ? 1 : 0); ++g_kernel_launches;
+}
+
+__global__ void zb_pack_kernel(const double* __restrict__ dense, long ldz, int n, long live, double* __restrict__ Zb,
+                               int npad, long ncols) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)npad * ncols) return;
+    int r = (int)(idx % npad);
+    long col = idx / npad;
+    double v = (r < n && col < live) ? dense[col * ldz + r] : 0.0;
+    Zb[((col / 64) * (npad / BK) + r / BK) * ZB_ELEMS + (col % 64) * ZB_LD + r % BK] = v;
+}
+void launch_zb_pack(cudaStream_t st, const double* dense, long ldz, int n, long ncols_live, double* Zb, int npad, long ncols) {
+    long tot = (long)npad * ncols;
+    zb_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(dense, ldz, n, ncols_live, Zb, npad, ncols); ++g_kernel_launches;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -3,7 +3,7 @@
 # dominant kernels.  Run under gpurun; results land in gpurun_out/ and summaries are copied to profiles/ by hand.
 set -u
 OUT=gpurun_out
-CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --draws 8192"
+CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --draws 20000"
 $CMD > $OUT/ncu_plain.log 2>&1 || { echo "plain run failed"; tail -5 $OUT/ncu_plain.log; exit 1; }
 tail -c 600 $OUT/ncu_plain.log
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches.csv $CMD > $OUT/ncu_launches.log 2>&1
