@@ -111,11 +111,13 @@ EXPORTED_SYMBOLS = tuple(_SIGS.keys())
 _lib = None
 
 
-def load_library(path: str = LIB_PATH):
-    """dlopen the library (fails loudly if it was not built) and attach prototypes."""
+def load_library(path: str = None):
+    """dlopen the library (fails loudly if it was not built) and attach prototypes.  GEORDD_B200_LIB selects
+    another build of the same library (kernel experiments)."""
     global _lib
     if _lib is not None:
         return _lib
+    path = path or os.environ.get("GEORDD_B200_LIB") or LIB_PATH
     if not os.path.exists(path):
         raise GeorddError(-2, f"{path} not found: build it with `python geordd.jl_b200/build.py` "
                               "(there is no CPU fallback)")

@@ -82,6 +82,11 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(smem_u32(bar)) : "memory");
 }
+// Arrive whose address depends on `dep_zero` (always 0 at run time): the instruction cannot issue before the
+// registers that fed dep_zero are written, i.e. before the shared-memory loads that produced them have returned.
+__device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, unsigned dep_zero) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(smem_u32(bar) + dep_zero) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(smem_u32(bar)),
                  "r"(bytes)

@@ -12,13 +12,19 @@
 //             (tile-blocked padded factor storage, kernels.h)
 //   ROWS_GEN / BLK_GEN   the same two shapes moved with 16-byte cp.async (LDGSTS) by all threads, completion
 //             signalled on the same mbarrier (cp.async.mbarrier.arrive.noinc)
-// RULE (empirical, round 1): the *_TMA modes are used only in kernels WITHOUT inter-CTA dataflow flags (the
-// triangular multiply, the plain GEMM).  The flagged kernels (Cholesky, forward/backward solves) move both
-// operands with the *_GEN modes.  With bulk copies in those kernels a stress test (20 000 right-hand sides
-// against SciPy, scripts/gpu_stress_solve.py) showed rare wrong accumulator tiles -- for the flag-published X
-// blocks AND for the kernel-constant factor tiles -- although the ring contents compared equal to global memory
-// at consume time and the same ring with bulk copies is exact in the flag-free triangular multiply, with injected
-// skew, acquire loads and fences.  The cause was not identified; the generic-proxy ring is exact in all tests.
+// Releasing a stage that the TMA unit refills (any *_TMA mode): the consumer's arrive on `empty` must not issue
+// while the warp's last fragment loads are still in flight.  ptxas sinks the DMMAs that consume those loads below
+// the arrive and SYNCS.ARRIVE does not wait on LDS scoreboards; the refill then comes through the async proxy,
+// which is not ordered behind generic-proxy loads still in the LSU pipe, and can overwrite data not yet read
+// (seen as rare wrong accumulator strips in the flagged solves, where long flag waits keep the ring full; 20 000
+// right-hand sides against SciPy, scripts/gpu_stress_solve.py).  Fix: the arrive's address carries a run-time-zero
+// data dependency on every fragment register of the stage (mbar_arrive_after), so it issues only after all loads
+// of the stage have returned.  A fence.proxy.async before the arrive is the textbook alternative and is also
+// exact, but measured slower.  Refills through the generic proxy (*_GEN) stay ordered behind the loads in the
+// same pipe and need neither.
+// The flagged solves and the Cholesky keep the *_GEN modes: with the dependency in place the bulk-copy variants
+// are exact there too but not faster (row copies of the in-place X are the limiter); the flag-free triangular
+// multiply and the plain GEMM use the TMA modes.
 //
 // Fragments are read with conflict-free LDS.64 (row strides == 4 mod 16 doubles) and multiplied with
 // mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4), 16-32 independent accumulators per warp.
@@ -42,6 +48,7 @@ struct Ring {
     uint64_t* full;    // [STAGES] data landed
     uint64_t* empty;   // [STAGES] stage free (8 arrivals, one per warp)
     unsigned it;       // chunks pushed through the ring so far (same value in every thread)
+    unsigned zero;     // 0 at run time, opaque to nvcc and ptxas (mbar_arrive_after)
     int* abort_word;
 };
 
@@ -77,6 +84,7 @@ struct Mainloop {
     static constexpr unsigned STAGE_TX_BYTES =
         bytes_of(A_MODE_, A_ELEMS, A_ROWS, A_RUN) + bytes_of(B_MODE_, B_ELEMS, B_ROWS, B_RUN);
     static constexpr bool ANY_GEN = copy_is_gen(A_MODE_) || copy_is_gen(B_MODE_);
+    static constexpr bool ANY_TMA = !copy_is_gen(A_MODE_) || !copy_is_gen(B_MODE_);
     static constexpr bool ANY_ROWS_TMA = A_MODE_ == ROWS_TMA || B_MODE_ == ROWS_TMA;
     // only thread 0 has anything to do in produce(): warps 1..7 can skip it entirely
     static constexpr bool SOLO = !ANY_GEN && !ANY_ROWS_TMA;
@@ -93,6 +101,11 @@ struct Mainloop {
         ring.full = bars;
         ring.empty = bars + STAGES;
         ring.it = 0;
+        {
+            unsigned hi;
+            asm volatile("mov.u32 %0, %%clock_hi;" : "=r"(hi));
+            ring.zero = hi >> 31;   // stays 0 for centuries of uptime; cannot be constant-folded
+        }
         ring.abort_word = abort_word;
         if (threadIdx.x == 0) {
             for (int s = 0; s < STAGES; ++s) {
@@ -184,7 +197,10 @@ struct Mainloop {
         return true;
     }
 
-    __device__ static __forceinline__ void compute(const double* smem, int s, Acc& acc) {
+    // Returns the OR of the high words of every fragment loaded from the stage (the release dependency; only
+    // materialised when the TMA unit refills the ring).
+    __device__ static __forceinline__ unsigned compute(const double* smem, int s, Acc& acc) {
+        unsigned token = 0;
         const double* As = smem + s * STAGE_ELEMS;
         const double* Bs = As + A_ELEMS;
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -204,11 +220,18 @@ struct Mainloop {
                 int n = wn0 + j * 8 + g;
                 b[j] = B_NC ? Bs[k * SB + n] : Bs[n * SB + k];
             }
+            if (ANY_TMA) {
+#pragma unroll
+                for (int i = 0; i < MI; ++i) token |= (unsigned)__double2hiint(a[i]);
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) token |= (unsigned)__double2hiint(b[j]);
+            }
 #pragma unroll
             for (int i = 0; i < MI; ++i)
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) dmma(acc.v[i][j][0], acc.v[i][j][1], a[i], b[j]);
         }
+        return token;
     }
 
     // Runs the whole K loop of one job.  Returns false (for this warp) if a wait was aborted; callers combine
@@ -232,9 +255,12 @@ struct Mainloop {
             }
             const int s = it_use % STAGES;
             if (!mbar_wait(ring.full + s, (it_use / STAGES) & 1u, ring.abort_word)) return false;
-            compute(smem, s, acc);
+            const unsigned token = compute(smem, s, acc);
             __syncwarp();
-            if (lane == 0) mbar_arrive(ring.empty + s);
+            if (lane == 0) {
+                if (ANY_TMA) mbar_arrive_after(ring.empty + s, token & ring.zero);
+                else mbar_arrive(ring.empty + s);
+            }
             ++it_use;
         }
         return true;

@@ -16,7 +16,7 @@
 
 namespace geordd {
 
-// Flagged dataflow kernel: both operands are moved with generic-proxy block copies (mainloop.cuh RULE).
+// Flagged dataflow kernel: both operands are moved with generic-proxy block copies (see the stage-release note in mainloop.cuh).
 using PotrfML = Mainloop<128, /*A_MC=*/true, /*B_NC=*/true, 4, BLK_GEN, BLK_GEN>;
 constexpr int CHUNKS_PER_TILE = TILE / BK;
 

@@ -28,7 +28,7 @@ constexpr int CHUNKS_PER_TILE_S = TILE / BK;
 // All three modes read the factor with the row index contiguous: forward / TRMM from the lower tiles of L,
 // backward from the mirrored upper tiles (L' stored above the diagonal by launch_mirror_factor).
 // Triangular multiply (no flags): factor chunk and Z chunk (ZB storage) are ONE TMA block copy each, issued by
-// thread 0.  Solves (flagged dataflow): both operands through the generic proxy (mainloop.cuh RULE).
+// thread 0.  Solves (flagged dataflow): both operands through the generic proxy (see the stage-release note in mainloop.cuh).
 template <int MODE>
 struct SolveCfg {
     using ML = Mainloop<SLAB, /*A_MC=*/true, /*B_NC=*/false, 4, MODE == SOLVE_TRMM ? BLK_TMA : BLK_GEN,

@@ -1,5 +1,5 @@
 """Stress test of the batched dataflow solves: 20 000 right-hand sides against SciPy, every column checked.
-(This is the test that exposed the rare wrong tiles with bulk async copies in the flagged kernels.)"""
+(This is the test that exposed the stage-release race with TMA refills, see mainloop.cuh.)"""
 import ctypes as C, os, sys
 import numpy as np, scipy.linalg as sl
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
