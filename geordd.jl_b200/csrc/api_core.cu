@@ -213,15 +213,16 @@ int make_posdef(geordd_ctx* c, double* K, double* L, long ld, int n, int npad, i
     return -1;
 }
 
-void pd_solve(geordd_ctx* c, const double* L, int npad, double* B, long ldb, int ncols, const SolveEpilogue& epi_bwd) {
+void pd_solve(geordd_ctx* c, const double* L, int npad, double* B, long ldb, int ncols, const SolveEpilogue& epi_bwd,
+              int live_cols) {
     SolveEpilogue none;
     {
         ProfScope ps(c, PC_FWD);
-        launch_solve(c->stream, c->sched, SOLVE_FWD, L, npad, B, ldb, ncols, none);
+        launch_solve(c->stream, c->sched, SOLVE_FWD, L, npad, B, ldb, ncols, none, live_cols);
     }
     {
         ProfScope ps(c, PC_BWD);
-        launch_solve(c->stream, c->sched, SOLVE_BWD, L, npad, B, ldb, ncols, epi_bwd);
+        launch_solve(c->stream, c->sched, SOLVE_BWD, L, npad, B, ldb, ncols, epi_bwd, live_cols);
     }
 }
 
@@ -239,7 +240,7 @@ void gp_update_alpha(geordd_gp* gp) {
     GD_CUDA(cudaMemsetAsync(gp->dAlpha, 0, (size_t)npad * 64 * sizeof(double), c->stream));
     GD_CUDA(cudaMemcpyAsync(gp->dAlpha, gp->dR, (size_t)npad * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     SolveEpilogue none;
-    pd_solve(c, gp->dL, npad, gp->dAlpha, npad, 64, none);
+    pd_solve(c, gp->dL, npad, gp->dAlpha, npad, 64, none, 1);
     launch_reduce(c->stream, 2, gp->dR, gp->dAlpha, 0, gp->n, 0, c->d_scal);
     check_abort(c);
     double quad = read_scalar(c, c->d_scal);
@@ -661,7 +662,7 @@ int geordd_dbg_trsm(geordd_ctx* c, int mode, const double* L, int n, double* B, 
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         GD_CUDA(cudaStreamSynchronize(c->stream));
         cudaEventRecord(e0, c->stream);
-        launch_solve(c->stream, c->sched, (SolveMode)mode, dL, npad, dIn, npad, ncols, epi);
+        launch_solve(c->stream, c->sched, (SolveMode)mode, dL, npad, dIn, npad, ncols, epi, nrhs);
         cudaEventRecord(e1, c->stream);
         check_abort(c);
         float t = 0.f;

@@ -160,7 +160,8 @@ KernelSpecDev to_dev(const geordd_kernel& k);
 // place.  Returns 0 or the LAPACK info after the 11th failed attempt.
 int make_posdef(geordd_ctx* c, double* K, double* L, long ld, int n, int npad, int* rounds);
 // B <- L^-T L^-1 B (ncols multiple of 64) with optional fused epilogue on the backward pass.
-void pd_solve(geordd_ctx* c, const double* L, int npad, double* B, long ldb, int ncols, const SolveEpilogue& epi_bwd);
+void pd_solve(geordd_ctx* c, const double* L, int npad, double* B, long ldb, int ncols, const SolveEpilogue& epi_bwd,
+              int live_cols = 0);
 void gemm(geordd_ctx* c, bool a_mc, bool b_nc, int M, int N, int K, double alpha, const double* A, long lda,
           const double* B, long ldb, double beta, double* C, long ldc, int splitk);
 int pick_splitk(geordd_ctx* c, int M, int N, int K);

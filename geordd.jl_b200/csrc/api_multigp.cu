@@ -150,7 +150,7 @@ static int mg_update_mll(geordd_multigp* h, const geordd_kernel* k, double lin_e
     GD_CUDA(cudaMemsetAsync(h->dAlpha, 0, (size_t)np * 64 * sizeof(double), c->stream));
     GD_CUDA(cudaMemcpyAsync(h->dAlpha, h->dR, (size_t)np * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     SolveEpilogue none;
-    pd_solve(c, h->dL, np, h->dAlpha, np, 64, none);
+    pd_solve(c, h->dL, np, h->dAlpha, np, 64, none, 1);
     launch_reduce(c->stream, 2, h->dR, h->dAlpha, 0, n, 0, c->d_scal);
     check_abort(c);
     double quad = read_scalar(c, c->d_scal);
@@ -347,7 +347,7 @@ int geordd_multigp_postmean_beta(geordd_multigp* h, const geordd_kernel* k, doub
         {
             ProfScope ps(c__, PC_FWD);
             SolveEpilogue none;
-            launch_solve(st, c__->sched, SOLVE_FWD, h->dL, np, W, np, pp, none);
+            launch_solve(st, c__->sched, SOLVE_FWD, h->dL, np, W, np, pp, none, p);
         }
         prec = dalloc((size_t)pp * pp, st, true);
         gemm(c__, false, false, pp, pp, np, 1.0, W, np, W, np, 0.0, prec, pp, 0);
@@ -357,7 +357,7 @@ int geordd_multigp_postmean_beta(geordd_multigp* h, const geordd_kernel* k, doub
         launch_axpby(st, n, 1.0, h->dY, 0.0, rhs);
         launch_add_const(st, rhs, np, n, 1, -k->mean_const);
         SolveEpilogue none;
-        pd_solve(c__, h->dL, np, rhs, np, 64, none);
+        pd_solve(c__, h->dL, np, rhs, np, 64, none, 1);
         // beta = precision \ (D * rhs)    [== (precision \ D) * rhs, :342]
         v = dalloc((size_t)pp * 64, st, true);
         // D (p x n) stored ppad x np column-major: A(m,k) = D(m,k) at k*ppad + m -> a_mc with M = pp needs ld >= pp: use Dt'

@@ -32,7 +32,7 @@ void cliff_face_dev(geordd_gp* T, geordd_gp* C, const double* dXb, int nb, int n
         {
             ProfScope ps(c, PC_FWD);
             SolveEpilogue none;
-            launch_solve(c->stream, c->sched, SOLVE_FWD, gp->dL, mp, Kxb, mp, nbp, none);
+            launch_solve(c->stream, c->sched, SOLVE_FWD, gp->dL, mp, Kxb, mp, nbp, none, nb);
         }
         gemm(c, false, false, nbp, nbp, mp, -1.0, Kxb, mp, Kxb, mp, 1.0, dSigma, nbp, 0);
     }
@@ -110,7 +110,7 @@ static void calib_cov_mu_delta(geordd_gp* T, geordd_gp* C, const double* dXb, in
             ProfScope ps(c, PC_COV);
             launch_cov(c->stream, to_dev(T->k), T->dX, mT, dXb, nb, 2, false, false, 0.0, WT, mTp, mTp, nbp, false);
         }
-        pd_solve(c, T->dL, mTp, WT, mTp, nbp, none);
+        pd_solve(c, T->dL, mTp, WT, mTp, nbp, none, nb);
         P = dalloc((size_t)std::max(mTp, mCp) * nbp, c->stream, false);
         // P = KTT * WT_c ; out = WT_c' P
         gemm(c, true, false, mTp, nbp, mTp, 1.0, T->dK, mTp, WT, mTp, 0.0, P, mTp, 0);
@@ -121,7 +121,7 @@ static void calib_cov_mu_delta(geordd_gp* T, geordd_gp* C, const double* dXb, in
                 ProfScope ps(c, PC_COV);
                 launch_cov(c->stream, to_dev(C->k), C->dX, mC, dXb, nb, 2, false, false, 0.0, WC, mCp, mCp, nbp, false);
             }
-            pd_solve(c, C->dL, mCp, WC, mCp, nbp, none);
+            pd_solve(c, C->dL, mCp, WC, mCp, nbp, none, nb);
             gemm(c, true, false, mCp, nbp, mCp, 1.0, C->dK, mCp, WC, mCp, 0.0, P, mCp, 0);
             gemm(c, false, false, nbp, nbp, mCp, 1.0, WC, mCp, P, mCp, 1.0, dOut, nbp, 0);
             // KCT = cov(kernel_C, X_C, X_T) (mCp x mTp); P = KCT * WT_c (mCp x nbp); E = WC_c' P ; out -= E + E'
@@ -342,10 +342,10 @@ static double null_cov_mu_tau(geordd_null* h, bool as_shipped) {
         calib_cov_mu_delta(h->T, h->C, h->dXb, nb, nbp, as_shipped, cmd);
         // cov_mu_tau = sum((Sigma \ cmd) * (Sigma \ 1))
         SolveEpilogue none;
-        pd_solve(c, h->dLSig, nbp, cmd, nbp, nbp, none);
+        pd_solve(c, h->dLSig, nbp, cmd, nbp, nbp, none, nb);
         one = dalloc((size_t)nbp * 64, c->stream, true);
         GD_CUDA(cudaMemcpyAsync(one, h->dOnes, (size_t)nbp * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-        pd_solve(c, h->dLSig, nbp, one, nbp, 64, none);
+        pd_solve(c, h->dLSig, nbp, one, nbp, 64, none, 1);
         // v = (Sigma\cmd) * s  then sum(v)  == sum over all entries of (Sigma\cmd)(i,j) * s(j)
         double* v = dalloc((size_t)nbp * 64, c->stream, true);
         gemm(c, true, false, nbp, 64, nbp, 1.0, cmd, nbp, one, nbp, 0.0, v, nbp, 1);
@@ -542,7 +542,7 @@ int geordd_weight_at_units(geordd_gp* gp, const double* Xb, int nb, const double
             launch_cov(c__->stream, to_dev(gp->k), gp->dX, gp->n, dXb, nb, gp->dim, false, false, 0.0, KXb, mp, mp, nbp, false);
         }
         SolveEpilogue none;
-        pd_solve(c__, gp->dL, mp, KXb, mp, nbp, none);          // K_XX \ K_Xb
+        pd_solve(c__, gp->dL, mp, KXb, mp, nbp, none, nb);      // K_XX \ K_Xb
         gemm(c__, true, false, mp, 64, nbp, 1.0 / sw, KXb, mp, w, nbp, 0.0, out, mp, 1);
         GD_CUDA(cudaMemcpyAsync(w_unit, out, (size_t)gp->n * sizeof(double), cudaMemcpyDeviceToHost, c__->stream));
         check_abort(c__);
@@ -641,7 +641,7 @@ static int null_set_sentinels(geordd_null* h, const double* Xb, int nb, double n
     try {
         GD_CUDA(cudaMemcpyAsync(slab, h->dOnes, (size_t)nbp * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         SolveEpilogue none;
-        pd_solve(c, h->dLSig, nbp, slab, nbp, 64, none);
+        pd_solve(c, h->dLSig, nbp, slab, nbp, 64, none, 1);
         launch_reduce(c->stream, 1, slab, nullptr, 0, nb, 0, c->d_scal + 2);
         check_abort(c);
         h->denom = read_scalar(c, c->d_scal + 2);

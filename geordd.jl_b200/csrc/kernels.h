@@ -100,8 +100,14 @@ struct SolveEpilogue {
     double add_const = 0.0, add_T = 0.0;
     double sub_0 = 0.0, sub_1 = 0.0, sub_T = 0.0, sub_C = 0.0;
 };
+// live_cols > 0: the caller states that only the first live_cols columns are non-zero / needed; with few of them
+// (<= NARROW_MAX_COLS) and no fused epilogue, FWD/BWD go to the latency-optimised narrow kernel (solve_narrow.cu,
+// 8-column slabs).  live_cols = 0: always the 64-column-slab kernel.
+constexpr int NARROW_MAX_COLS = 128;
 void launch_solve(cudaStream_t st, Sched& sched, SolveMode mode, const double* L, int npad, double* B, long ldb,
-                  int ncols, const SolveEpilogue& epi);
+                  int ncols, const SolveEpilogue& epi, int live_cols = 0);
+void launch_solve_narrow(cudaStream_t st, Sched& sched, SolveMode mode, const double* L, int npad, double* B, long ldb,
+                         int live_cols);
 
 // ---- gemm.cu --------------------------------------------------------------------------------------
 // C(M x N) = alpha * op(A) * op(B) + beta * C.  M multiple of 128, N multiple of 64, K multiple of 16.

@@ -221,7 +221,14 @@ static void launch_mode(cudaStream_t st, Sched& sched, const SolveParams& p) {
 
 
 void launch_solve(cudaStream_t st, Sched& sched, SolveMode mode, const double* L, int npad, double* B, long ldb,
-                  int ncols, const SolveEpilogue& epi) {
+                  int ncols, const SolveEpilogue& epi, int live_cols) {
+    // Opt-in only (live_cols > 0): the simulation path must use ONE kernel whatever the batch size, so that
+    // statistics stay bit-identical across batch and shard boundaries.
+    if (mode != SOLVE_TRMM && live_cols > 0 && live_cols <= NARROW_MAX_COLS && live_cols <= ncols && npad > TILE &&
+        !epi.dot0 && !epi.dot1) {
+        launch_solve_narrow(st, sched, mode, L, npad, B, ldb, live_cols);
+        return;
+    }
     SolveParams p;
     p.L = L; p.T = npad / TILE; p.B = B; p.ldb = ldb; p.nslabs = ncols / SLAB;
     p.flags = sched.flags; p.counter = sched.counter; p.abort_word = sched.abort_word; p.epi = epi;

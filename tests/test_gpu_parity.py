@@ -463,6 +463,25 @@ def test_many_rhs_triangular_ops_every_column(G, O, ctx, n, nrhs):
             assert int((err > 1e-10).sum()) == 0, (mode, rep, float(err.max()))
 
 
+@pytest.mark.parametrize("n,nrhs", [(129, 1), (300, 8), (700, 9), (1000, 100), (2000, 128), (2000, 1), (4000, 3)])
+def test_few_rhs_triangular_solves(G, O, ctx, n, nrhs):
+    """<= 128 right-hand sides take the latency-optimised 8-column-slab kernel (solve_narrow.cu): forward and
+    backward substitution against SciPy, repeated (persistent CTAs run several jobs, flags carry the epoch)."""
+    import scipy.linalg as sl
+    rng = np.random.default_rng(n + nrhs)
+    X = rng.random((2, n))
+    K = O.cov_sym(O.KernelSpec(O.MAT32, 0.3, 1.0, 400.0), X, 0.09)
+    L = np.asfortranarray(np.linalg.cholesky(K))
+    B = np.asfortranarray(rng.standard_normal((n, nrhs)))
+    refs = {0: sl.solve_triangular(L, B, lower=True), 1: sl.solve_triangular(L.T, B, lower=False)}
+    for mode in (0, 1):
+        for rep in range(3):
+            out = B.copy(order="F")
+            ctx.check(ctx.lib.geordd_dbg_trsm(ctx._h, mode, G.capi.dptr(L), n, G.capi.dptr(out), nrhs, None))
+            err = np.abs(out - refs[mode]).max(axis=0) / np.abs(refs[mode]).max()
+            assert int((err > 1e-10).sum()) == 0, (mode, rep, float(err.max()))
+
+
 @pytest.mark.parametrize("m", [1000, 2000])
 def test_null_identities_every_draw_at_scale(G, O, ctx, m):
     """20 000 device draws: y = L_N z  =>  mll_null + z'z/2 is the same constant for EVERY draw (1e-9), the chi2
