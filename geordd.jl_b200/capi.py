@@ -102,6 +102,7 @@ _SIGS = {
     "geordd_dbg_potrf": (C.c_int, [C.c_void_p, c_double_p, C.c_int, c_double_p, c_double_p]),
     "geordd_dbg_trsm": (C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_int, c_double_p, C.c_int, c_double_p]),
     "geordd_bench_potrf": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p]),
+    "geordd_bench_tileops": (C.c_int, [C.c_void_p, c_double_p]),
     "geordd_bench_dmma_peak": (C.c_int, [C.c_void_p, c_double_p]),
     "geordd_bench_dmma": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p]),
 }

@@ -173,16 +173,17 @@ struct SimRequest {
 
 static long pick_batch(geordd_null* h, long nsim) {
     geordd_ctx* c = h->ctx;
+    const long need = (nsim + 63) / 64 * 64;
+    long want = need;
+    if (c->max_batch > 0) want = std::min(want, std::max<long>(64, c->max_batch / 64 * 64));
+    if (want <= h->cap_cols) return want;   // buffers of an earlier call suffice: no driver query on the hot path
     const long npN = h->N->npad, mT = h->T->npad, mC = h->C->npad, nbp = h->nbp;
-    const long per_col = 8 * (npN + 2 * (npN + TILE) + mT + mC + 2 * nbp + (npN + mT + mC + 2 * nbp) / TILE + 8);
+    const long per_col = 8 * (npN * 5 / 4 + 2 * (npN + TILE) + mT + mC + 2 * nbp + (npN + mT + mC + 2 * nbp) / TILE + 8);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     long budget = (long)std::min<size_t>((size_t)24 << 30, free_b / 2);
-    long cap = budget / per_col;
-    if (c->max_batch > 0) cap = std::min(cap, c->max_batch);
-    cap = std::max<long>(64, cap / 64 * 64);
-    long need = (nsim + 63) / 64 * 64;
-    return std::min(cap, need);
+    long cap = std::max<long>(64, budget / per_col / 64 * 64);
+    return std::min(cap, want);
 }
 
 static void run_sims(geordd_null* h, SimRequest& rq) {

@@ -4,6 +4,7 @@
 //   geordd_bench_potrf     : the dataflow Cholesky on a synthetic SPD covariance built on device.
 #include "api_internal.h"
 #include "common.cuh"
+#include "tileops.cuh"
 #include <algorithm>
 #include <random>
 
@@ -26,6 +27,42 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink)
 
 }  // namespace geordd
 
+using namespace geordd;
+
+namespace geordd {
+// Cycle counts of the in-shared-memory tile operations that sit on the critical path of the dataflow Cholesky and
+// solves (one CTA, clock64 around each op, best of `reps`).
+__global__ void __launch_bounds__(NTHREADS, 1) tileops_cycles_kernel(const double* __restrict__ Aimg, const double* __restrict__ Limg,
+                                                                      int reps, long long* out) {
+    extern __shared__ __align__(16) double smem[];
+    double* Cs = smem;
+    double* Lp = Cs + TILE * SC;
+    double* invd = Lp + TILE * LRS;
+    __shared__ int sh_info;
+    long long best[4] = {1LL << 62, 1LL << 62, 1LL << 62, 1LL << 62};
+    __shared__ long long prof[8];
+    if (threadIdx.x < 8) prof[threadIdx.x] = 0;
+    for (int op = 0; op < 4; ++op) {
+        for (int r = 0; r < reps; ++r) {
+            for (int idx = threadIdx.x; idx < TILE * SC; idx += NTHREADS) Cs[idx] = Aimg[idx];
+            if (threadIdx.x == 0) sh_info = 0;
+            __syncthreads();
+            long long t0 = clock64();
+            if (op == 0) potrf_tile(Cs, invd, &sh_info, r == reps - 1 ? prof : nullptr);
+            if (op == 1) trsm_right_tile(Cs, Lp, invd, Limg, TLD, r == reps - 1 ? prof + 3 : nullptr);
+            if (op == 2) solve_fwd_tile(Cs, 64, Lp, invd, Limg, TLD);
+            if (op == 3) solve_bwd_tile(Cs, 64, Lp, invd, Limg, TLD);
+            __syncthreads();
+            long long t1 = clock64();
+            if (t1 - t0 < best[op]) best[op] = t1 - t0;
+        }
+    }
+    if (threadIdx.x == 0)
+        for (int op = 0; op < 4; ++op) out[op] = best[op];
+    __syncthreads();
+    if (threadIdx.x < 6) out[4 + threadIdx.x] = prof[threadIdx.x];
+}
+}  // namespace geordd
 using namespace geordd;
 
 extern "C" {
@@ -133,6 +170,43 @@ int geordd_bench_potrf(geordd_ctx* c, int n, int reps, double* ms_best, double* 
         return ctx_fail(c, e);
     }
     dfree(dX); dfree(dK); dfree(dL);
+    return 0;
+}
+
+int geordd_bench_tileops(geordd_ctx* c, double* cycles4) {
+    if (!c || !cycles4) return GEORDD_ERR_ARG;
+    double *dX = nullptr, *dK = nullptr, *dL = nullptr, *dA = nullptr;
+    long long* dOut = nullptr;
+    try {
+        ctx_use(c);
+        const int n = TILE;
+        std::mt19937_64 rng(1);
+        std::uniform_real_distribution<double> U(0.0, 1.0);
+        std::vector<double> X((size_t)2 * n);
+        for (auto& v : X) v = U(rng);
+        dX = dalloc((size_t)2 * n, c->stream, false);
+        dK = dalloc((size_t)n * n, c->stream, false);
+        dL = dalloc(factor_elems(n), c->stream, false);
+        dA = dalloc(factor_elems(n), c->stream, true);
+        dOut = reinterpret_cast<long long*>(dalloc(10, c->stream, true));
+        GD_CUDA(cudaMemcpyAsync(dX, X.data(), X.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        KernelSpecDev spec{2, 0.3, 1.0, 400.0};
+        launch_cov(c->stream, spec, dX, n, dX, n, 2, true, true, 0.09, dK, n, n, n, false);
+        launch_potrf(c->stream, c->sched, dK, dL, n, n);
+        GD_CUDA(cudaMemcpy2DAsync(dA, TLD * sizeof(double), dK, n * sizeof(double), n * sizeof(double), n, cudaMemcpyDeviceToDevice, c->stream));
+        const size_t smem = (size_t)(TILE * SC + TILE * LRS + TILE) * sizeof(double);
+        cudaFuncSetAttribute(tileops_cycles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tileops_cycles_kernel<<<1, NTHREADS, smem, c->stream>>>(dA, dL, 5, dOut);
+        long long h[10];
+        GD_CUDA(cudaMemcpyAsync(h, dOut, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        GD_CUDA(cudaStreamSynchronize(c->stream));
+        GD_CUDA(cudaGetLastError());
+        for (int i = 0; i < 10; ++i) cycles4[i] = (double)h[i];
+    } catch (const ApiError& e) {
+        dfree(dX); dfree(dK); dfree(dL); dfree(dA); dfree(dOut);
+        return ctx_fail(c, e);
+    }
+    dfree(dX); dfree(dK); dfree(dL); dfree(dA); dfree(dOut);
     return 0;
 }
 

@@ -14,6 +14,19 @@ constexpr int SC = TILE + PAD;   // 132: stride of tiles held in smem
 constexpr int NB = 32;           // inner block
 constexpr int LRS = NB + PAD;    // 36: stride of a row-panel held k-contiguous
 
+// 1/sqrt(x) for normal positive x: MUFU.RSQ64H seed (2^-22) + two Newton steps in FMA form, ~1 ulp, no slow path
+// (the CUDA rsqrt() carries a call for subnormals that costs registers and a stack frame in the tile kernels).
+__device__ __forceinline__ double rsqrt_pos(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double h = 0.5 * x;
+    double e = fma(-h * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-h * y, y, 0.5);
+    y = fma(y, e, y);
+    return y;
+}
+
 // C(m0.., n0..) -= A * B over K = NB, for 8x8 output tiles (mt, nt), mt in [0,mtiles), nt in
 // [0,ntiles); fa(m,k), fb(k,n) fetch operands (m, n relative to m0, n0).  If `lower`, only tiles
 // with m0+8mt >= n0+8nt are touched.  All 8 warps participate; caller syncs before/after.
@@ -69,38 +82,50 @@ __device__ __forceinline__ void tile_update(double* Cs, int m0, int mtiles, int 
 // ---- Cholesky of the 128x128 lower triangle held in Cs (in place).  sh_info: shared int, must be
 // 0 on entry; set to (local index + 1) of the first non-positive pivot.  The strict upper triangle
 // is left untouched (caller zeroes it on write-out).  invd[128] receives 1/L(c,c).
-__device__ inline void potrf_tile(double* Cs, double* invd, int* sh_info) {
+__device__ inline void potrf_tile(double* Cs, double* invd, int* sh_info, long long* prof = nullptr) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    long long tp = prof ? clock64() : 0;
+    auto lap = [&](int k) { if (prof) { long long t = clock64(); if (tid == 0) prof[k] += t - tp; tp = t; } };
     for (int o = 0; o < TILE; o += NB) {
-        // 1. 32x32 diagonal block, one warp, row per lane, registers + shuffles
+        // 1. 32x32 diagonal block, one warp, row per lane, registers + shuffles.  The dependent chain per pivot is
+        //    kept short: every lane tracks its OWN diagonal entry in `diag` (updated with lane-local FMAs) and
+        //    evaluates rsqrt on it each step, so a step costs fma -> rsqrt -> one shuffle -> mul; the column
+        //    shuffles for the off-diagonal updates stay off the chain.  L(c,c) = a * rsqrt(a), 1/L(c,c) = rsqrt(a).
         if (warp == 0) {
             double a[NB];
 #pragma unroll
             for (int c = 0; c < NB; ++c) a[c] = Cs[(o + c) * SC + o + lane];
-            bool failed = false;
+            double diag = Cs[(o + lane) * SC + o + lane];   // (not a[lane]: that would put a[] in local memory)
+            int first_bad = 0;   // 1-based column of the first bad pivot seen by this lane (its own column only)
 #pragma unroll
             for (int c = 0; c < NB; ++c) {
-                double dcc = __shfl_sync(0xffffffffu, a[c], c);
-                if (!(dcc > 0.0)) {   // also catches NaN
-                    if (!failed && lane == 0) atomicCAS(sh_info, 0, o + c + 1);
-                    failed = true;
-                    dcc = 1.0;
+                const bool pos = diag >= 2.2250738585072014e-308;  // positive normal (also catches NaN); lane c's counts
+                const double inv_own = rsqrt_pos(pos ? diag : 1.0);
+                const double inv = __shfl_sync(0xffffffffu, inv_own, c);
+                if (lane == c && !pos) first_bad = c + 1;          // branch-free in SASS: keeps the block one basic block
+                const double l = a[c] * inv;                       // column c of L below the diagonal (lanes > c)
+                if (lane == c) {
+                    a[c] = diag * inv;                             // L(c,c)
+                    invd[o + c] = inv;
+                } else {
+                    a[c] = l;
                 }
-                double d = sqrt(dcc);
-                double inv = 1.0 / d;
-                a[c] = (lane == c) ? d : a[c] * inv;
-                if (lane == c) invd[o + c] = inv;
+                diag = fma(-l, l, diag);                           // own pivot, no shuffle (only lanes > c still need it)
 #pragma unroll
-                for (int c2 = c + 1; c2 < NB; ++c2) {
-                    double l2 = __shfl_sync(0xffffffffu, a[c], c2);
-                    a[c2] -= a[c] * l2;
+                for (int c2 = c + 1; c2 < NB; ++c2) {              // branch-free: entries on/above the diagonal are
+                    double l2 = __shfl_sync(0xffffffffu, l, c2);   // never read again
+                    a[c2] = fma(-l, l2, a[c2]);
                 }
             }
 #pragma unroll
             for (int c = 0; c < NB; ++c)
                 if (lane >= c) Cs[(o + c) * SC + o + lane] = a[c];
+            // LAPACK info = first non-positive pivot: smallest failing column over the lanes
+            unsigned bad = __ballot_sync(0xffffffffu, first_bad != 0);
+            if (bad != 0 && lane == 0) atomicCAS(sh_info, 0, o + __ffs(bad));
         }
         __syncthreads();
+        lap(0);
         const int rest = TILE - o - NB;
         if (rest == 0) break;
         // 2. panel below: X = C * L^-T, one row per thread
@@ -119,6 +144,7 @@ __device__ inline void potrf_tile(double* Cs, double* invd, int* sh_info) {
             for (int c = 0; c < NB; ++c) Cs[(o + c) * SC + r] = x[c];
         }
         __syncthreads();
+        lap(1);
         // 3. trailing lower triangle -= P P^T
         {
             const double* P = Cs + o * SC + (o + NB);   // P(m,k) at P[k*SC + m]
@@ -127,6 +153,7 @@ __device__ inline void potrf_tile(double* Cs, double* invd, int* sh_info) {
                 [&](int k, int n) { return P[k * SC + n]; }, true);
         }
         __syncthreads();
+        lap(2);
     }
 }
 
@@ -153,11 +180,14 @@ __device__ __forceinline__ void load_row_panel(double* Lr, double* invd, const d
 }
 
 // ---- X * Lt^T = C  (C: 128 x 128 in Cs, overwritten by X).  Rows are independent. -------------
-__device__ inline void trsm_right_tile(double* Cs, double* Lp, double* invd, const double* Lt, long ld) {
+__device__ inline void trsm_right_tile(double* Cs, double* Lp, double* invd, const double* Lt, long ld, long long* prof = nullptr) {
     const int tid = threadIdx.x;
+    long long tp = prof ? clock64() : 0;
+    auto lap = [&](int k) { if (prof) { long long t = clock64(); if (tid == 0) prof[k] += t - tp; tp = t; } };
     for (int o = 0; o < TILE; o += NB) {
         load_col_panel(Lp, invd, Lt, ld, o);
         __syncthreads();
+        lap(0);
         if (tid < TILE) {
             const int r = tid;
             double x[NB];
@@ -173,6 +203,7 @@ __device__ inline void trsm_right_tile(double* Cs, double* Lp, double* invd, con
             for (int c = 0; c < NB; ++c) Cs[(o + c) * SC + r] = x[c];
         }
         __syncthreads();
+        lap(1);
         const int rest = TILE - o - NB;
         if (rest > 0) {
             // C(:, n') -= X(:, o..o+NB) * L(n', o..o+NB)^T  for n' >= o+NB
@@ -182,6 +213,7 @@ __device__ inline void trsm_right_tile(double* Cs, double* Lp, double* invd, con
                 [&](int k, int n) { return Lp[k * SC + o + NB + n]; }, false);
         }
         __syncthreads();
+        lap(2);
     }
 }
 

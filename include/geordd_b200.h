@@ -197,6 +197,9 @@ GEORDD_API int geordd_dbg_potrf(geordd_ctx* ctx, const double* A, int n, double*
 GEORDD_API int geordd_dbg_trsm(geordd_ctx* ctx, int mode, const double* L, int n, double* B, int nrhs, double* ms);
 /* Device-resident micro-benchmarks (synthetic SPD matrix built on device): times in ms. */
 GEORDD_API int geordd_bench_potrf(geordd_ctx* ctx, int n, int reps, double* ms_best, double* ms_mean);
+/* cycles10[0..3]: the four shared-memory tile operations (potrf, right solve, forward solve, backward solve; one CTA);
+   [4..6]: potrf phases (diagonal block, panel, trailing update); [7..9]: right-solve phases (panel load, substitution, update) */
+GEORDD_API int geordd_bench_tileops(geordd_ctx* ctx, double* cycles10);
 GEORDD_API int geordd_bench_dmma_peak(geordd_ctx* ctx, double* tflops);
 GEORDD_API int geordd_bench_dmma(geordd_ctx* ctx, int threads_per_cta, int ctas, int iters, double* tflops);
 
