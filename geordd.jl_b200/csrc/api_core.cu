@@ -173,11 +173,11 @@ int pick_splitk(geordd_ctx* c, int M, int N, int K) {
 }
 
 void gemm(geordd_ctx* c, bool a_mc, bool b_nc, int M, int N, int K, double alpha, const double* A, long lda,
-          const double* B, long ldb, double beta, double* C, long ldc, int splitk) {
+          const double* B, long ldb, double beta, double* C, long ldc, int splitk, bool b_xb) {
     if (splitk <= 0) splitk = pick_splitk(c, M, N, K);
     if (splitk > 1) ensure_ws(c, (size_t)splitk * ldc * N);
     ProfScope ps(c, PC_GEMM);
-    launch_gemm(c->stream, a_mc, b_nc, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, splitk, c->ws.p);
+    launch_gemm(c->stream, a_mc, b_nc, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, splitk, c->ws.p, b_xb);
 }
 
 int make_posdef(geordd_ctx* c, double* K, double* L, long ld, int n, int npad, int* rounds) {
@@ -216,6 +216,7 @@ int make_posdef(geordd_ctx* c, double* K, double* L, long ld, int n, int npad, i
 void pd_solve(geordd_ctx* c, const double* L, int npad, double* B, long ldb, int ncols, const SolveEpilogue& epi_bwd,
               int live_cols) {
     SolveEpilogue none;
+    none.xb = epi_bwd.xb;
     {
         ProfScope ps(c, PC_FWD);
         launch_solve(c->stream, c->sched, SOLVE_FWD, L, npad, B, ldb, ncols, none, live_cols);
@@ -638,7 +639,10 @@ int geordd_dbg_potrf(geordd_ctx* c, const double* A, int n, double* L, double* m
 
 int geordd_dbg_trsm(geordd_ctx* c, int mode, const double* L, int n, double* B, int nrhs, double* ms) {
     API_BEGIN(c)
-    if (!L || !B || n <= 0 || nrhs <= 0 || mode < 0 || mode > 2) throw ApiError(GEORDD_ERR_ARG, "dbg_trsm: bad arguments");
+    // mode 0 / 1 / 2: forward, backward, multiply; 3 / 4: forward / backward with the right-hand sides in ZB storage
+    if (!L || !B || n <= 0 || nrhs <= 0 || mode < 0 || mode > 4) throw ApiError(GEORDD_ERR_ARG, "dbg_trsm: bad arguments");
+    const bool xb = mode >= 3;
+    if (xb) mode -= 3;
     const int npad = round_up(n, TILE), ncols = round_up(nrhs, 64);
     double *dL = nullptr, *dB = nullptr, *dO = nullptr;
     try {
@@ -658,17 +662,24 @@ int geordd_dbg_trsm(geordd_ctx* c, int mode, const double* L, int n, double* B, 
             launch_zb_pack(c->stream, dB, npad, n, nrhs, c->tmp1.p, npad, ncols);
             dIn = c->tmp1.p;
         }
+        if (xb) {
+            epi.xb = true;
+            c->tmp1.ensure(zb_elems(npad, ncols), c->stream, false);
+            launch_zb_pack(c->stream, dB, npad, n, nrhs, c->tmp1.p, npad, ncols);
+            dIn = c->tmp1.p;
+        }
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         GD_CUDA(cudaStreamSynchronize(c->stream));
         cudaEventRecord(e0, c->stream);
-        launch_solve(c->stream, c->sched, (SolveMode)mode, dL, npad, dIn, npad, ncols, epi, nrhs);
+        launch_solve(c->stream, c->sched, (SolveMode)mode, dL, npad, dIn, npad, ncols, epi, xb ? 0 : nrhs);
         cudaEventRecord(e1, c->stream);
         check_abort(c);
         float t = 0.f;
         cudaEventElapsedTime(&t, e0, e1);
         cudaEventDestroy(e0); cudaEventDestroy(e1);
         if (ms) *ms = t;
+        if (xb) launch_zb_unpack(c->stream, dIn, npad, dB, npad, n, nrhs, 0);
         download2d(c, B, n, mode == 2 ? dO : dB, npad, n, nrhs);
         GD_CUDA(cudaStreamSynchronize(c->stream));
     } catch (...) {

@@ -163,7 +163,7 @@ int make_posdef(geordd_ctx* c, double* K, double* L, long ld, int n, int npad, i
 void pd_solve(geordd_ctx* c, const double* L, int npad, double* B, long ldb, int ncols, const SolveEpilogue& epi_bwd,
               int live_cols = 0);
 void gemm(geordd_ctx* c, bool a_mc, bool b_nc, int M, int N, int K, double alpha, const double* A, long lda,
-          const double* B, long ldb, double beta, double* C, long ldc, int splitk);
+          const double* B, long ldb, double beta, double* C, long ldc, int splitk, bool b_xb = false);
 int pick_splitk(geordd_ctx* c, int M, int N, int K);
 
 geordd_gp* gp_create(geordd_ctx* c, const geordd_kernel* k, const double* X, int dim, int n, const double* y,

@@ -178,7 +178,7 @@ static long pick_batch(geordd_null* h, long nsim) {
     if (c->max_batch > 0) want = std::min(want, std::max<long>(64, c->max_batch / 64 * 64));
     if (want <= h->cap_cols) return want;   // buffers of an earlier call suffice: no driver query on the hot path
     const long npN = h->N->npad, mT = h->T->npad, mC = h->C->npad, nbp = h->nbp;
-    const long per_col = 8 * (npN * 5 / 4 + 2 * (npN + TILE) + mT + mC + 2 * nbp + (npN + mT + mC + 2 * nbp) / TILE + 8);
+    const long per_col = 8 * ((3 * npN + mT + mC) * 5 / 4 + 2 * nbp + (npN + mT + mC + 2 * nbp) / TILE + 8);   // ZB storage: 20/16
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     long budget = (long)std::min<size_t>((size_t)24 << 30, free_b / 2);
@@ -193,7 +193,6 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
     const int n = N->n, npN = N->npad, mT = T->n, mTp = T->npad, mC = C->n, mCp = C->npad, nbp = h->nbp, nb = h->nb;
     if (rq.nsim <= 0) throw ApiError(GEORDD_ERR_ARG, "nsim must be positive");
     if (rq.want_cliff && nb <= 0) throw ApiError(GEORDD_ERR_ARG, "null handle was prepared without sentinels");
-    const long ldN = npN + TILE;
     const long cap = pick_batch(h, rq.nsim);
     const int TN = npN / TILE, TT = mTp / TILE, TC = mCp / TILE, TS = nbp > 0 ? nbp / TILE : 0;
     // (re)allocate simulation buffers for `cap` columns; padded regions must be zero, so a fresh
@@ -203,12 +202,13 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
         h->partN.release(); h->partT.release(); h->partC.release(); h->partChi.release(); h->partNum.release();
         h->cap_cols = 0;
     }
-    h->Z.ensure(zb_elems(npN, cap), st, true);   // ZB storage
-    h->AT.ensure((size_t)mTp * cap, st, true);
-    h->AC.ensure((size_t)mCp * cap, st, true);
+    // Z and every buffer the solves work on in place are in ZB storage (kernels.h)
+    h->Z.ensure(zb_elems(npN, cap), st, true);
+    h->AT.ensure(zb_elems(mTp, cap), st, true);
+    h->AC.ensure(zb_elems(mCp, cap), st, true);
     if (rq.want_mll) {
-        h->RN.ensure((size_t)ldN * cap, st, true);
-        h->AN.ensure((size_t)ldN * cap, st, true);
+        h->RN.ensure(zb_elems(npN, cap), st, true);
+        h->AN.ensure(zb_elems(npN, cap), st, true);
         h->partN.ensure((size_t)TN * cap, st, true);
         h->partT.ensure((size_t)TT * cap, st, true);
         h->partC.ensure((size_t)TC * cap, st, true);
@@ -246,10 +246,11 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
         // 2. prior_rand: y = m_N + L_N z (+ tau on treated), scattered into residual buffers
         {
             SolveEpilogue e;
+            e.xb = true;
             e.nrows = n; e.split = mT; e.add_const = mN; e.add_T = rq.tau;
             if (rq.want_mll) {
-                e.out0 = h->RN.p; e.ld0 = ldN; e.sub_0 = mN;
-                e.out1 = h->AN.p; e.ld1 = ldN; e.sub_1 = mN;
+                e.out0 = h->RN.p; e.ld0 = npN; e.sub_0 = mN;
+                e.out1 = h->AN.p; e.ld1 = npN; e.sub_1 = mN;
             }
             e.outT = h->AT.p; e.ldT = mTp; e.sub_T = mTc;
             e.outC = h->AC.p; e.ldC = mCp; e.sub_C = mCc;
@@ -259,16 +260,18 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
         // 3. update_alpha! on T, C (and N), with the (y - m)' alpha quadratic forms fused into the solves
         {
             SolveEpilogue eT, eC;
+            eT.xb = eC.xb = true;
             if (rq.want_mll) {
-                eT.wmat = h->RN.p; eT.ldw = ldN; eT.wshift = mN - mTc; eT.wrows = mT; eT.dot0 = h->partT.p;
-                eC.wmat = h->RN.p + mT; eC.ldw = ldN; eC.wshift = mN - mCc; eC.wrows = mC; eC.dot0 = h->partC.p;
+                eT.wmat = h->RN.p; eT.ldw = npN; eT.wshift = mN - mTc; eT.wrows = mT; eT.dot0 = h->partT.p;
+                eC.wmat = h->RN.p; eC.wrow0 = mT; eC.ldw = npN; eC.wshift = mN - mCc; eC.wrows = mC; eC.dot0 = h->partC.p;
             }
             pd_solve(c, T->dL, mTp, h->AT.p, mTp, ncols, eT);
             pd_solve(c, C->dL, mCp, h->AC.p, mCp, ncols, eC);
             if (rq.want_mll) {
                 SolveEpilogue eN;
-                eN.wmat = h->RN.p; eN.ldw = ldN; eN.dot0 = h->partN.p;
-                pd_solve(c, N->dL, npN, h->AN.p, ldN, ncols, eN);
+                eN.xb = true;
+                eN.wmat = h->RN.p; eN.ldw = npN; eN.dot0 = h->partN.p;
+                pd_solve(c, N->dL, npN, h->AN.p, npN, ncols, eN);
             }
         }
         // Partials of dead columns in the last slab are garbage-free (zero inputs) and ignored.
@@ -285,8 +288,8 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
         }
         // 4. mu_b = (m_T - m_C) + cK_T alpha_T - cK_C alpha_C ; Sigma \ mu ; chi2 and inverse-variance
         if (rq.want_cliff) {
-            gemm(c, true, false, nbp, ncols, mTp, 1.0, h->dKbT, nbp, h->AT.p, mTp, 0.0, h->M.p, nbp, 1);
-            gemm(c, true, false, nbp, ncols, mCp, -1.0, h->dKbC, nbp, h->AC.p, mCp, 1.0, h->M.p, nbp, 1);
+            gemm(c, true, false, nbp, ncols, mTp, 1.0, h->dKbT, nbp, h->AT.p, mTp, 0.0, h->M.p, nbp, 1, /*b_xb=*/true);
+            gemm(c, true, false, nbp, ncols, mCp, -1.0, h->dKbC, nbp, h->AC.p, mCp, 1.0, h->M.p, nbp, 1, /*b_xb=*/true);
             launch_add_const(st, h->M.p, nbp, nb, ncols, mTc - mCc);
             GD_CUDA(cudaMemcpyAsync(h->W.p, h->M.p, (size_t)nbp * ncols * sizeof(double), cudaMemcpyDeviceToDevice, st));
             SolveEpilogue e;
@@ -303,14 +306,17 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
         }
         if (done + cap >= rq.nsim && rq.want_mll && (rq.last_y || rq.last_alpha)) {
             // the reference leaves gpNull.y / .alpha at the final draw (src/hypotest_mll.jl:6,10)
-            const size_t col = (size_t)(live - 1) * ldN;
+            c->tmp2.ensure((size_t)2 * n, st, false);
             if (rq.last_y) {
-                GD_CUDA(cudaMemcpyAsync(rq.last_y, h->RN.p + col, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+                launch_zb_unpack(st, h->RN.p, npN, c->tmp2.p, n, n, 1, live - 1);
+                GD_CUDA(cudaMemcpyAsync(rq.last_y, c->tmp2.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
                 GD_CUDA(cudaStreamSynchronize(st));
                 for (int i = 0; i < n; ++i) rq.last_y[i] += mN;
             }
-            if (rq.last_alpha)
-                GD_CUDA(cudaMemcpyAsync(rq.last_alpha, h->AN.p + col, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+            if (rq.last_alpha) {
+                launch_zb_unpack(st, h->AN.p, npN, c->tmp2.p + n, n, n, 1, live - 1);
+                GD_CUDA(cudaMemcpyAsync(rq.last_alpha, c->tmp2.p + n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+            }
         }
     }
     const size_t bytes = (size_t)rq.nsim * sizeof(double);

@@ -8,11 +8,12 @@
 
 namespace geordd {
 
-template <bool A_MC, bool B_NC>
+template <bool A_MC, bool B_NC, bool B_XB = false>
 __global__ void __launch_bounds__(NTHREADS, 2)
 gemm_kernel(int K, double alpha, const double* __restrict__ A, long lda, const double* __restrict__ B, long ldb,
             double beta, double* __restrict__ C, long ldc, int splitk, double* __restrict__ ws, long ws_stride) {
-    using ML = Mainloop<64, A_MC, B_NC, 3>;
+    using ML = Mainloop<64, A_MC, B_NC, 3, ROWS_TMA, B_XB ? BLK_TMA : ROWS_TMA>;
+    static_assert(!B_XB || !B_NC, "ZB storage is the k-contiguous B stage");
     extern __shared__ __align__(16) double smem[];
     __shared__ int sh_abort;   // never set: plain GEMM has no dataflow waits, only the ring watchdog
     if (threadIdx.x == 0) sh_abort = 0;
@@ -30,9 +31,10 @@ gemm_kernel(int K, double alpha, const double* __restrict__ A, long lda, const d
     src.lda = lda;
     src.ldb = ldb;
     src.a = A_MC ? A + k0 * lda + (long)mt * TILE : A + (long)mt * TILE * lda + k0;
-    src.b = B_NC ? B + k0 * ldb + (long)nt * 64 : B + (long)nt * 64 * ldb + k0;
+    src.b = B_XB ? B + ((long)nt * kchunks_total + c0) * ZB_ELEMS
+                 : (B_NC ? B + k0 * ldb + (long)nt * 64 : B + (long)nt * 64 * ldb + k0);
     src.a_step = A_MC ? (long)BK * lda : BK;
-    src.b_step = B_NC ? (long)BK * ldb : BK;
+    src.b_step = B_XB ? (long)ZB_ELEMS : (B_NC ? (long)BK * ldb : BK);
     typename ML::Acc acc;
     ML::zero(acc);
     ML::run(smem, ring, nch, src, acc);
@@ -67,19 +69,19 @@ __global__ void splitk_reduce_kernel(int M, int N, double alpha, double beta, do
     *p = v;
 }
 
-template <bool A_MC, bool B_NC>
+template <bool A_MC, bool B_NC, bool B_XB = false>
 static void launch_t(cudaStream_t st, int M, int N, int K, double alpha, const double* A, long lda, const double* B,
                      long ldb, double beta, double* C, long ldc, int splitk, double* ws) {
-    using ML = Mainloop<64, A_MC, B_NC, 3>;
+    using ML = Mainloop<64, A_MC, B_NC, 3, ROWS_TMA, B_XB ? BLK_TMA : ROWS_TMA>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(gemm_kernel<A_MC, B_NC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(gemm_kernel<A_MC, B_NC, B_XB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(ML::SMEM_BYTES + ML::BAR_WORDS * 8));
         attr_set = true;
     }
     dim3 grid(M / TILE, N / 64, splitk);
     long ws_stride = (long)ldc * N;
-    gemm_kernel<A_MC, B_NC><<<grid, NTHREADS, ML::SMEM_BYTES + ML::BAR_WORDS * 8, st>>>(K, alpha, A, lda, B, ldb, beta, C, ldc, splitk, ws,
+    gemm_kernel<A_MC, B_NC, B_XB><<<grid, NTHREADS, ML::SMEM_BYTES + ML::BAR_WORDS * 8, st>>>(K, alpha, A, lda, B, ldb, beta, C, ldc, splitk, ws,
                                                                    ws_stride); ++g_kernel_launches;
     if (splitk > 1) {
         long tot = (long)M * N;
@@ -89,9 +91,10 @@ static void launch_t(cudaStream_t st, int M, int N, int K, double alpha, const d
 }
 
 void launch_gemm(cudaStream_t st, bool a_mc, bool b_nc, int M, int N, int K, double alpha, const double* A, long lda,
-                 const double* B, long ldb, double beta, double* C, long ldc, int splitk, double* ws) {
+                 const double* B, long ldb, double beta, double* C, long ldc, int splitk, double* ws, bool b_xb) {
     if (splitk < 1) splitk = 1;
-    if (a_mc && b_nc) launch_t<true, true>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, splitk, ws);
+    if (b_xb) launch_t<true, false, true>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, splitk, ws);
+    else if (a_mc && b_nc) launch_t<true, true>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, splitk, ws);
     else if (a_mc && !b_nc) launch_t<true, false>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, splitk, ws);
     else if (!a_mc && b_nc) launch_t<false, true>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, splitk, ws);
     else launch_t<false, false>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, splitk, ws);

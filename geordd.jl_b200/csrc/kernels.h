@@ -24,9 +24,17 @@ inline long tile_off(int I, int J, int T) { return ((long)J * T + I) * TSZ; }
 // [n = 0..63][k = 0..15 (+4 pad)] is a contiguous 64 x 20 image -- exactly the B stage of the mainloop -- so the
 // triangular multiply moves a chunk of Z with ONE bulk copy.  Element (row r, draw col):
 //   ((col/64) * (npad/16) + r/16) * ZB_ELEMS + (col%64) * ZB_LD + r%16
+// The simulation buffers that the solves work on in place (y - m, alpha of the three GPs) use the same storage
+// ("XB" in the solve kernels): every K-chunk of a right-hand-side slab is then ONE bulk copy as well.
 constexpr int ZB_LD = BK + 4;
 constexpr int ZB_ELEMS = 64 * ZB_LD;
 inline size_t zb_elems(int npad, long ncols) { return (size_t)(ncols / 64) * (npad / BK) * ZB_ELEMS; }
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline long zb_off(long r, long col, int npad) {
+    return ((col >> 6) * (npad / BK) + (r >> 4)) * ZB_ELEMS + (col & 63) * ZB_LD + (r & 15);
+}
 
 struct KernelSpecDev {
     int kind;            // 0 SE, 1 Mat12, 2 Mat32, 3 Mat52
@@ -81,6 +89,10 @@ enum SolveMode { SOLVE_FWD = 0, SOLVE_BWD = 1, SOLVE_TRMM = 2 };
 //   FWD:  B <- L^-1 B      BWD: B <- L^-T B      TRMM: out <- L * Z, Z given in ZB storage (ldb ignored)
 // BWD requires launch_mirror_factor to have been applied to L.
 struct SolveEpilogue {
+    // xb: the right-hand sides B (FWD/BWD, in place), wmat, and the TRMM outputs out0/out1/outT/outC are in ZB
+    // storage; their ld fields then hold the padded ROW COUNT of the buffer instead of a leading dimension.
+    bool xb = false;
+    int wrow0 = 0;   // xb only: wmat row r of this solve is row r + wrow0 of the wmat buffer
     // FWD/BWD: fused statistic partials, written per row block (deterministic; reduced later):
     //   dot0[rb*ncols + c] = sum_{r in block rb} (wmat(r,c) + (r < wrows ? wshift : 0)) * X(r,c)
     //   dot1[rb*ncols + c] = sum_{r in block rb} wvec[r] * X(r,c)
@@ -113,14 +125,16 @@ void launch_solve_narrow(cudaStream_t st, Sched& sched, SolveMode mode, const do
 // C(M x N) = alpha * op(A) * op(B) + beta * C.  M multiple of 128, N multiple of 64, K multiple of 16.
 //   a_mc: A(m,k) at A[k*lda+m] else A[m*lda+k];  b_nc: B(k,n) at B[k*ldb+n] else B[n*ldb+k]
 // splitk > 1: partial tiles go to ws (splitk * ldc * N doubles) and are summed in fixed order.
+// b_xb (requires a_mc, !b_nc): B is a K x N matrix in ZB storage (K = its padded row count, ldb ignored).
 void launch_gemm(cudaStream_t st, bool a_mc, bool b_nc, int M, int N, int K, double alpha, const double* A, long lda,
-                 const double* B, long ldb, double beta, double* C, long ldc, int splitk, double* ws);
+                 const double* B, long ldb, double beta, double* C, long ldc, int splitk, double* ws, bool b_xb = false);
 
 // ---- stats.cu -------------------------------------------------------------------------------------
 // blocked = false: Z is npad x ndraws column-major (ldz);  blocked = true: ZB storage (ndraws multiple of 64).
 void launch_philox_normals(cudaStream_t st, unsigned long long seed, unsigned long long draw0, int ndraws, int n,
                            double* Z, long ldz, int npad, bool blocked);
-// dense (n x ncols_live, ldz) -> ZB storage for ncols (multiple of 64) draws, zero padded
+// dense (n x ncols_live, ldz) -> ZB storage for ncols (multiple of 64) draws, zero padded; and back
 void launch_zb_pack(cudaStream_t st, const double* dense, long ldz, int n, long ncols_live, double* Zb, int npad, long ncols);
+void launch_zb_unpack(cudaStream_t st, const double* Zb, int npad, double* dense, long ldz, int n, long ncols_live, long col0);
 
 }  // namespace geordd

@@ -27,15 +27,18 @@ constexpr int CHUNKS_PER_TILE_S = TILE / BK;
 
 // All three modes read the factor with the row index contiguous: forward / TRMM from the lower tiles of L,
 // backward from the mirrored upper tiles (L' stored above the diagonal by launch_mirror_factor).
-// Triangular multiply (no flags): factor chunk and Z chunk (ZB storage) are ONE TMA block copy each, issued by
-// thread 0.  Solves (flagged dataflow): both operands through the generic proxy (see the stage-release note in mainloop.cuh).
-template <int MODE>
+// Operand feed: the triangular multiply and the XB solves (right-hand sides in ZB storage -- the simulation path)
+// move factor chunk and right-hand-side chunk with ONE TMA block copy each, issued by thread 0; only warp 0 ever
+// waits on a dataflow flag.  The column-major solves (fits, cliff face, misc callers) use the generic-proxy ring.
+// XB: the right-hand sides are in ZB storage, so the flagged solves run the same one-thread TMA feed as the
+// triangular multiply (exact since the stage release waits for the fragment loads, mainloop.cuh).
+template <int MODE, bool XB>
 struct SolveCfg {
-    using ML = Mainloop<SLAB, /*A_MC=*/true, /*B_NC=*/false, 4, MODE == SOLVE_TRMM ? BLK_TMA : BLK_GEN,
-                        MODE == SOLVE_TRMM ? BLK_TMA : ROWS_GEN>;
+    static constexpr bool BULK = XB || MODE == SOLVE_TRMM;
+    using ML = Mainloop<SLAB, /*A_MC=*/true, /*B_NC=*/false, 4, BULK ? BLK_TMA : BLK_GEN, BULK ? BLK_TMA : ROWS_GEN>;
 };
 
-template <int MODE>
+template <int MODE, bool XB>
 struct SolveSrc {
     const double* L;
     const double* X;   // slab base: column 0 of this slab, row 0
@@ -56,12 +59,15 @@ struct SolveSrc {
     __device__ __forceinline__ const double* b_ptr(int c) const {
         if (MODE == SOLVE_TRMM) return X + (long)c * ZB_ELEMS;   // ZB storage: chunk c of this slab is one block
         int kt = ktile(c), kk = (c % CHUNKS_PER_TILE_S) * BK;
+        if (XB) return X + ((long)kt * CHUNKS_PER_TILE_S + c % CHUNKS_PER_TILE_S) * ZB_ELEMS;
         return X + (long)kt * TILE + kk;   // B(k,n) = X(kt*128+kk+k, n): k contiguous
     }
     __device__ __forceinline__ bool ready(int c) const {   // warp level
         if (MODE == SOLVE_TRMM) return true;
         if (c % CHUNKS_PER_TILE_S != 0) return true;
-        return warp_wait_flags(flags + (long)ktile(c) * nslabs + s, nullptr, epoch, abort_word);
+        bool ok = warp_wait_flags(flags + (long)ktile(c) * nslabs + s, nullptr, epoch, abort_word);
+        if (XB) fence_proxy_async();   // the acquire (generic proxy) before the bulk copy of the published block
+        return ok;
     }
 };
 
@@ -80,14 +86,15 @@ struct SolveParams {
 
 constexpr int SOLVE_CS_ELEMS = SLAB * SC;                       // 8448
 constexpr int SOLVE_PANEL_ELEMS = TILE * LRS;                   // 4608 >= NB*SC = 4224
-constexpr int SOLVE_RING_ELEMS = SolveCfg<0>::ML::RING_ELEMS;   // identical for the three modes
+constexpr int SOLVE_RING_ELEMS = SolveCfg<0, false>::ML::RING_ELEMS;   // identical for all modes
 constexpr int SOLVE_WORK_ELEMS = SOLVE_CS_ELEMS + SOLVE_PANEL_ELEMS + NB;
-constexpr int SOLVE_SMEM_ELEMS = (SOLVE_RING_ELEMS > SOLVE_WORK_ELEMS ? SOLVE_RING_ELEMS : SOLVE_WORK_ELEMS) + SolveCfg<0>::ML::BAR_WORDS;
+constexpr int SOLVE_SMEM_ELEMS = (SOLVE_RING_ELEMS > SOLVE_WORK_ELEMS ? SOLVE_RING_ELEMS : SOLVE_WORK_ELEMS) + SolveCfg<0, false>::ML::BAR_WORDS;
 constexpr size_t SOLVE_SMEM = (size_t)SOLVE_SMEM_ELEMS * sizeof(double);
 
-template <int MODE>
+template <int MODE, bool XB>
 __global__ void __launch_bounds__(NTHREADS, 2) solve_dataflow_kernel(SolveParams p) {
-    using ML = typename SolveCfg<MODE>::ML;
+    using ML = typename SolveCfg<MODE, XB>::ML;
+    static_assert(SolveCfg<MODE, XB>::ML::RING_ELEMS == SOLVE_RING_ELEMS, "one shared-memory budget for all variants");
     static_assert(ML::SMEM_BYTES + ML::BAR_WORDS * 8 <= SOLVE_SMEM, "stage ring must fit");
     extern __shared__ __align__(16) double smem[];
     double* Cs = smem;
@@ -111,8 +118,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) solve_dataflow_kernel(SolveParams
         if (job >= njobs) break;
         const int lvl = job / p.nslabs, s = job % p.nslabs;
         const int rb = (MODE == SOLVE_FWD) ? lvl : (p.T - 1 - lvl);
-        double* Bslab = (MODE == SOLVE_TRMM) ? p.B + (long)s * (p.T * CHUNKS_PER_TILE_S) * ZB_ELEMS   // ZB: slab s
-                                             : p.B + (long)s * SLAB * p.ldb;
+        double* Bslab = (MODE == SOLVE_TRMM || XB) ? p.B + (long)s * (p.T * CHUNKS_PER_TILE_S) * ZB_ELEMS   // ZB: slab s
+                                                   : p.B + (long)s * SLAB * p.ldb;
+        // element (row m of block rb, column n of the slab) of an XB right-hand-side slab
+        auto xb_at = [&](int m, int n) { return Bslab + ((long)rb * CHUNKS_PER_TILE_S + (m >> 4)) * ZB_ELEMS + n * ZB_LD + (m & 15); };
 
         typename ML::Acc acc;
         if (MODE == SOLVE_TRMM) {
@@ -125,9 +134,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) solve_dataflow_kernel(SolveParams
                 for (int b = 0; b < ML::NJ; ++b)
 #pragma unroll
                     for (int e = 0; e < 2; ++e)
-                        acc.v[a][b][e] = -ldcg(Brb + (long)ML::acc_col(b, e) * p.ldb + ML::acc_row(a));
+                        acc.v[a][b][e] = XB ? -ldcg(xb_at(ML::acc_row(a), ML::acc_col(b, e)))
+                                            : -ldcg(Brb + (long)ML::acc_col(b, e) * p.ldb + ML::acc_row(a));
         }
-        SolveSrc<MODE> src{p.L, Bslab, 0, p.ldb, rb, p.T, s, p.nslabs, p.flags, p.epoch, p.abort_word};
+        SolveSrc<MODE, XB> src{p.L, Bslab, 0, p.ldb, rb, p.T, s, p.nslabs, p.flags, p.epoch, p.abort_word};
         int nchunks = (MODE == SOLVE_FWD) ? rb * CHUNKS_PER_TILE_S
                     : (MODE == SOLVE_BWD) ? (p.T - 1 - rb) * CHUNKS_PER_TILE_S
                                           : (rb + 1) * CHUNKS_PER_TILE_S;
@@ -155,13 +165,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) solve_dataflow_kernel(SolveParams
                 double v = Cs[n * SC + m];
                 bool live = r < e.nrows;
                 if (live) v += e.add_const + (r < e.split ? e.add_T : 0.0);
-                if (e.out0) e.out0[col * e.ld0 + r] = live ? v - e.sub_0 : 0.0;
-                if (e.out1) e.out1[col * e.ld1 + r] = live ? v - e.sub_1 : 0.0;
+                if (e.out0) e.out0[e.xb ? zb_off(r, col, (int)e.ld0) : col * e.ld0 + r] = live ? v - e.sub_0 : 0.0;
+                if (e.out1) e.out1[e.xb ? zb_off(r, col, (int)e.ld1) : col * e.ld1 + r] = live ? v - e.sub_1 : 0.0;
                 if (live) {
                     if (r < e.split) {
-                        if (e.outT) e.outT[col * e.ldT + r] = v - e.sub_T;
+                        if (e.outT) e.outT[e.xb ? zb_off(r, col, (int)e.ldT) : col * e.ldT + r] = v - e.sub_T;
                     } else {
-                        if (e.outC) e.outC[col * e.ldC + (r - e.split)] = v - e.sub_C;
+                        if (e.outC) e.outC[e.xb ? zb_off(r - e.split, col, (int)e.ldC) : col * e.ldC + (r - e.split)] = v - e.sub_C;
                     }
                 }
             }
@@ -169,7 +179,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) solve_dataflow_kernel(SolveParams
             double* Brb = Bslab + (long)rb * TILE;
             for (int idx = tid; idx < SLAB * TILE; idx += NTHREADS) {
                 int n = idx / TILE, m = idx % TILE;
-                Brb[(long)n * p.ldb + m] = Cs[n * SC + m];
+                if (XB) *xb_at(m, n) = Cs[n * SC + m];
+                else Brb[(long)n * p.ldb + m] = Cs[n * SC + m];
             }
             // fused statistic partials: 4 threads per column, 32 rows each, quad shuffle-reduce
             if (e.dot0 || e.dot1) {
@@ -182,7 +193,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) solve_dataflow_kernel(SolveParams
                     int r = rb * TILE + m;
                     double x = Cs[n * SC + m];
                     if (e.dot0) {
-                        double w = ldcg(e.wmat + col * e.ldw + r);
+                        double w = ldcg(XB ? e.wmat + zb_off(r + e.wrow0, col, (int)e.ldw) : e.wmat + col * e.ldw + r);
                         if (r < e.wrows) w += e.wshift;
                         s0 += w * x;
                     }
@@ -205,18 +216,18 @@ __global__ void __launch_bounds__(NTHREADS, 2) solve_dataflow_kernel(SolveParams
     }
 }
 
-template <int MODE>
+template <int MODE, bool XB>
 static void launch_mode(cudaStream_t st, Sched& sched, const SolveParams& p) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(solve_dataflow_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM);
+        cudaFuncSetAttribute(solve_dataflow_kernel<MODE, XB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM);
         attr_set = true;
     }
     int njobs = p.T * p.nslabs;
     int grid = 2 * sched.num_sms;
     if (grid > njobs) grid = njobs;
 
-    solve_dataflow_kernel<MODE><<<grid, NTHREADS, SOLVE_SMEM, st>>>(p); ++g_kernel_launches;
+    solve_dataflow_kernel<MODE, XB><<<grid, NTHREADS, SOLVE_SMEM, st>>>(p); ++g_kernel_launches;
 }
 
 
@@ -225,7 +236,7 @@ void launch_solve(cudaStream_t st, Sched& sched, SolveMode mode, const double* L
     // Opt-in only (live_cols > 0): the simulation path must use ONE kernel whatever the batch size, so that
     // statistics stay bit-identical across batch and shard boundaries.
     if (mode != SOLVE_TRMM && live_cols > 0 && live_cols <= NARROW_MAX_COLS && live_cols <= ncols && npad > TILE &&
-        !epi.dot0 && !epi.dot1) {
+        !epi.dot0 && !epi.dot1 && !epi.xb) {
         launch_solve_narrow(st, sched, mode, L, npad, B, ldb, live_cols);
         return;
     }
@@ -235,9 +246,14 @@ void launch_solve(cudaStream_t st, Sched& sched, SolveMode mode, const double* L
     cudaMemsetAsync(sched.counter, 0, sizeof(unsigned), st);
     sched.epoch++;
     p.epoch = sched.epoch;
-    if (mode == SOLVE_FWD) launch_mode<SOLVE_FWD>(st, sched, p);
-    else if (mode == SOLVE_BWD) launch_mode<SOLVE_BWD>(st, sched, p);
-    else launch_mode<SOLVE_TRMM>(st, sched, p);
+    if (mode == SOLVE_TRMM) launch_mode<SOLVE_TRMM, false>(st, sched, p);
+    else if (epi.xb) {
+        if (mode == SOLVE_FWD) launch_mode<SOLVE_FWD, true>(st, sched, p);
+        else launch_mode<SOLVE_BWD, true>(st, sched, p);
+    } else {
+        if (mode == SOLVE_FWD) launch_mode<SOLVE_FWD, false>(st, sched, p);
+        else launch_mode<SOLVE_BWD, false>(st, sched, p);
+    }
 }
 
 }  // namespace geordd

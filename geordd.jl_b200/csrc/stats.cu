@@ -71,6 +71,19 @@ __global__ void zb_pack_kernel(const double* __restrict__ dense, long ldz, int n
     double v = (r < n && col < live) ? dense[col * ldz + r] : 0.0;
     Zb[((col / 64) * (npad / BK) + r / BK) * ZB_ELEMS + (col % 64) * ZB_LD + r % BK] = v;
 }
+__global__ void zb_unpack_kernel(const double* __restrict__ Zb, int npad, double* __restrict__ dense, long ldz, int n, long live,
+                                 long col0) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)n * live) return;
+    int r = (int)(idx % n);
+    long c = idx / n;
+    dense[c * ldz + r] = Zb[zb_off(r, col0 + c, npad)];
+}
+void launch_zb_unpack(cudaStream_t st, const double* Zb, int npad, double* dense, long ldz, int n, long ncols_live, long col0) {
+    long tot = (long)n * ncols_live;
+    if (tot <= 0) return;
+    zb_unpack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Zb, npad, dense, ldz, n, ncols_live, col0); ++g_kernel_launches;
+}
 void launch_zb_pack(cudaStream_t st, const double* dense, long ldz, int n, long ncols_live, double* Zb, int npad, long ncols) {
     long tot = (long)npad * ncols;
     zb_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(dense, ldz, n, ncols_live, Zb, npad, ncols); ++g_kernel_launches;

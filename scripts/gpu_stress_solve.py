@@ -12,7 +12,7 @@ for n in (1000, 2000):
     L = np.asfortranarray(np.linalg.cholesky(K))
     for nr in (5632, 20000, 20000):
         B = np.asfortranarray(rng.standard_normal((n, nr)))
-        for mode, ref in ((2, L @ B), (0, sl.solve_triangular(L, B, lower=True)), (1, sl.solve_triangular(L.T, B, lower=False))):
+        for mode, ref in ((2, L @ B), (0, sl.solve_triangular(L, B, lower=True)), (1, sl.solve_triangular(L.T, B, lower=False)), (3, sl.solve_triangular(L, B, lower=True)), (4, sl.solve_triangular(L.T, B, lower=False))):
             out = B.copy(order="F"); rc = lib.geordd_dbg_trsm(ctx._h, mode, capi.dptr(L), n, capi.dptr(out), nr, None); assert rc == 0
             err = np.abs(out - ref) / np.max(np.abs(ref)); bad = np.nonzero(err.max(axis=0) > 1e-9)[0]
             print(f"n={n} nrhs={nr} mode={mode}: max err {err.max():.2e}, bad columns {len(bad)}")

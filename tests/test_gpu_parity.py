@@ -455,7 +455,8 @@ def test_many_rhs_triangular_ops_every_column(G, O, ctx, n, nrhs):
     L = np.asfortranarray(np.linalg.cholesky(K))
     B = np.asfortranarray(rng.standard_normal((n, nrhs)))
     refs = {2: L @ B, 0: sl.solve_triangular(L, B, lower=True), 1: sl.solve_triangular(L.T, B, lower=False)}
-    for mode in (2, 0, 1):
+    refs[3], refs[4] = refs[0], refs[1]          # same solves with the right-hand sides in slab-blocked (ZB) storage
+    for mode in (2, 0, 1, 3, 4):
         for rep in range(2):
             out = B.copy(order="F")
             ctx.check(ctx.lib.geordd_dbg_trsm(ctx._h, mode, G.capi.dptr(L), n, G.capi.dptr(out), nrhs, None))
