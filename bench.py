@@ -226,7 +226,7 @@ def main():
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     launches = lib.geordd_launch_count() - launches0
-    prof = {nm: ctx.profile_get(nm) for nm in ("solve_fwd", "solve_bwd", "trmm", "rng", "finish", "gemm", "potrf", "cov")}
+    prof = {nm: ctx.profile_get(nm) for nm in ("solve_seq", "solve_fwd", "solve_bwd", "trmm", "rng", "finish", "gemm", "potrf", "cov")}
     ctx.profile(False)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -306,8 +306,8 @@ def main():
         ctx.check(lib.geordd_null_chi2(gN._h, S, 1, 10 ** 9, None, 1e300, None, C.byref(cnt)))
         ctx.sync(); chi_rate = S / (time.time() - t0)
 
-        solve_ms = prof["solve_fwd"][0] + prof["solve_bwd"][0] + prof["trmm"][0]
-        solve_n = prof["solve_fwd"][1] + prof["solve_bwd"][1] + prof["trmm"][1]
+        solve_ms = prof["solve_seq"][0] + prof["solve_fwd"][0] + prof["solve_bwd"][0] + prof["trmm"][0]
+        solve_n = prof["solve_seq"][1] + prof["solve_fwd"][1] + prof["solve_bwd"][1] + prof["trmm"][1]
         algo_flops_per_launch = flops_per_mll_draw(M_SIDE) * S * args.steps / max(solve_n, 1)
         achieved = flops_per_mll_draw(M_SIDE) * S * args.steps / (solve_ms * 1e-3) / 1e12
         traffic = None
@@ -317,9 +317,9 @@ def main():
                 traffic = tj["dram_gbytes_per_launch"] * 1e9
         except Exception:
             pass
-        roofline = {"bound": "tensor", "kernel": "solve_dataflow_kernel<FWD|BWD|TRMM> (FP64 DMMA)",
+        roofline = {"bound": "tensor", "kernel": "solve_seq_kernel (6 fused forward/backward solves) + solve_dataflow_kernel<TRMM> (FP64 DMMA)",
                     "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak,
-                    "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read+write, avg over the 7 launches of a step)",
+                    "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read+write, avg over the DMMA launches of a step)",
                     "launches": int(solve_n), "avg_launch_ms": solve_ms / max(solve_n, 1),
                     "algorithmic_flops_per_launch": algo_flops_per_launch,
                     "peak_source": "measured live: register-resident mma.sync.m8n8k4.f64 loop (MEASURED_PEAKS.json has no FP64 figure)",

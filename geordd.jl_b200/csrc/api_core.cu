@@ -7,7 +7,7 @@ namespace geordd {
 long long g_kernel_launches = 0;
 
 const char* const kProfNames[PC_COUNT] = {"cov", "potrf", "solve_fwd", "solve_bwd", "trmm",
-                                          "gemm", "rng", "finish", "lu", "misc"};
+                                          "gemm", "rng", "finish", "lu", "misc", "solve_seq"};
 
 // ---- profiling -------------------------------------------------------------------------------------
 ProfScope::ProfScope(geordd_ctx* ctx, int cls) : c(ctx) {

@@ -15,7 +15,7 @@
 
 namespace geordd {
 
-enum ProfClass { PC_COV = 0, PC_POTRF, PC_FWD, PC_BWD, PC_TRMM, PC_GEMM, PC_RNG, PC_FINISH, PC_LU, PC_MISC, PC_COUNT };
+enum ProfClass { PC_COV = 0, PC_POTRF, PC_FWD, PC_BWD, PC_TRMM, PC_GEMM, PC_RNG, PC_FINISH, PC_LU, PC_MISC, PC_SEQ, PC_COUNT };
 extern const char* const kProfNames[PC_COUNT];
 
 struct ApiError : std::runtime_error {

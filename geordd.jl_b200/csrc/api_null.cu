@@ -265,14 +265,24 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
                 eT.wmat = h->RN.p; eT.ldw = npN; eT.wshift = mN - mTc; eT.wrows = mT; eT.dot0 = h->partT.p;
                 eC.wmat = h->RN.p; eC.wrow0 = mT; eC.ldw = npN; eC.wshift = mN - mCc; eC.wrows = mC; eC.dot0 = h->partC.p;
             }
-            pd_solve(c, T->dL, mTp, h->AT.p, mTp, ncols, eT);
-            pd_solve(c, C->dL, mCp, h->AC.p, mCp, ncols, eC);
+            // forward and backward solves of all GPs as ONE persistent kernel (solve.cu, fused solve sequence)
+            SolveEpilogue none;
+            none.xb = true;
+            SolveSeqItem it[SOLVE_SEQ_MAX];
+            int ns = 0;
+            it[ns++] = SolveSeqItem{SOLVE_FWD, T->dL, mTp, h->AT.p, none, -1};
+            it[ns++] = SolveSeqItem{SOLVE_FWD, C->dL, mCp, h->AC.p, none, -1};
+            if (rq.want_mll) it[ns++] = SolveSeqItem{SOLVE_FWD, N->dL, npN, h->AN.p, none, -1};
+            it[ns++] = SolveSeqItem{SOLVE_BWD, T->dL, mTp, h->AT.p, eT, 0};
+            it[ns++] = SolveSeqItem{SOLVE_BWD, C->dL, mCp, h->AC.p, eC, 1};
             if (rq.want_mll) {
                 SolveEpilogue eN;
                 eN.xb = true;
                 eN.wmat = h->RN.p; eN.ldw = npN; eN.dot0 = h->partN.p;
-                pd_solve(c, N->dL, npN, h->AN.p, npN, ncols, eN);
+                it[ns++] = SolveSeqItem{SOLVE_BWD, N->dL, npN, h->AN.p, eN, 2};
             }
+            ProfScope ps(c, PC_SEQ);
+            launch_solve_seq(st, c->sched, it, ns, ncols);
         }
         // Partials of dead columns in the last slab are garbage-free (zero inputs) and ignored.
         if (rq.want_mll) {

@@ -118,6 +118,19 @@ struct SolveEpilogue {
 constexpr int NARROW_MAX_COLS = 128;
 void launch_solve(cudaStream_t st, Sched& sched, SolveMode mode, const double* L, int npad, double* B, long ldb,
                   int ncols, const SolveEpilogue& epi, int live_cols = 0);
+// Several XB solves over the same ncols right-hand sides as ONE persistent kernel (no per-kernel tails).  `after`
+// (index of an earlier item, or -1): a job of this item may start once that item has finished the job's slab
+// (backward after forward of the same buffer).
+constexpr int SOLVE_SEQ_MAX = 6;
+struct SolveSeqItem {
+    SolveMode mode;
+    const double* L;
+    int npad;
+    double* B;
+    SolveEpilogue epi;
+    int after = -1;
+};
+void launch_solve_seq(cudaStream_t st, Sched& sched, const SolveSeqItem* items, int n, int ncols);
 void launch_solve_narrow(cudaStream_t st, Sched& sched, SolveMode mode, const double* L, int npad, double* B, long ldb,
                          int live_cols);
 

@@ -187,13 +187,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) solve_dataflow_kernel(SolveParams
                 const int n = tid >> 2, q = tid & 3;
                 const long col = (long)s * SLAB + n;
                 double s0 = 0.0, s1 = 0.0;
-#pragma unroll 4
+                // wmat is not written by this kernel: read-only cached loads (a thread's 32 rows share two L1 lines)
+#pragma unroll 8
                 for (int mm = 0; mm < 32; ++mm) {
                     int m = q * 32 + mm;
                     int r = rb * TILE + m;
                     double x = Cs[n * SC + m];
                     if (e.dot0) {
-                        double w = ldcg(XB ? e.wmat + zb_off(r + e.wrow0, col, (int)e.ldw) : e.wmat + col * e.ldw + r);
+                        double w = __ldg(XB ? e.wmat + zb_off(r + e.wrow0, col, (int)e.ldw) : e.wmat + col * e.ldw + r);
                         if (r < e.wrows) w += e.wshift;
                         s0 += w * x;
                     }
@@ -230,6 +231,188 @@ static void launch_mode(cudaStream_t st, Sched& sched, const SolveParams& p) {
     solve_dataflow_kernel<MODE, XB><<<grid, NTHREADS, SOLVE_SMEM, st>>>(p); ++g_kernel_launches;
 }
 
+
+// ---- fused solve sequence ---------------------------------------------------------------------------------
+// update_alpha! of the three GPs of one batch of draws (src/hypotest_mll.jl:1-19) is six solves: forward and
+// backward against L_T, L_C, L_N.  Launched one by one, every kernel ends with a tail in which CTAs idle while the
+// longest (last-level) jobs finish.  Here all six run as ONE persistent kernel over a single job list ordered
+//   fwd(0), fwd(1), fwd(2), bwd(0), bwd(1), bwd(2)
+// (level-major inside each): CTAs that run out of jobs of one solve continue with the next one, whose jobs depend on
+// nothing that is still running (a backward job waits for "forward of its slab complete", published long before).
+// Right-hand sides are in ZB storage (one-thread TMA feed).
+struct SeqSolve {
+    const double* L;
+    double* B;
+    int T;
+    int mode;        // SOLVE_FWD / SOLVE_BWD
+    int flag_off;    // this solve's flag region
+    int after_off;   // >= 0: flag region of the forward solve whose slab must be complete before a job may start
+    int after_T;
+    SolveEpilogue epi;
+};
+struct SeqParams {
+    int nsolves, nslabs;
+    int job_end[SOLVE_SEQ_MAX];
+    unsigned* flags;
+    unsigned epoch;
+    unsigned* counter;
+    int* abort_word;
+    SeqSolve s[SOLVE_SEQ_MAX];
+};
+
+struct SeqSrc {
+    const double* L;
+    const double* X;
+    long lda, ldb;
+    int rb, T, s, nslabs, mode;
+    const unsigned* flags;
+    unsigned epoch;
+    int* abort_word;
+    __device__ __forceinline__ int ktile(int c) const {
+        return mode == SOLVE_BWD ? (T - 1 - c / CHUNKS_PER_TILE_S) : c / CHUNKS_PER_TILE_S;
+    }
+    __device__ __forceinline__ const double* a_ptr(int c) const {
+        return L + tile_off(rb, ktile(c), T) + (long)(c % CHUNKS_PER_TILE_S) * BK * TLD;
+    }
+    __device__ __forceinline__ const double* b_ptr(int c) const {
+        return X + ((long)ktile(c) * CHUNKS_PER_TILE_S + c % CHUNKS_PER_TILE_S) * ZB_ELEMS;
+    }
+    __device__ __forceinline__ bool ready(int c) const {   // warp 0 only (one-thread feed)
+        if (c % CHUNKS_PER_TILE_S != 0) return true;
+        bool ok = warp_wait_flags(flags + (long)ktile(c) * nslabs + s, nullptr, epoch, abort_word);
+        fence_proxy_async();
+        return ok;
+    }
+};
+
+__global__ void __launch_bounds__(NTHREADS, 2) solve_seq_kernel(const __grid_constant__ SeqParams p) {
+    using ML = SolveCfg<SOLVE_FWD, true>::ML;
+    extern __shared__ __align__(16) double smem[];
+    double* Cs = smem;
+    double* Lp = smem + SOLVE_CS_ELEMS;
+    double* invd = Lp + SOLVE_PANEL_ELEMS;
+    __shared__ int sh_job;
+    const int tid = threadIdx.x;
+    Ring ring;
+    ML::ring_init(ring, reinterpret_cast<uint64_t*>(smem + SOLVE_SMEM_ELEMS - ML::BAR_WORDS), p.abort_word);
+    const int njobs = p.job_end[p.nsolves - 1];
+    const long ncols = (long)p.nslabs * SLAB;
+
+    while (true) {
+        if (tid == 0) {
+            int jb = (int)atomicAdd(p.counter, 1u);
+            if (ld_volatile_int(p.abort_word) != 0) jb = njobs;
+            sh_job = jb;
+        }
+        __syncthreads();
+        int job = sh_job;
+        if (job >= njobs) break;
+        int k = 0;
+        while (job >= p.job_end[k]) ++k;
+        if (k > 0) job -= p.job_end[k - 1];
+        const SeqSolve& q = p.s[k];
+        const int mode = q.mode, T = q.T;
+        const int lvl = job / p.nslabs, s = job % p.nslabs;
+        const int rb = (mode == SOLVE_FWD) ? lvl : (T - 1 - lvl);
+        const unsigned* flags = p.flags + q.flag_off;
+        double* Bslab = q.B + (long)s * (T * CHUNKS_PER_TILE_S) * ZB_ELEMS;
+        auto xb_at = [&](int m, int n) { return Bslab + ((long)rb * CHUNKS_PER_TILE_S + (m >> 4)) * ZB_ELEMS + n * ZB_LD + (m & 15); };
+
+        if (q.after_off >= 0) {   // the forward solve of this slab has written all of B (and nobody reads it any more)
+            int okf = 1;
+            if (tid == 0) okf = wait_flag(p.flags + q.after_off + (long)(q.after_T - 1) * p.nslabs + s, p.epoch, p.abort_word);
+            if (!__syncthreads_and(okf)) break;
+        }
+        typename ML::Acc acc;
+#pragma unroll
+        for (int a = 0; a < ML::MI; ++a)
+#pragma unroll
+            for (int b = 0; b < ML::NJ; ++b)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) acc.v[a][b][e] = -ldcg(xb_at(ML::acc_row(a), ML::acc_col(b, e)));
+        SeqSrc src{q.L, Bslab, 0, 0, rb, T, s, p.nslabs, mode, flags, p.epoch, p.abort_word};
+        const int nchunks = (mode == SOLVE_FWD ? rb : T - 1 - rb) * CHUNKS_PER_TILE_S;
+        bool ok = ML::run(smem, ring, nchunks, src, acc);
+        if (__syncthreads_or(!ok)) break;
+#pragma unroll
+        for (int a = 0; a < ML::MI; ++a)
+#pragma unroll
+            for (int b = 0; b < ML::NJ; ++b)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) Cs[ML::acc_col(b, e) * SC + ML::acc_row(a)] = -acc.v[a][b][e];
+        __syncthreads();
+
+        const double* Ldiag = q.L + tile_off(rb, rb, T);
+        if (mode == SOLVE_FWD) solve_fwd_tile(Cs, SLAB, Lp, invd, Ldiag, TLD);
+        else solve_bwd_tile(Cs, SLAB, Lp, invd, Ldiag, TLD);
+
+        const SolveEpilogue& e = q.epi;
+        for (int idx = tid; idx < SLAB * TILE; idx += NTHREADS) {
+            int n = idx / TILE, m = idx % TILE;
+            *xb_at(m, n) = Cs[n * SC + m];
+        }
+        if (e.dot0 || e.dot1) {   // same partials, same summation order as solve_dataflow_kernel
+            const int n = tid >> 2, qq = tid & 3;
+            const long col = (long)s * SLAB + n;
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll 8
+            for (int mm = 0; mm < 32; ++mm) {
+                int m = qq * 32 + mm;
+                int r = rb * TILE + m;
+                double x = Cs[n * SC + m];
+                if (e.dot0) {
+                    double w = __ldg(e.wmat + zb_off(r + e.wrow0, col, (int)e.ldw));
+                    if (r < e.wrows) w += e.wshift;
+                    s0 += w * x;
+                }
+                if (e.dot1) s1 += e.wvec[r] * x;
+            }
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+            if (qq == 0) {
+                if (e.dot0) e.dot0[(long)rb * ncols + col] = s0;
+                if (e.dot1) e.dot1[(long)rb * ncols + col] = s1;
+            }
+        }
+        __threadfence();
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) st_release(p.flags + q.flag_off + (long)rb * p.nslabs + s, p.epoch);
+    }
+}
+
+void launch_solve_seq(cudaStream_t st, Sched& sched, const SolveSeqItem* items, int n, int ncols) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(solve_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM);
+        attr_set = true;
+    }
+    SeqParams p;
+    p.nsolves = n; p.nslabs = ncols / SLAB;
+    p.flags = sched.flags; p.counter = sched.counter; p.abort_word = sched.abort_word;
+    int off = 0, jobs = 0;
+    int offs[SOLVE_SEQ_MAX];
+    for (int k = 0; k < n; ++k) {
+        SeqSolve& q = p.s[k];
+        q.L = items[k].L; q.B = items[k].B; q.T = items[k].npad / TILE; q.mode = (int)items[k].mode;
+        q.flag_off = off; offs[k] = off;
+        q.after_off = items[k].after >= 0 ? offs[items[k].after] : -1;
+        q.after_T = items[k].after >= 0 ? items[items[k].after].npad / TILE : 0;
+        q.epi = items[k].epi;
+        off += q.T * p.nslabs;
+        jobs += q.T * p.nslabs;
+        p.job_end[k] = jobs;
+    }
+    for (int k = n; k < SOLVE_SEQ_MAX; ++k) p.job_end[k] = jobs;
+    cudaMemsetAsync(sched.counter, 0, sizeof(unsigned), st);
+    sched.epoch++;
+    p.epoch = sched.epoch;
+    int grid = 2 * sched.num_sms;
+    if (grid > jobs) grid = jobs;
+    solve_seq_kernel<<<grid, NTHREADS, SOLVE_SMEM, st>>>(p); ++g_kernel_launches;
+}
 
 void launch_solve(cudaStream_t st, Sched& sched, SolveMode mode, const double* L, int npad, double* B, long ldb,
                   int ncols, const SolveEpilogue& epi, int live_cols) {
