@@ -312,7 +312,7 @@ def main():
         achieved = flops_per_mll_draw(M_SIDE) * S * args.steps / (solve_ms * 1e-3) / 1e12
         traffic = None
         try:   # per-launch DRAM traffic of the dominant kernel family from the committed ncu capture (same draw count only)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01c_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01d_traffic.json")))
             if tj.get("draws") == S:
                 traffic = tj["dram_gbytes_per_launch"] * 1e9
         except Exception:

@@ -16,7 +16,7 @@ def main():
     for rep in sys.argv[1:]:
         hdr, units, rows = raw(rep); idx = {h: i for i, h in enumerate(hdr)}
         for r in rows:
-            name = r[idx['Kernel Name']].split('(')[0].replace('void ', '')
+            name = r[idx['Kernel Name']].split('(geordd')[0].split('(Solve')[0].replace('void ', '').replace('geordd::', '').replace('(int)', '').replace('(bool)', '').replace(', ', ';').replace(',', ';')
             lines.append(name + ',' + ','.join(r[idx[k]].replace(',', '') if k in idx else '' for k in KEYS))
     print('\n'.join(lines))
 main()
