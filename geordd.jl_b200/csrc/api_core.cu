@@ -437,6 +437,12 @@ int geordd_ctx_set_max_batch(geordd_ctx* c, long mb) {
     return 0;
 }
 
+int geordd_ctx_set_mll_forward_only(geordd_ctx* c, int enable) {
+    if (!c) return GEORDD_ERR_ARG;
+    c->mll_forward_only = enable != 0;
+    return 0;
+}
+
 int geordd_cov_sym(geordd_ctx* c, const geordd_kernel* k, const double* X, int dim, int n, double diag_add, double* K) {
     API_BEGIN(c)
     check_kernel(k);

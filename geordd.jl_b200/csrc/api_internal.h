@@ -60,6 +60,7 @@ struct geordd_ctx {
     geordd::Sched sched{};
     std::string err;
     long max_batch = 0;
+    bool mll_forward_only = false;
     // caching device-memory pool
     std::multimap<size_t, void*> pool_free;
     std::unordered_map<void*, size_t> pool_live;

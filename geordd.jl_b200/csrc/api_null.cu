@@ -193,6 +193,8 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
     const int n = N->n, npN = N->npad, mT = T->n, mTp = T->npad, mC = C->n, mCp = C->npad, nbp = h->nbp, nb = h->nb;
     if (rq.nsim <= 0) throw ApiError(GEORDD_ERR_ARG, "nsim must be positive");
     if (rq.want_cliff && nb <= 0) throw ApiError(GEORDD_ERR_ARG, "null handle was prepared without sentinels");
+    // opt-in forward-only evaluation of the mll quadratic forms (include/geordd_b200.h, geordd_ctx_set_mll_forward_only)
+    const bool fwd_only = c->mll_forward_only && rq.want_mll && !rq.want_cliff && !rq.last_y && !rq.last_alpha;
     const long cap = pick_batch(h, rq.nsim);
     const int TN = npN / TILE, TT = mTp / TILE, TC = mCp / TILE, TS = nbp > 0 ? nbp / TILE : 0;
     // (re)allocate simulation buffers for `cap` columns; padded regions must be zero, so a fresh
@@ -207,8 +209,10 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
     h->AT.ensure(zb_elems(mTp, cap), st, true);
     h->AC.ensure(zb_elems(mCp, cap), st, true);
     if (rq.want_mll) {
-        h->RN.ensure(zb_elems(npN, cap), st, true);
-        h->AN.ensure(zb_elems(npN, cap), st, true);
+        if (!fwd_only) {
+            h->RN.ensure(zb_elems(npN, cap), st, true);
+            h->AN.ensure(zb_elems(npN, cap), st, true);
+        }
         h->partN.ensure((size_t)TN * cap, st, true);
         h->partT.ensure((size_t)TT * cap, st, true);
         h->partC.ensure((size_t)TC * cap, st, true);
@@ -248,7 +252,7 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
             SolveEpilogue e;
             e.xb = true;
             e.nrows = n; e.split = mT; e.add_const = mN; e.add_T = rq.tau;
-            if (rq.want_mll) {
+            if (rq.want_mll && !fwd_only) {
                 e.out0 = h->RN.p; e.ld0 = npN; e.sub_0 = mN;
                 e.out1 = h->AN.p; e.ld1 = npN; e.sub_1 = mN;
             }
@@ -258,7 +262,18 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
             launch_solve(st, c->sched, SOLVE_TRMM, N->dL, npN, h->Z.p, npN, ncols, e);
         }
         // 3. update_alpha! on T, C (and N), with the (y - m)' alpha quadratic forms fused into the solves
-        {
+        if (fwd_only) {
+            // (y-m)'K^-1(y-m) = |L^-1 (y-m)|^2: forward solves only, sum of squares fused; pooled null: z'z
+            launch_zb_colsumsq(st, h->Z.p, npN, ncols, h->partN.p);
+            SolveEpilogue eT, eC;
+            eT.xb = eC.xb = true;
+            eT.dot_self = eC.dot_self = true;
+            eT.dot0 = h->partT.p; eC.dot0 = h->partC.p;
+            SolveSeqItem it[2] = {SolveSeqItem{SOLVE_FWD, T->dL, mTp, h->AT.p, eT, -1},
+                                  SolveSeqItem{SOLVE_FWD, C->dL, mCp, h->AC.p, eC, -1}};
+            ProfScope ps(c, PC_SEQ);
+            launch_solve_seq(st, c->sched, it, 2, ncols);
+        } else {
             SolveEpilogue eT, eC;
             eT.xb = eC.xb = true;
             if (rq.want_mll) {
@@ -288,7 +303,7 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
         if (rq.want_mll) {
             FinishMll f{};
             f.partN = h->partN.p; f.partT = h->partT.p; f.partC = h->partC.p;
-            f.nbN = TN; f.nbT = TT; f.nbC = TC; f.ncols = ncols; f.ndraws = live;
+            f.nbN = fwd_only ? 1 : TN; f.nbT = TT; f.nbC = TC; f.ncols = ncols; f.ndraws = live;
             f.halflogdetN = N->logdet / 2.0; f.halflogdetT = T->logdet / 2.0; f.halflogdetC = C->logdet / 2.0;
             f.constN = (double)n * kLog2Pi / 2.0; f.constT = (double)mT * kLog2Pi / 2.0; f.constC = (double)mC * kLog2Pi / 2.0;
             f.dmll_obs = rq.dmll_obs; f.out_null = h->oNull.p; f.out_alt = h->oAlt.p; f.out_off = done;

@@ -96,7 +96,9 @@ struct SolveEpilogue {
     // FWD/BWD: fused statistic partials, written per row block (deterministic; reduced later):
     //   dot0[rb*ncols + c] = sum_{r in block rb} (wmat(r,c) + (r < wrows ? wshift : 0)) * X(r,c)
     //   dot1[rb*ncols + c] = sum_{r in block rb} wvec[r] * X(r,c)
+    //   dot_self: dot0 uses X itself as the weight (sum of squares of the solved block; wmat ignored)
     const double* wmat = nullptr; long ldw = 0; double wshift = 0.0; int wrows = 0;
+    bool dot_self = false;
     double* dot0 = nullptr;
     const double* wvec = nullptr;
     double* dot1 = nullptr;
@@ -148,6 +150,8 @@ void launch_philox_normals(cudaStream_t st, unsigned long long seed, unsigned lo
                            double* Z, long ldz, int npad, bool blocked);
 // dense (n x ncols_live, ldz) -> ZB storage for ncols (multiple of 64) draws, zero padded; and back
 void launch_zb_pack(cudaStream_t st, const double* dense, long ldz, int n, long ncols_live, double* Zb, int npad, long ncols);
+// out[col] = sum over rows of Z(r, col)^2 for ncols draws in ZB storage (padded rows are zero)
+void launch_zb_colsumsq(cudaStream_t st, const double* Zb, int npad, long ncols, double* out);
 void launch_zb_unpack(cudaStream_t st, const double* Zb, int npad, double* dense, long ldz, int n, long ncols_live, long col0);
 
 }  // namespace geordd

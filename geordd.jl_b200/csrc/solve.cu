@@ -194,8 +194,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) solve_dataflow_kernel(SolveParams
                     int r = rb * TILE + m;
                     double x = Cs[n * SC + m];
                     if (e.dot0) {
-                        double w = __ldg(XB ? e.wmat + zb_off(r + e.wrow0, col, (int)e.ldw) : e.wmat + col * e.ldw + r);
-                        if (r < e.wrows) w += e.wshift;
+                        double w = x;
+                        if (!e.dot_self) {
+                            w = __ldg(XB ? e.wmat + zb_off(r + e.wrow0, col, (int)e.ldw) : e.wmat + col * e.ldw + r);
+                            if (r < e.wrows) w += e.wshift;
+                        }
                         s0 += w * x;
                     }
                     if (e.dot1) s1 += e.wvec[r] * x;
@@ -361,8 +364,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) solve_seq_kernel(const __grid_con
                 int r = rb * TILE + m;
                 double x = Cs[n * SC + m];
                 if (e.dot0) {
-                    double w = __ldg(e.wmat + zb_off(r + e.wrow0, col, (int)e.ldw));
-                    if (r < e.wrows) w += e.wshift;
+                    double w = x;
+                    if (!e.dot_self) {
+                        w = __ldg(e.wmat + zb_off(r + e.wrow0, col, (int)e.ldw));
+                        if (r < e.wrows) w += e.wshift;
+                    }
                     s0 += w * x;
                 }
                 if (e.dot1) s1 += e.wvec[r] * x;

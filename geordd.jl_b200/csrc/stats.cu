@@ -71,6 +71,31 @@ __global__ void zb_pack_kernel(const double* __restrict__ dense, long ldz, int n
     double v = (r < n && col < live) ? dense[col * ldz + r] : 0.0;
     Zb[((col / 64) * (npad / BK) + r / BK) * ZB_ELEMS + (col % 64) * ZB_LD + r % BK] = v;
 }
+// one warp per draw: lanes stride over the K-chunks of the column, fixed-order shuffle reduction (deterministic)
+__global__ void zb_colsumsq_kernel(const double* __restrict__ Zb, int npad, long ncols, double* __restrict__ out) {
+    long col = (long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    if (col >= ncols) return;
+    const int lane = threadIdx.x & 31;
+    const int nch = npad / BK;
+    const double* base = Zb + ((col >> 6) * nch) * (long)ZB_ELEMS + (col & 63) * ZB_LD;
+    double s = 0.0;
+    for (int ch = lane; ch < nch; ch += 32) {
+        const double2* p = reinterpret_cast<const double2*>(base + (long)ch * ZB_ELEMS);
+#pragma unroll
+        for (int k = 0; k < BK / 2; ++k) {
+            double2 v = p[k];
+            s = fma(v.x, v.x, s);
+            s = fma(v.y, v.y, s);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[col] = s;
+}
+void launch_zb_colsumsq(cudaStream_t st, const double* Zb, int npad, long ncols, double* out) {
+    zb_colsumsq_kernel<<<(unsigned)((ncols + 7) / 8), 256, 0, st>>>(Zb, npad, ncols, out); ++g_kernel_launches;
+}
+
 __global__ void zb_unpack_kernel(const double* __restrict__ Zb, int npad, double* __restrict__ dense, long ldz, int n, long live,
                                  long col0) {
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -211,6 +211,11 @@ class Context:
     def set_max_batch(self, n: int) -> None:
         self.check(self.lib.geordd_ctx_set_max_batch(self._h, int(n)))
 
+    def set_mll_forward_only(self, on: bool) -> None:
+        """Opt-in: quadratic forms of the mll test as |L^-1 (y-m)|^2 / z'z (no backward solves); see the header."""
+        self.check(self.lib.geordd_ctx_set_mll_forward_only(self._h, 1 if on else 0))
+        self._mll_forward_only = bool(on)
+
     def profile(self, enable: bool) -> None:
         self.check(self.lib.geordd_ctx_profile(self._h, 1 if enable else 0))
 
@@ -600,15 +605,19 @@ def nsim_invvar_calib(gpT: GPE, gpC: GPE, Xb, nsim: int, nugget: float = 1e-10, 
 def nsim_logP(gpT: GPE, gpC: GPE, gpNull: NullGPE, nsim: int, *, seed: int = 0, draw0: int = 0, Z=None,
               dmll_obs: float = math.inf, return_count: bool = False):
     """nsim_logP(gpT, gpC, gpNull, nsim) (src/hypotest_mll.jl:21-30): list of (mll_null, mll_alt).
-    Like the reference it leaves gpNull.y / .alpha / .mll at the last draw (:6,10,14)."""
+    Like the reference it leaves gpNull.y / .alpha / .mll at the last draw (:6,10,14) -- except in the opt-in
+    forward-only mode (Context.set_mll_forward_only), which never forms alpha and leaves y / alpha untouched."""
     Zf, nz = _zarg(Z, gpNull.nobs)
     nsim = nz if nz is not None else int(nsim)
     mnull, malt = np.empty(nsim), np.empty(nsim)
-    last_y, last_a = np.empty(gpNull.nobs), np.empty(gpNull.nobs)
+    fwd_only = getattr(gpT.ctx, "_mll_forward_only", False)
+    last_y, last_a = (None, None) if fwd_only else (np.empty(gpNull.nobs), np.empty(gpNull.nobs))
     cnt = C.c_longlong()
     gpT.ctx.check(gpT.ctx.lib.geordd_null_mll(gpNull._h, nsim, seed, draw0, dptr(Zf), float(dmll_obs), dptr(mnull),
                                               dptr(malt), C.byref(cnt), dptr(last_y), dptr(last_a)))
-    gpNull.y, gpNull.alpha, gpNull.mll = last_y, last_a, float(mnull[-1])
+    if not fwd_only:
+        gpNull.y, gpNull.alpha = last_y, last_a
+    gpNull.mll = float(mnull[-1])
     sims = list(zip(mnull.tolist(), malt.tolist()))
     return (sims, cnt.value, mnull, malt) if return_count else sims
 

@@ -67,12 +67,18 @@ GEORDD_API int geordd_ctx_set_stream(geordd_ctx* ctx, void* cuda_stream);
 GEORDD_API int geordd_ctx_sync(geordd_ctx* ctx);
 /* Per-kernel-class CUDA-event timing (on the launching stream).  enable != 0 starts/clears it.
  * geordd_ctx_profile_get returns accumulated milliseconds and launch count for a kernel class
- * ("cov", "potrf", "solve_fwd", "solve_bwd", "trmm", "gemm", "rng", "finish", "lu", "misc"),
+ * ("cov", "potrf", "solve_fwd", "solve_bwd", "solve_seq", "trmm", "gemm", "rng", "finish", "lu", "misc"),
  * or for "*" the total over all classes. */
 GEORDD_API int geordd_ctx_profile(geordd_ctx* ctx, int enable);
 GEORDD_API int geordd_ctx_profile_get(geordd_ctx* ctx, const char* name, double* ms, long long* launches);
 /* Upper bound on null draws processed per internal batch (0 = automatic). */
 GEORDD_API int geordd_ctx_set_max_batch(geordd_ctx* ctx, long max_batch);
+/* Opt-in (default 0): evaluate the quadratic forms of geordd_null_mll without the backward solves,
+ *   (y-m)' K^-1 (y-m) = |L^-1 (y-m)|^2   and, for the pooled null GP whose draw is y = m + L z,   = z'z,
+ * instead of the reference's stepwise alpha = cK \ (y-m); dot(y-m, alpha) (src/gp_utils.jl:15-22,
+ * src/hypotest_mll.jl:1-19).  Same statistic in exact arithmetic (rounding-level differences, ~1e-12 relative), 6 m^2
+ * instead of 16 m^2 flop per draw.  Ignored when the caller asks for the final draw's y / alpha. */
+GEORDD_API int geordd_ctx_set_mll_forward_only(geordd_ctx* ctx, int enable);
 
 /* ---- K1 covariance assembly: cov(kernel, X, X) + diag_add*I and cov(kernel, X1, X2) ----------
  * replaces GaussianProcesses.cov / cov! (call sites src/hypotest_chi2.jl:38-39, src/power.jl:60-62,

@@ -223,6 +223,16 @@ function nsim_logP(gpT::B200GPE, gpC::B200GPE, gpNull::B200Null, nsim::Int; seed
     return collect(zip(mnull, malt))
 end
 
+"""
+    set_mll_forward_only!(ctx, on)
+
+Opt-in (default off): evaluate the quadratic forms of `nsim_logP` / `boot_mlltest` as |L⁻¹(y-m)|² (and z'z for the
+pooled null GP) instead of the reference's stepwise `alpha = cK \\ (y-m); dot(y-m, alpha)` -- the same statistic to
+rounding (~1e-12 relative) at 6 m² instead of 16 m² flop per draw.
+"""
+set_mll_forward_only!(ctx, on::Bool) =
+    check(ctx, ccall((:geordd_ctx_set_mll_forward_only, LIB), Cint, (Ptr{Cvoid}, Cint), ctx.ptr, on ? 1 : 0))
+
 "boot_mlltest(gpT, gpC, nsim) (src/hypotest_mll.jl:32-45)"
 function boot_mlltest(gpT::B200GPE, gpC::B200GPE, nsim::Int; kwargs...)
     mll_alt = gpT.mll + gpC.mll

@@ -464,6 +464,27 @@ def test_many_rhs_triangular_ops_every_column(G, O, ctx, n, nrhs):
             assert int((err > 1e-10).sum()) == 0, (mode, rep, float(err.max()))
 
 
+def test_mll_forward_only_mode_matches_stepwise(G, O, ctx):
+    """Opt-in |L^-1 (y-m)|^2 / z'z evaluation of the mll quadratic forms == the stepwise reference evaluation to
+    rounding, same exceedance count, also with non-zero means and unequal region sizes."""
+    d, (oT, oC), (gT, gC) = _pair(G, O, m=260, nb=16, kind=2, ragged=17, mean=(0.3, -0.2))
+    gN = G.make_null(gT, gC)
+    S = 700
+    d_obs = gT.mll + gC.mll - gN.mll
+    _, cnt0, n0, a0 = G.nsim_logP(gT, gC, gN, S, seed=9, dmll_obs=d_obs, return_count=True)
+    ctx.set_mll_forward_only(True)
+    try:
+        _, cnt1, n1, a1 = G.nsim_logP(gT, gC, gN, S, seed=9, dmll_obs=d_obs, return_count=True)
+        ctx.set_max_batch(128)
+        _, cnt2, n2, a2 = G.nsim_logP(gT, gC, gN, S, seed=9, dmll_obs=d_obs, return_count=True)
+    finally:
+        ctx.set_mll_forward_only(False)
+        ctx.set_max_batch(0)
+    assert relerr(n1, n0) < 1e-11 and relerr(a1, a0) < 1e-11
+    assert cnt1 == cnt0
+    assert np.array_equal(n1, n2) and np.array_equal(a1, a2) and cnt2 == cnt1
+
+
 @pytest.mark.parametrize("n,nrhs", [(129, 1), (300, 8), (700, 9), (1000, 100), (2000, 128), (2000, 1), (4000, 3)])
 def test_few_rhs_triangular_solves(G, O, ctx, n, nrhs):
     """<= 128 right-hand sides take the latency-optimised 8-column-slab kernel (solve_narrow.cu): forward and
