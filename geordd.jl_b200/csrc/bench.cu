@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tileops_cycles_kernel(const doubl
     extern __shared__ __align__(16) double smem[];
     double* Cs = smem;
     double* Lp = Cs + TILE * SC;
-    double* invd = Lp + TILE * LRS;
+    double* invd = Lp + 2 * NB * SC;   // two panel buffers (right solve) >= TILE*LRS (row panel of the backward solve)
     __shared__ int sh_info;
     long long best[4] = {1LL << 62, 1LL << 62, 1LL << 62, 1LL << 62};
     __shared__ long long prof[8];
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tileops_cycles_kernel(const doubl
             __syncthreads();
             long long t0 = clock64();
             if (op == 0) potrf_tile(Cs, invd, &sh_info, r == reps - 1 ? prof : nullptr);
-            if (op == 1) trsm_right_tile(Cs, Lp, invd, Limg, TLD, r == reps - 1 ? prof + 3 : nullptr);
+            if (op == 1) trsm_right_tile(Cs, Lp, Lp + NB * SC, invd, Limg, TLD, r == reps - 1 ? prof + 3 : nullptr);
             if (op == 2) solve_fwd_tile(Cs, 64, Lp, invd, Limg, TLD);
             if (op == 3) solve_bwd_tile(Cs, 64, Lp, invd, Limg, TLD);
             __syncthreads();
@@ -194,7 +194,7 @@ int geordd_bench_tileops(geordd_ctx* c, double* cycles4) {
         launch_cov(c->stream, spec, dX, n, dX, n, 2, true, true, 0.09, dK, n, n, n, false);
         launch_potrf(c->stream, c->sched, dK, dL, n, n);
         GD_CUDA(cudaMemcpy2DAsync(dA, TLD * sizeof(double), dK, n * sizeof(double), n * sizeof(double), n, cudaMemcpyDeviceToDevice, c->stream));
-        const size_t smem = (size_t)(TILE * SC + TILE * LRS + TILE) * sizeof(double);
+        const size_t smem = (size_t)(TILE * SC + 2 * NB * SC + TILE) * sizeof(double);
         cudaFuncSetAttribute(tileops_cycles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         tileops_cycles_kernel<<<1, NTHREADS, smem, c->stream>>>(dA, dL, 5, dOut);
         long long h[10];

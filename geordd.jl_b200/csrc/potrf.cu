@@ -43,7 +43,7 @@ struct PotrfSrc {
 
 constexpr int POTRF_CS_ELEMS = TILE * SC;
 constexpr int POTRF_LP_ELEMS = NB * SC;
-constexpr size_t POTRF_SMEM = (size_t)(POTRF_CS_ELEMS + POTRF_LP_ELEMS + TILE + PotrfML::BAR_WORDS) * sizeof(double);
+constexpr size_t POTRF_SMEM = (size_t)(POTRF_CS_ELEMS + 2 * POTRF_LP_ELEMS + TILE + PotrfML::BAR_WORDS) * sizeof(double);
 static_assert(PotrfML::SMEM_BYTES <= POTRF_CS_ELEMS * sizeof(double), "stage ring must fit under the C tile");
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -52,7 +52,8 @@ potrf_dataflow_kernel(const double* __restrict__ A, double* __restrict__ L, long
     extern __shared__ __align__(16) double smem[];
     double* Cs = smem;                       // aliases the mainloop stage ring
     double* Lp = smem + POTRF_CS_ELEMS;
-    double* invd = Lp + POTRF_LP_ELEMS;
+    double* Lp1 = Lp + POTRF_LP_ELEMS;   // second panel buffer of the right solve
+    double* invd = Lp1 + POTRF_LP_ELEMS;
     __shared__ int sh_job;
     __shared__ int sh_info;
     const int tid = threadIdx.x;
@@ -111,7 +112,7 @@ potrf_dataflow_kernel(const double* __restrict__ A, double* __restrict__ L, long
             int okf = 1;
             if (tid == 0) okf = wait_flag(flags + (long)j * T + j, epoch, abort_word);
             if (!__syncthreads_and(okf)) break;
-            trsm_right_tile(Cs, Lp, invd, L + tile_off(j, j, T), TLD);
+            trsm_right_tile(Cs, Lp, Lp1, invd, L + tile_off(j, j, T), TLD);
             for (int idx = tid; idx < TILE * TLD; idx += NTHREADS) {
                 int m = idx % TLD;
                 Lij[idx] = (m < TILE) ? Cs[idx] : 0.0;

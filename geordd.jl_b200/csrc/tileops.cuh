@@ -14,17 +14,42 @@ constexpr int SC = TILE + PAD;   // 132: stride of tiles held in smem
 constexpr int NB = 32;           // inner block
 constexpr int LRS = NB + PAD;    // 36: stride of a row-panel held k-contiguous
 
-// 1/sqrt(x) for normal positive x: MUFU.RSQ64H seed (2^-22) + two Newton steps in FMA form, ~1 ulp, no slow path
-// (the CUDA rsqrt() carries a call for subnormals that costs registers and a stack frame in the tile kernels).
+// 1/sqrt(x) for normal positive x: MUFU.RSQ64H seed (relative error e0 ~ 2^-22) + ONE third-order step
+//   y1 = y0 + y0*e*(1/2 + 3/8 e),  e = 1 - x*y0^2        (error ~ e0^3, below the rounding of the final FMA)
+// Four dependent FP64 operations instead of the six of two Newton steps: this sits on the pivot chain of the
+// Cholesky.  No slow path (the CUDA rsqrt() carries a call for subnormals that costs registers and a stack frame).
 __device__ __forceinline__ double rsqrt_pos(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double h = 0.5 * x;
-    double e = fma(-h * y, y, 0.5);
-    y = fma(y, e, y);
-    e = fma(-h * y, y, 0.5);
-    y = fma(y, e, y);
-    return y;
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    const double q = y * e;
+    return fma(q, p, y);
+}
+
+// x[c2] -= xc * row[c2] for c2 in (c, NB): `row` points at 32 consecutive doubles in shared memory, 16-byte aligned;
+// pairs starting at an even c2 are fetched with one LDS.128 (the substitution loops are bound by broadcast loads).
+template <int C>
+__device__ __forceinline__ void axpy_tail(double (&x)[NB], double xc, const double* row) {
+    constexpr int first = C + 1;
+    if constexpr ((first & 1) != 0 && first < NB) x[first] -= xc * row[first];
+    constexpr int p0 = (first + 1) & ~1;   // first even index >= first
+#pragma unroll
+    for (int c2 = p0; c2 + 1 < NB; c2 += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(row + c2);
+        x[c2] -= xc * v.x;
+        x[c2 + 1] -= xc * v.y;
+    }
+}
+template <int C = 0>
+__device__ __forceinline__ void forward_subst32(double (&x)[NB], const double* invd, const double* L00, int stride) {
+    // x <- x solved against the 32x32 lower block whose column c starts at L00 + c*stride (rows c.. contiguous)
+    if constexpr (C < NB) {
+        x[C] *= invd[C];
+        axpy_tail<C>(x, x[C], L00 + C * stride);
+        forward_subst32<C + 1>(x, invd, L00, stride);
+    }
 }
 
 // C(m0.., n0..) -= A * B over K = NB, for 8x8 output tiles (mt, nt), mt in [0,mtiles), nt in
@@ -100,7 +125,7 @@ __device__ inline void potrf_tile(double* Cs, double* invd, int* sh_info, long l
 #pragma unroll
             for (int c = 0; c < NB; ++c) {
                 const bool pos = diag >= 2.2250738585072014e-308;  // positive normal (also catches NaN); lane c's counts
-                const double inv_own = rsqrt_pos(pos ? diag : 1.0);
+                const double inv_own = rsqrt_pos(diag);            // NaN / inf for a bad pivot: flagged below, never used
                 const double inv = __shfl_sync(0xffffffffu, inv_own, c);
                 if (lane == c && !pos) first_bad = c + 1;          // branch-free in SASS: keeps the block one basic block
                 const double l = a[c] * inv;                       // column c of L below the diagonal (lanes > c)
@@ -134,12 +159,7 @@ __device__ inline void potrf_tile(double* Cs, double* invd, int* sh_info, long l
             double x[NB];
 #pragma unroll
             for (int c = 0; c < NB; ++c) x[c] = Cs[(o + c) * SC + r];
-#pragma unroll
-            for (int c = 0; c < NB; ++c) {
-                x[c] *= invd[o + c];
-#pragma unroll
-                for (int c2 = c + 1; c2 < NB; ++c2) x[c2] -= x[c] * Cs[(o + c) * SC + o + c2];
-            }
+            forward_subst32(x, invd + o, Cs + o * SC + o, SC);
 #pragma unroll
             for (int c = 0; c < NB; ++c) Cs[(o + c) * SC + r] = x[c];
         }
@@ -179,13 +199,36 @@ __device__ __forceinline__ void load_row_panel(double* Lr, double* invd, const d
     if (threadIdx.x < NB) invd[threadIdx.x] = 1.0 / ldcg(Lt + (long)(o + threadIdx.x) * ld + o + threadIdx.x);
 }
 
+// cp.async copy of columns [o, o+NB) of the lower-triangular 128x128 tile Lt, rows [o, 128), into Lp(k, m) = Lp[k*SC + m]
+// (m absolute row in the tile).  o is a multiple of 32 and ld*8 a multiple of 16, so every 16-byte piece is aligned.
+__device__ __forceinline__ void load_col_panel_async(double* Lp, const double* Lt, long ld, int o) {
+    const int half = (TILE - o) / 2;   // 16-byte pieces per column
+    for (int id = threadIdx.x; id < NB * half; id += NTHREADS) {
+        int k = id / half, m = o + 2 * (id % half);
+        cp_async16(Lp + k * SC + m, Lt + (long)(o + k) * ld + m);
+    }
+    cp_async_commit();
+}
+
 // ---- X * Lt^T = C  (C: 128 x 128 in Cs, overwritten by X).  Rows are independent. -------------
-__device__ inline void trsm_right_tile(double* Cs, double* Lp, double* invd, const double* Lt, long ld, long long* prof = nullptr) {
+// The column panels of Lt are double-buffered (Lp0 / Lp1, NB*SC doubles each): the copy of the next panel runs under
+// the substitution and update of the current block.
+__device__ inline void trsm_right_tile(double* Cs, double* Lp0, double* Lp1, double* invd, const double* Lt, long ld,
+                                       long long* prof = nullptr) {
     const int tid = threadIdx.x;
     long long tp = prof ? clock64() : 0;
     auto lap = [&](int k) { if (prof) { long long t = clock64(); if (tid == 0) prof[k] += t - tp; tp = t; } };
-    for (int o = 0; o < TILE; o += NB) {
-        load_col_panel(Lp, invd, Lt, ld, o);
+    load_col_panel_async(Lp0, Lt, ld, 0);
+    for (int o = 0, b = 0; o < TILE; o += NB, b ^= 1) {
+        double* Lp = b ? Lp1 : Lp0;
+        if (o + NB < TILE) {
+            load_col_panel_async(b ? Lp0 : Lp1, Lt, ld, o + NB);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (tid < NB) invd[tid] = 1.0 / Lp[tid * SC + o + tid];
         __syncthreads();
         lap(0);
         if (tid < TILE) {
@@ -193,12 +236,7 @@ __device__ inline void trsm_right_tile(double* Cs, double* Lp, double* invd, con
             double x[NB];
 #pragma unroll
             for (int c = 0; c < NB; ++c) x[c] = Cs[(o + c) * SC + r];
-#pragma unroll
-            for (int c = 0; c < NB; ++c) {
-                x[c] *= invd[c];
-#pragma unroll
-                for (int c2 = c + 1; c2 < NB; ++c2) x[c2] -= x[c] * Lp[c * SC + o + c2];
-            }
+            forward_subst32(x, invd, Lp + o, SC);
 #pragma unroll
             for (int c = 0; c < NB; ++c) Cs[(o + c) * SC + r] = x[c];
         }
@@ -228,12 +266,7 @@ __device__ inline void solve_fwd_tile(double* Cs, int ncols, double* Lp, double*
             double x[NB];
 #pragma unroll
             for (int r = 0; r < NB; ++r) x[r] = col[r];
-#pragma unroll
-            for (int r = 0; r < NB; ++r) {
-                x[r] *= invd[r];
-#pragma unroll
-                for (int r2 = r + 1; r2 < NB; ++r2) x[r2] -= x[r] * Lp[r * SC + o + r2];
-            }
+            forward_subst32(x, invd, Lp + o, SC);
 #pragma unroll
             for (int r = 0; r < NB; ++r) col[r] = x[r];
         }
