@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libgeordd_b200.so")
-SOURCES = ["cov.cu", "potrf.cu", "solve.cu", "solve_narrow.cu", "gemm.cu", "stats.cu", "api_core.cu", "api_null.cu", "api_multigp.cu",
+SOURCES = ["cov.cu", "potrf.cu", "solve.cu", "solve_narrow.cu", "gemm.cu", "stats.cu", "geom.cu", "api_core.cu", "api_null.cu", "api_multigp.cu",
            "bench.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

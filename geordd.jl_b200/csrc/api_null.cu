@@ -449,6 +449,46 @@ int geordd_cliff_face(geordd_gp* T, geordd_gp* C, const double* Xb, int nb, doub
     API_END
 }
 
+int geordd_projection_points(geordd_ctx* c, const double* X, int n, const double* V, int nv, const int* part_start, int nparts,
+                             double* Xproj, double* dist) {
+    API_BEGIN(c)
+    if (!X || !V || !Xproj || !dist || n <= 0 || nv < 2 || nparts < 0 || (nparts > 0 && !part_start))
+        throw ApiError(GEORDD_ERR_ARG, "projection_points: bad arguments");
+    std::vector<unsigned char> brk((size_t)nv, 0);
+    brk[0] = 1;
+    for (int k = 0; k < nparts; ++k) {
+        if (part_start[k] < 0 || part_start[k] >= nv) throw ApiError(GEORDD_ERR_ARG, "projection_points: part_start out of range");
+        brk[part_start[k]] = 1;
+    }
+    bool any_segment = false;
+    for (int v = 1; v < nv; ++v) any_segment |= !brk[v];
+    if (!any_segment) throw ApiError(GEORDD_ERR_ARG, "projection_points: the border has no segment");
+    double *dX = nullptr, *dV = nullptr, *dP = nullptr, *dD = nullptr, *dB = nullptr;
+    try {
+        dX = dalloc((size_t)2 * n, c__->stream, false);
+        dV = dalloc((size_t)2 * nv, c__->stream, false);
+        dP = dalloc((size_t)2 * n, c__->stream, false);
+        dD = dalloc((size_t)n, c__->stream, false);
+        dB = dalloc((size_t)(nv + 7) / 8 + 1, c__->stream, false);
+        GD_CUDA(cudaMemcpyAsync(dX, X, (size_t)2 * n * sizeof(double), cudaMemcpyHostToDevice, c__->stream));
+        GD_CUDA(cudaMemcpyAsync(dV, V, (size_t)2 * nv * sizeof(double), cudaMemcpyHostToDevice, c__->stream));
+        GD_CUDA(cudaMemcpyAsync(dB, brk.data(), (size_t)nv, cudaMemcpyHostToDevice, c__->stream));
+        {
+            ProfScope ps(c__, PC_MISC);
+            launch_projection(c__->stream, dX, n, dV, reinterpret_cast<const unsigned char*>(dB), nv, dP, dD);
+        }
+        GD_CUDA(cudaMemcpyAsync(Xproj, dP, (size_t)2 * n * sizeof(double), cudaMemcpyDeviceToHost, c__->stream));
+        GD_CUDA(cudaMemcpyAsync(dist, dD, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c__->stream));
+        GD_CUDA(cudaStreamSynchronize(c__->stream));
+        GD_CUDA(cudaGetLastError());
+    } catch (...) {
+        dfree(dX); dfree(dV); dfree(dP); dfree(dD); dfree(dB);
+        throw;
+    }
+    dfree(dX); dfree(dV); dfree(dP); dfree(dD); dfree(dB);
+    API_END
+}
+
 int geordd_chistat_obs(geordd_gp* T, geordd_gp* C, const double* Xb, int nb, double* chi2) {
     if (!T) return GEORDD_ERR_ARG;
     API_BEGIN(T->ctx)

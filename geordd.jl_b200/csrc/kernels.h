@@ -154,4 +154,10 @@ void launch_zb_pack(cudaStream_t st, const double* dense, long ldz, int n, long 
 void launch_zb_colsumsq(cudaStream_t st, const double* Zb, int npad, long ncols, double* out);
 void launch_zb_unpack(cudaStream_t st, const double* Zb, int npad, double* dense, long ldz, int n, long ncols_live, long col0);
 
+// ---- geom.cu --------------------------------------------------------------------------------------
+// Nearest point on a (multi-)polyline for n units.  X: 2 x n, V: 2 x nv vertices, brk[v] != 0 where vertex v starts a
+// new line (no segment (v-1, v)).  Outputs: Xproj 2 x n, dist n.
+void launch_projection(cudaStream_t st, const double* X, int n, const double* V, const unsigned char* brk, int nv,
+                       double* Xproj, double* dist);
+
 }  // namespace geordd

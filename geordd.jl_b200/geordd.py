@@ -460,6 +460,75 @@ def weights_invvar(gpT: GPE, gpC: GPE, Xb):
 
 
 # ----------------------------------------------------------------------------------------------
+# Border geometry feeding the projected estimators (src/geometry.jl:22-30, src/border_projection.jl:4-31,
+# src/weight_at_units.jl:44-53,80-86)
+# ----------------------------------------------------------------------------------------------
+def sentinels(border, nsent: int) -> np.ndarray:
+    """sentinels(border, nsent) (src/geometry.jl:22-30): nsent points equally spaced in arclength along the border
+    polyline (nv x 2), end points included -> 2 x nsent.  O(nv + nsent) host geometry."""
+    V = np.asarray(border, dtype=np.float64)
+    seg = np.sqrt(np.sum(np.diff(V, axis=0) ** 2, axis=1))
+    cum = np.concatenate([[0.0], np.cumsum(seg)])
+    q = np.linspace(0.0, cum[-1], int(nsent))
+    idx = np.clip(np.searchsorted(cum, q, side="right") - 1, 0, len(seg) - 1)
+    safe = np.where(seg[idx] > 0, seg[idx], 1.0)
+    t = np.where(seg[idx] > 0, (q - cum[idx]) / safe, 0.0)
+    return fmat((V[idx] + t[:, None] * (V[idx + 1] - V[idx])).T)
+
+
+def _as_units(gp_or_X):
+    return fmat(gp_or_X.x if isinstance(gp_or_X, GPE) else gp_or_X)
+
+
+def projection_points_all(gp_or_X, border, part_start=(), ctx: Optional[Context] = None):
+    """Nearest point on the border and distance for EVERY unit (the per-unit LibGEOS distance / nearestPoints calls
+    of src/border_projection.jl:8-19, on the device).  border: nv x 2 vertices; part_start: vertex indices at which
+    further lines of a MultiLineString start.  Returns (Xproj 2 x n, dist n)."""
+    X = _as_units(gp_or_X)
+    if ctx is None:
+        ctx = gp_or_X.ctx if isinstance(gp_or_X, GPE) else default_context()
+    V = np.asarray(border, dtype=np.float64)
+    if V.ndim != 2 or V.shape[1] != 2:
+        raise ValueError("border must be an nv x 2 array of vertices")
+    Vt = fmat(V.T)                                                           # 2 x nv column-major
+    ps = np.ascontiguousarray(part_start, dtype=np.int32)
+    n = X.shape[1]
+    Xp, d = np.empty((2, n), order="F"), np.empty(n)
+    ctx.check(ctx.lib.geordd_projection_points(ctx._h, dptr(X), n, dptr(Vt), V.shape[0],
+                                               ps.ctypes.data_as(C.POINTER(C.c_int)) if ps.size else None, int(ps.size),
+                                               dptr(Xp), dptr(d)))
+    return Xp, d
+
+
+def projection_points(gp_or_X, border, maxdist: float, part_start=(), ctx: Optional[Context] = None) -> np.ndarray:
+    """projection_points(gp, border, maxdist) (src/border_projection.jl:4-22): projections of the units that lie
+    within maxdist of the border, in unit order."""
+    Xp, d = projection_points_all(gp_or_X, border, part_start, ctx)
+    return fmat(Xp[:, d <= maxdist])
+
+
+def proj_estimator(gpT: GPE, gpC: GPE, border, maxdist: float, part_start=()) -> Normal:
+    """proj_estimator(gpT, gpC, border, maxdist) (src/border_projection.jl:24-31; test/test_simulated.jl:58)."""
+    Xb = np.hstack([projection_points(gpT, border, maxdist, part_start), projection_points(gpC, border, maxdist, part_start)])
+    mu, S = cliff_face(gpT, gpC, fmat(Xb))
+    return unweighted_mean(mu, S)
+
+
+def weights_proj(gpT: GPE, gpC: GPE, border, maxdist: float, part_start=()):
+    """weights_proj (src/weight_at_units.jl:44-53): unit weights of the projected finite-population estimator."""
+    Xb = fmat(np.hstack([projection_points(gpT, border, maxdist, part_start), projection_points(gpC, border, maxdist, part_start)]))
+    wb = np.ones(Xb.shape[1])
+    return Xb, wb, np.concatenate([weight_at_units(gpT, Xb, wb), -weight_at_units(gpC, Xb, wb)])
+
+
+def weights_rho(gpT: GPE, gpC: GPE, density, nb: int, border):
+    """weights_rho (src/weight_at_units.jl:80-86): density-weighted sentinels equally spaced along the border."""
+    Xb = sentinels(border, nb)
+    wb = np.array([float(density(x1, x2)) for x1, x2 in zip(Xb[0], Xb[1])])
+    return Xb, wb, np.concatenate([weight_at_units(gpT, Xb, wb), -weight_at_units(gpC, Xb, wb)])
+
+
+# ----------------------------------------------------------------------------------------------
 # Null handle: make_null + draw-independent setup, and the Monte-Carlo tests
 # ----------------------------------------------------------------------------------------------
 class NullGPE:

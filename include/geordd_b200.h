@@ -113,6 +113,15 @@ GEORDD_API int geordd_inverse_variance(geordd_ctx* ctx, const double* mu, const 
 /* Julia's generic `A \\ B` on a dense square Matrix = lu(A) \\ B (partial pivoting; hit at
  * src/weight_at_units.jl:36, src/hypotest_chi2.jl:9).  A is n x n, B (n x nrhs) is overwritten by the solution. */
 GEORDD_API int geordd_solve_general(geordd_ctx* ctx, const double* A, int n, double* B, int nrhs);
+/* ---- K7 projection of units onto the border: nearest point on a (Multi)LineString and its distance ----------
+ * replaces the per-unit LibGEOS calls distance(border, point) / nearestPoints(border, point)[1] of projection_points
+ * (src/border_projection.jl:4-22), which feed proj_estimator (:24-31) and weights_proj (src/weight_at_units.jl:44-53).
+ * X: 2 x n unit coordinates; V: 2 x nv border vertices; part_start[nparts]: vertex indices at which a new line of a
+ * MultiLineString starts (vertex 0 always does; nparts may be 0).  Outputs: Xproj 2 x n, dist n; the caller keeps the
+ * columns with dist <= maxdist.  GEOS 3.8 arithmetic restated operation by operation (first minimum wins). */
+GEORDD_API int geordd_projection_points(geordd_ctx* ctx, const double* X, int n, const double* V, int nv, const int* part_start,
+                                        int nparts, double* Xproj, double* dist);
+
 /* weight_at_units(gp, sentinels, weights) (src/weight_at_units.jl:12-18): w_unit (n). */
 GEORDD_API int geordd_weight_at_units(geordd_gp* gp, const double* Xb, int nb, const double* w_border, double* w_unit);
 

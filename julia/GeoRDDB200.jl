@@ -224,6 +224,37 @@ function nsim_logP(gpT::B200GPE, gpC::B200GPE, gpNull::B200Null, nsim::Int; seed
 end
 
 """
+    projection_points(gp, border, maxdist)   (src/border_projection.jl:4-22)
+
+Nearest border point of every unit within `maxdist` of the border -- one device call instead of a LibGEOS call per unit.
+`border` is the LibGEOS (Multi)LineString; only its vertex coordinates cross the ABI.
+"""
+function projection_points(gp::B200GPE, border, maxdist::Float64)
+    lines = border isa LibGEOS.MultiLineString ? GeoInterface.coordinates(border) : [GeoInterface.coordinates(border)]
+    V = Matrix{Float64}(undef, 2, sum(length, lines)); starts = Cint[]; v = 0
+    for (k, line) in enumerate(lines)
+        k > 1 && push!(starts, v)
+        for p in line
+            v += 1; V[1, v] = p[1]; V[2, v] = p[2]
+        end
+    end
+    n = size(gp.x, 2); Xp = Matrix{Float64}(undef, 2, n); d = Vector{Float64}(undef, n)
+    GC.@preserve V starts Xp d begin
+        check(gp.ctx, ccall((:geordd_projection_points, LIB), Cint,
+                            (Ptr{Cvoid}, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Cint, Ptr{Cint}, Cint, Ptr{Cdouble}, Ptr{Cdouble}),
+                            gp.ctx.ptr, gp.x, n, V, size(V, 2), starts, length(starts), Xp, d))
+    end
+    return Xp[:, d .<= maxdist]
+end
+
+"proj_estimator(gpT, gpC, border, maxdist) (src/border_projection.jl:24-31)"
+function proj_estimator(gpT::B200GPE, gpC::B200GPE, border, maxdist::Float64)
+    X∂ = [projection_points(gpT, border, maxdist) projection_points(gpC, border, maxdist)]
+    μpost, Σpost = cliff_face(gpT, gpC, X∂)
+    return unweighted_mean(μpost, Σpost)
+end
+
+"""
     set_mll_forward_only!(ctx, on)
 
 Opt-in (default off): evaluate the quadratic forms of `nsim_logP` / `boot_mlltest` as |L⁻¹(y-m)|² (and z'z for the

@@ -809,3 +809,73 @@ def polyline_sentinels(border: np.ndarray, nsent: int) -> np.ndarray:
     t = np.where(seg[idx] > 0, (q - cum[idx]) / np.where(seg[idx] > 0, seg[idx], 1.0), 0.0)
     pts = border[idx] + t[:, None] * (border[idx + 1] - border[idx])
     return np.asfortranarray(pts.T)
+
+
+# ---------------------------------------------------------------------------------------------
+# Projection of units onto the border (src/border_projection.jl:4-31, src/weight_at_units.jl:44-53)
+# ---------------------------------------------------------------------------------------------
+def _geos_point_to_segment(px, py, ax, ay, bx, by):
+    """GEOS 3.8.1 algorithm/Distance.cpp Distance::pointToSegment [recalled; GEOS_jll 3.8.1+0, Manifest.toml:216-220],
+    vectorised over points; every operation separately rounded (NumPy never contracts to FMA)."""
+    if ax == bx and ay == by:
+        return np.sqrt((px - ax) * (px - ax) + (py - ay) * (py - ay))
+    ex, ey = bx - ax, by - ay
+    len2 = ex * ex + ey * ey
+    r = ((px - ax) * ex + (py - ay) * ey) / len2
+    dA = np.sqrt((px - ax) * (px - ax) + (py - ay) * (py - ay))
+    dB = np.sqrt((px - bx) * (px - bx) + (py - by) * (py - by))
+    sn = ((ay - py) * ex - (ax - px) * ey) / len2
+    dS = np.abs(sn) * np.sqrt(len2)
+    return np.where(r <= 0.0, dA, np.where(r >= 1.0, dB, dS))
+
+
+def projection_points_all(X: np.ndarray, border: np.ndarray, part_start=()):
+    """distance(border, point) and nearestPoints(border, point)[1] for every unit (src/border_projection.jl:8-19).
+    X: 2 x n; border: nv x 2 vertices of a LineString, or of a MultiLineString whose lines start at the vertex
+    indices in part_start.  GEOS DistanceOp scans the segments of every line in order and keeps the FIRST minimum
+    (strict <); the closest point is LineSegment::closestPoint on that segment [recalled].
+    Returns (Xproj 2 x n, dist n)."""
+    X = np.asarray(X, dtype=np.float64)
+    V = np.asarray(border, dtype=np.float64)
+    n, nv = X.shape[1], V.shape[0]
+    brk = np.zeros(nv, dtype=bool)
+    brk[list(part_start)] = True
+    px, py = X[0], X[1]
+    best = np.full(n, np.inf)
+    bseg = np.zeros(n, dtype=np.int64)
+    for s in range(nv - 1):
+        if brk[s + 1]:
+            continue
+        d = _geos_point_to_segment(px, py, V[s, 0], V[s, 1], V[s + 1, 0], V[s + 1, 1])
+        upd = d < best
+        best = np.where(upd, d, best)
+        bseg = np.where(upd, s, bseg)
+    A, B = V[bseg], V[bseg + 1]
+    ex, ey = B[:, 0] - A[:, 0], B[:, 1] - A[:, 1]
+    len2 = ex * ex + ey * ey
+    with np.errstate(invalid="ignore", divide="ignore"):
+        r = ((px - A[:, 0]) * ex + (py - A[:, 1]) * ey) / len2
+    r = np.where((px == A[:, 0]) & (py == A[:, 1]), 0.0, np.where((px == B[:, 0]) & (py == B[:, 1]), 1.0, r))
+    inside = (r > 0.0) & (r < 1.0)
+    qx = A[:, 0] + r * ex
+    qy = A[:, 1] + r * ey
+    dA = np.sqrt((px - A[:, 0]) ** 2 + (py - A[:, 1]) ** 2)
+    dB = np.sqrt((px - B[:, 0]) ** 2 + (py - B[:, 1]) ** 2)
+    ex_ = np.where(dA < dB, A[:, 0], B[:, 0])
+    ey_ = np.where(dA < dB, A[:, 1], B[:, 1])
+    Xp = np.vstack([np.where(inside, qx, ex_), np.where(inside, qy, ey_)])
+    return np.asfortranarray(Xp), best
+
+
+def projection_points(X: np.ndarray, border: np.ndarray, maxdist: float, part_start=()) -> np.ndarray:
+    """projection_points(gp, border, maxdist) (src/border_projection.jl:4-22): X_proj[:, distances .<= maxdist]."""
+    Xp, d = projection_points_all(X, border, part_start)
+    return np.asfortranarray(Xp[:, d <= maxdist])
+
+
+def proj_estimator(gpT, gpC, border: np.ndarray, maxdist: float, part_start=()):
+    """proj_estimator (src/border_projection.jl:24-31): cliff face at the projected units, unweighted mean.
+    Returns (mean, variance) of the Normal."""
+    Xb = np.hstack([projection_points(gpT.x, border, maxdist, part_start), projection_points(gpC.x, border, maxdist, part_start)])
+    mu, Sig = cliff_face(gpT, gpC, np.asfortranarray(Xb))
+    return unweighted_mean(mu, Sig)

@@ -464,6 +464,49 @@ def test_many_rhs_triangular_ops_every_column(G, O, ctx, n, nrhs):
             assert int((err > 1e-10).sum()) == 0, (mode, rep, float(err.max()))
 
 
+@pytest.mark.parametrize("n,nv", [(1, 2), (257, 3), (3000, 1025), (5000, 2600)])
+def test_projection_points_bit_exact(G, O, ctx, n, nv):
+    """K7: nearest border point and distance for every unit == the GEOS restatement of the oracle BIT FOR BIT (each
+    operation separately rounded), so the set of units within maxdist is identical; tiles of 1024 vertices, a
+    MultiLineString break, repeated vertices, units on the border."""
+    rng = np.random.default_rng(n + nv)
+    th = np.linspace(0.0, np.pi / 2, nv)
+    border = np.column_stack([0.7 * np.cos(th), 0.7 * np.sin(th)]) + 1e-3 * rng.standard_normal((nv, 2))
+    part_start = ()
+    if nv >= 1025:
+        border[500] = border[499]                   # zero-length segment
+        part_start = (700, 1024)                    # lines start inside a tile and exactly at a tile boundary
+    X = rng.random((2, n)) * 1.1
+    X[:, 0] = border[0]
+    Xp, d = G.projection_points_all(X, border, part_start, ctx=ctx)
+    Xo, do = O.projection_points_all(X, border, part_start)
+    assert np.array_equal(d, do) and np.array_equal(Xp, Xo)
+    for maxdist in (0.05, 0.3):
+        assert np.array_equal(G.projection_points(X, border, maxdist, part_start, ctx=ctx), O.projection_points(X, border, maxdist, part_start))
+
+
+def test_proj_estimator_and_weights_proj(G, O, ctx):
+    """proj_estimator (src/border_projection.jl:24-31, used by test/test_simulated.jl:58) and weights_proj /
+    weights_rho (src/weight_at_units.jl:44-53,80-86) against the oracle; the estimator equals sum(w_units * y)."""
+    d, (oT, oC), (gT, gC) = _pair(G, O, m=300, nb=40, kind=0)
+    th = np.linspace(0.0, np.pi / 2, 1000)
+    r = np.hypot(d["Xb"][0, 0], d["Xb"][1, 0])
+    border = np.column_stack([r * np.cos(th), r * np.sin(th)])
+    maxdist = 0.15
+    est = G.proj_estimator(gT, gC, border, maxdist)
+    ref = O.proj_estimator(oT, oC, border, maxdist)
+    assert abs(est.mu - ref.mu) < 1e-9 * max(1.0, abs(ref.mu)) and abs(est.sigma - ref.sigma) < 1e-9 * ref.sigma
+    Xb, wb, wu = G.weights_proj(gT, gC, border, maxdist)
+    assert Xb.shape[1] == wb.shape[0] > 10 and wu.shape[0] == gT.nobs + gC.nobs
+    y = np.concatenate([gT.y, gC.y])
+    assert abs(float(wu @ y) - est.mu) < 1e-8 * max(1.0, abs(est.mu))     # MeanZero: the estimator is linear in y
+    Xs = G.sentinels(border, 25)
+    assert np.allclose(Xs, O.polyline_sentinels(border, 25), rtol=0, atol=1e-14)
+    Xr, wr, wur = G.weights_rho(gT, gC, lambda a, b: 1.0 + a, 25, border)
+    wo = np.concatenate([O.weight_at_units(oT, Xs, wr), -O.weight_at_units(oC, Xs, wr)])
+    assert relerr(wur, wo) < 1e-8
+
+
 def test_mll_forward_only_mode_matches_stepwise(G, O, ctx):
     """Opt-in |L^-1 (y-m)|^2 / z'z evaluation of the mll quadratic forms == the stepwise reference evaluation to
     rounding, same exceedance count, also with non-zero means and unequal region sizes."""

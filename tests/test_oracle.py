@@ -243,3 +243,36 @@ def test_mississippi_size_table(O, golden):
     assert abs(size[0] - 0.05) < se and abs(size[1] - 0.05) < se and abs(size[3] - 0.05) < se
     assert abs(size[4] - 0.05) < se                      # corrected analytic calibration
     assert 0.06 < size[2] < 0.13                         # published 0.09
+
+
+def test_projection_points_is_the_nearest_point_on_the_polyline(O):
+    """Pins the GEOS restatement by brute force: for every unit the returned point lies on the polyline, its distance
+    equals the reported one, and no densely sampled point of the polyline is closer; ties keep the first segment;
+    degenerate (zero-length) segments and a MultiLineString break are handled."""
+    rng = np.random.default_rng(5)
+    th = np.linspace(0.0, np.pi / 2, 41)
+    border = np.column_stack([0.7 * np.cos(th), 0.7 * np.sin(th)])
+    border = np.vstack([border[:20], border[19:20], border[20:], [[2.0, 2.0], [2.5, 2.0]]])   # repeated vertex + 2nd line
+    part_start = (border.shape[0] - 2,)
+    X = rng.random((2, 400)) * 1.2
+    X[:, 0] = border[5]                        # a unit exactly on a vertex
+    X[:, 1] = 0.5 * (border[7] + border[8])    # a unit on a segment
+    Xp, d = O.projection_points_all(X, border, part_start)
+    assert np.allclose(np.hypot(X[0] - Xp[0], X[1] - Xp[1]), d, rtol=1e-12, atol=1e-15)
+    assert d[0] == 0.0 and d[1] < 1e-16
+    # dense sampling of every real segment
+    t = np.linspace(0.0, 1.0, 2001)[:, None]
+    best = np.full(X.shape[1], np.inf)
+    for s_ in range(border.shape[0] - 1):
+        if s_ + 1 in part_start:
+            continue
+        pts = border[s_] + t * (border[s_ + 1] - border[s_])
+        dd = np.sqrt((X[0][None, :] - pts[:, :1]) ** 2 + (X[1][None, :] - pts[:, 1:]) ** 2).min(axis=0)
+        best = np.minimum(best, dd)
+    assert np.all(d <= best + 1e-12) and np.all(best <= d + 1e-6)
+    # first minimum wins: a unit equidistant from two parallel segments projects onto the earlier one
+    two = np.array([[0.0, 0.0], [1.0, 0.0], [1.0, 2.0], [0.0, 2.0]])
+    q, dq = O.projection_points_all(np.array([[0.5], [1.0]]), two, (2,))
+    assert dq[0] == 1.0 and q[1, 0] == 0.0
+    keep = O.projection_points(X, border, 0.1, part_start)
+    assert keep.shape[1] == int((d <= 0.1).sum()) and np.array_equal(keep, Xp[:, d <= 0.1])
