@@ -1054,3 +1054,16 @@ def placebo_mll(angle: float, X, Y, kern, mean, logNoise: float, nsim: int, **kw
     """placebo_mll (src/hypotest_mll.jl:47-60)."""
     _, gl, gr = _placebo_split(angle, X, Y, kern, mean, logNoise)
     return boot_mlltest(gl, gr, nsim, **kw)
+
+
+def placebo_sweep(which: str, angles, X, Y, kern, mean, logNoise: float, nsim: int = 0, **kw) -> np.ndarray:
+    """The placebo sweep of the notebooks (`[placebo_chi(angle, ...) for angle in 1:2:180]`,
+    notebooks/NYC_analysis-2015.ipynb:1452-1555): one p-value per angle.  Under torch.distributed the angles are dealt
+    to the ranks (one independent fit + test per GPU at a time, parallel.map_sharded); single process: a loop."""
+    from . import parallel
+    fns = {"chi": lambda a: placebo_chi(a, X, Y, kern, mean, logNoise, nsim, **kw),
+           "mll": lambda a: placebo_mll(a, X, Y, kern, mean, logNoise, nsim, **kw),
+           "invvar": lambda a: placebo_invvar(a, X, Y, kern, mean, logNoise)}
+    if which not in fns:
+        raise ValueError("which must be 'chi', 'mll' or 'invvar'")
+    return parallel.map_sharded(fns[which], list(angles))

@@ -43,3 +43,19 @@ def gather_stats(local, nsim: int, device=None):
     out = [torch.zeros(mx, dtype=torch.float64, device=device) for _ in range(world)]
     dist.all_gather(out, buf)
     return np.concatenate([o[:s].cpu().numpy() for o, s in zip(out, sizes)])
+
+
+def map_sharded(fn, items, device=None):
+    """The second, coarser parallel axis of SURVEY §8e: independent problems (placebo angles, adjacent region pairs --
+    notebooks/NYC_analysis-2015.ipynb:1452-1555, src/regiondata.jl:64-68) are dealt contiguously to the ranks, each
+    rank evaluates `fn(item)` (a float) for its share on its own GPU with no data-path collective, and the results
+    are assembled with one all-gather.  Single process: plain map."""
+    import numpy as np
+    import torch.distributed as dist
+    items = list(items)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return np.array([float(fn(it)) for it in items])
+    rank, world = dist.get_rank(), dist.get_world_size()
+    lo, cnt = shard_draws(len(items), rank, world)
+    local = np.array([float(fn(it)) for it in items[lo:lo + cnt]])
+    return gather_stats(local, len(items), device=device)

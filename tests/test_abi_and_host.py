@@ -101,6 +101,7 @@ def test_shard_draws_partition(G):
 _WORKER = r"""
 import os, sys
 sys.path.insert(0, {root!r})
+import math
 import numpy as np, torch.distributed as dist
 import georddb200
 G = georddb200.load()
@@ -114,6 +115,10 @@ tally = G.parallel.allreduce_tallies([int((local > 1.0).sum()), int((local < -2.
 full = G.parallel.gather_stats(local, nsim)
 assert tally == [int((stats > 1.0).sum()), int((stats < -2.0).sum())], tally
 assert np.array_equal(full, stats)
+angles = list(range(1, 180, 7))                          # the coarse axis: independent problems dealt to the ranks
+calls = []
+res = G.parallel.map_sharded(lambda a: (calls.append(a), math.cos(a * 0.1))[1], angles)
+assert np.array_equal(res, np.cos(np.array(angles) * 0.1)) and len(calls) in (len(angles) // 2, len(angles) - len(angles) // 2)
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """

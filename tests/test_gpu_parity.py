@@ -414,6 +414,19 @@ def test_placebo_drivers_run(G, O, ctx):
 # ---------------------------------------------------------------------------------------------
 # Full-size (BASELINE configs) size-independent properties
 # ---------------------------------------------------------------------------------------------
+def test_placebo_sweep_single_process(G, O, ctx):
+    """placebo_sweep == the per-angle drivers (single process: plain loop; the rank-sharded path is covered by the
+    gloo test)."""
+    d = O.synth_two_region(60, 8, seed=4)
+    k = G.SEIso(math.log(0.3), 0.0) + G.Const(math.log(20.0))
+    X, Y = d["X"][:, :110], d["Y"][:110]
+    angles = [10.0, 55.0, 120.0]
+    ps = G.placebo_sweep("invvar", angles, X, Y, k, G.MeanZero(), math.log(0.3))
+    assert np.array_equal(ps, np.array([G.placebo_invvar(a, X, Y, k, G.MeanZero(), math.log(0.3)) for a in angles]))
+    pc = G.placebo_sweep("chi", angles[:2], X, Y, k, G.MeanZero(), math.log(0.3), 200, seed=3)
+    assert np.all((pc >= 0.0) & (pc <= 1.0))
+
+
 def test_full_size_identities_c4(G, O, ctx):
     """C4 shape (4 000 units/side, Matern-3/2 + Const, 100 sentinels): y = L_N z  =>  (y-m)' K_N^-1 (y-m) = z'z,
     i.e. mll_null = -z'z/2 - logdet/2 - n log(2 pi)/2 to 1e-8 for device draws; shard invariance at size."""
