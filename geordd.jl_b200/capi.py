@@ -70,6 +70,8 @@ _SIGS = {
     "geordd_weight_at_units": (C.c_int, [C.c_void_p, c_double_p, C.c_int, c_double_p, c_double_p]),
     "geordd_projection_points": (C.c_int, [C.c_void_p, c_double_p, C.c_int, c_double_p, C.c_int, C.POINTER(C.c_int), C.c_int,
                                            c_double_p, c_double_p]),
+    "geordd_points_in_region": (C.c_int, [C.c_void_p, c_double_p, C.c_int, c_double_p, C.c_int, C.POINTER(C.c_int), C.c_int,
+                                          C.POINTER(C.c_ubyte)]),
     "geordd_chistat_obs": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, C.c_int, c_double_p]),
     "geordd_invvar_obs": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, C.c_int, C.c_double, c_double_p, c_double_p,
                                     c_double_p]),

@@ -489,6 +489,41 @@ int geordd_projection_points(geordd_ctx* c, const double* X, int n, const double
     API_END
 }
 
+int geordd_points_in_region(geordd_ctx* c, const double* P, int n, const double* R, int nr, const int* ring_start, int nrings,
+                            unsigned char* inside) {
+    API_BEGIN(c)
+    if (!P || !R || !inside || n <= 0 || nr < 4 || nrings < 0 || (nrings > 0 && !ring_start))
+        throw ApiError(GEORDD_ERR_ARG, "points_in_region: bad arguments");
+    std::vector<unsigned char> brk((size_t)nr, 0);
+    brk[0] = 1;
+    for (int k = 0; k < nrings; ++k) {
+        if (ring_start[k] < 0 || ring_start[k] >= nr) throw ApiError(GEORDD_ERR_ARG, "points_in_region: ring_start out of range");
+        brk[ring_start[k]] = 1;
+    }
+    double *dP = nullptr, *dR = nullptr, *dB = nullptr, *dO = nullptr;
+    try {
+        dP = dalloc((size_t)2 * n, c__->stream, false);
+        dR = dalloc((size_t)2 * nr, c__->stream, false);
+        dB = dalloc((size_t)(nr + 7) / 8 + 1, c__->stream, false);
+        dO = dalloc((size_t)(n + 7) / 8 + 1, c__->stream, false);
+        GD_CUDA(cudaMemcpyAsync(dP, P, (size_t)2 * n * sizeof(double), cudaMemcpyHostToDevice, c__->stream));
+        GD_CUDA(cudaMemcpyAsync(dR, R, (size_t)2 * nr * sizeof(double), cudaMemcpyHostToDevice, c__->stream));
+        GD_CUDA(cudaMemcpyAsync(dB, brk.data(), (size_t)nr, cudaMemcpyHostToDevice, c__->stream));
+        {
+            ProfScope ps(c__, PC_MISC);
+            launch_in_region(c__->stream, dP, n, dR, reinterpret_cast<const unsigned char*>(dB), nr, reinterpret_cast<unsigned char*>(dO));
+        }
+        GD_CUDA(cudaMemcpyAsync(inside, dO, (size_t)n, cudaMemcpyDeviceToHost, c__->stream));
+        GD_CUDA(cudaStreamSynchronize(c__->stream));
+        GD_CUDA(cudaGetLastError());
+    } catch (...) {
+        dfree(dP); dfree(dR); dfree(dB); dfree(dO);
+        throw;
+    }
+    dfree(dP); dfree(dR); dfree(dB); dfree(dO);
+    API_END
+}
+
 int geordd_chistat_obs(geordd_gp* T, geordd_gp* C, const double* Xb, int nb, double* chi2) {
     if (!T) return GEORDD_ERR_ARG;
     API_BEGIN(T->ctx)

@@ -85,6 +85,62 @@ __global__ void __launch_bounds__(256) projection_kernel(const double2* __restri
     dist[i] = best;
 }
 
+// Point-in-region for the grid of infinite_proj_sentinels (LibGEOS.within(p, region), src/border_projection.jl:70):
+// GEOS RayCrossingCounter restated per ring segment (p1, p2) for the test point q --
+//   both ends strictly left of q: skip;  q == p2: on boundary;  horizontal segment at q.y: on boundary if q.x within it;
+//   ((p1.y > q.y && p2.y <= q.y) || (p2.y > q.y && p1.y <= q.y)): orientation sign of (p1, p2, q), flipped if p2.y < p1.y,
+//   0 -> on boundary, left turn -> one crossing
+// -- with the orientation determinant in plain (separately rounded) FP64 instead of GEOS's double-double; the two differ
+// only for points within rounding of an edge.  Crossing parities are XOR-ed over ALL rings (shells and holes of every
+// polygon: even-odd rule == interior of a valid MultiPolygon); boundary points are not within.
+__global__ void __launch_bounds__(256) in_region_kernel(const double2* __restrict__ P, int n, const double2* __restrict__ R,
+                                                        const unsigned char* __restrict__ brk, int nr, unsigned char* __restrict__ inside) {
+    __shared__ double2 sv[GEOM_TILE + 1];
+    __shared__ unsigned char sb[GEOM_TILE + 1];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n;
+    const double2 q = live ? P[i] : make_double2(0.0, 0.0);
+    int crossings = 0;
+    bool on_boundary = false;
+    for (int v0 = 0; v0 < nr - 1; v0 += GEOM_TILE) {
+        const int cnt = min(GEOM_TILE + 1, nr - v0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
+            sv[t] = R[v0 + t];
+            sb[t] = brk[v0 + t];
+        }
+        __syncthreads();
+        if (live) {
+            for (int s = 0; s + 1 < cnt; ++s) {
+                if (sb[s + 1]) continue;   // vertex s+1 starts a new ring
+                const double2 p1 = sv[s], p2 = sv[s + 1];
+                if (p1.x < q.x && p2.x < q.x) continue;
+                if (q.x == p2.x && q.y == p2.y) { on_boundary = true; continue; }
+                if (p1.y == q.y && p2.y == q.y) {
+                    const double minx = fmin(p1.x, p2.x), maxx = fmax(p1.x, p2.x);
+                    if (q.x >= minx && q.x <= maxx) on_boundary = true;
+                    continue;
+                }
+                if ((p1.y > q.y && p2.y <= q.y) || (p2.y > q.y && p1.y <= q.y)) {
+                    const double det = __dsub_rn(__dmul_rn(__dsub_rn(p2.x, p1.x), __dsub_rn(q.y, p1.y)),
+                                                 __dmul_rn(__dsub_rn(p2.y, p1.y), __dsub_rn(q.x, p1.x)));
+                    int sign = det > 0.0 ? 1 : (det < 0.0 ? -1 : 0);
+                    if (sign == 0) { on_boundary = true; continue; }
+                    if (p2.y < p1.y) sign = -sign;
+                    if (sign == 1) ++crossings;
+                }
+            }
+        }
+    }
+    if (live) inside[i] = (!on_boundary && (crossings & 1)) ? 1 : 0;
+}
+
+void launch_in_region(cudaStream_t st, const double* P, int n, const double* R, const unsigned char* brk, int nr,
+                      unsigned char* inside) {
+    in_region_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const double2*>(P), n, reinterpret_cast<const double2*>(R), brk, nr,
+                                                    inside); ++g_kernel_launches;
+}
+
 void launch_projection(cudaStream_t st, const double* X, int n, const double* V, const unsigned char* brk, int nv,
                        double* Xproj, double* dist) {
     projection_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const double2*>(X), n, reinterpret_cast<const double2*>(V), brk,

@@ -159,5 +159,8 @@ void launch_zb_unpack(cudaStream_t st, const double* Zb, int npad, double* dense
 // new line (no segment (v-1, v)).  Outputs: Xproj 2 x n, dist n.
 void launch_projection(cudaStream_t st, const double* X, int n, const double* V, const unsigned char* brk, int nv,
                        double* Xproj, double* dist);
+// inside[i] = 1 if point i lies strictly inside the region given by its rings (R: 2 x nr closed rings, brk marks ring starts)
+void launch_in_region(cudaStream_t st, const double* P, int n, const double* R, const unsigned char* brk, int nr,
+                      unsigned char* inside);
 
 }  // namespace geordd

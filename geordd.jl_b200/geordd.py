@@ -528,6 +528,70 @@ def weights_rho(gpT: GPE, gpC: GPE, density, nb: int, border):
     return Xb, wb, np.concatenate([weight_at_units(gpT, Xb, wb), -weight_at_units(gpC, Xb, wb)])
 
 
+def points_in_region(P, rings, ring_start=(), ctx: Optional[Context] = None) -> np.ndarray:
+    """LibGEOS.within(point, region) for the columns of P (2 x n) on the device.  rings: nr x 2 vertices of all closed
+    rings (shells and holes) of the (Multi)Polygon; ring_start: vertex indices at which further rings start."""
+    ctx = ctx or default_context()
+    Pm = fmat(P)
+    R = np.asarray(rings, dtype=np.float64)
+    if R.ndim != 2 or R.shape[1] != 2:
+        raise ValueError("rings must be an nr x 2 array of vertices")
+    Rt = fmat(R.T)
+    rs = np.ascontiguousarray(ring_start, dtype=np.int32)
+    out = np.empty(Pm.shape[1], dtype=np.uint8)
+    ctx.check(ctx.lib.geordd_points_in_region(ctx._h, dptr(Pm), Pm.shape[1], dptr(Rt), R.shape[0],
+                                              rs.ctypes.data_as(C.POINTER(C.c_int)) if rs.size else None, int(rs.size),
+                                              out.ctypes.data_as(C.POINTER(C.c_ubyte))))
+    return out.astype(bool)
+
+
+def infinite_proj_sentinels(gpT: GPE, gpC: GPE, border, region_rings, maxdist: float, gridspace: float, density=None,
+                            part_start=(), ring_start=()):
+    """infinite_proj_sentinels (src/border_projection.jl:44-102): grid over the region's envelope, filtered by distance
+    to the border and within(region) and projected onto the border ON THE DEVICE (the reference spends 5-28 s per call
+    in LibGEOS here); the per-point density and the accumulation of weights on coinciding projections stay on the
+    host.  Returns (X_projected 2 x k, weights k)."""
+    ctx = gpT.ctx
+    R = np.asarray(region_rings, dtype=np.float64)
+    x1 = R[:, 0].min() + gridspace * np.arange(int(math.floor((R[:, 0].max() - R[:, 0].min()) / gridspace)) + 1)
+    x2 = R[:, 1].min() + gridspace * np.arange(int(math.floor((R[:, 1].max() - R[:, 1].min()) / gridspace)) + 1)
+    S1, S2 = np.meshgrid(x1, x2, indexing="ij")
+    P = fmat(np.vstack([S1.ravel(order="F"), S2.ravel(order="F")]))       # s1 fastest, as Iterators.product
+    Xp, d = projection_points_all(P, border, part_start, ctx=ctx)
+    keep = (d <= maxdist) & points_in_region(P, R, ring_start, ctx=ctx)
+    Pk, Xk = P[:, keep], Xp[:, keep]
+    rho = np.ones(Pk.shape[1]) if density is None else np.array([float(density(a, b)) for a, b in zip(Pk[0], Pk[1])])
+    # weights of coinciding projections: first-appearance order, sequential accumulation in grid order
+    uniq, first, inv = np.unique(Xk.T, axis=0, return_index=True, return_inverse=True)
+    rank = np.empty(len(first), dtype=np.int64)
+    rank[np.argsort(first, kind="stable")] = np.arange(len(first))
+    w = np.zeros(len(first))
+    np.add.at(w, rank[np.ravel(inv)], rho)
+    Xb = np.empty((2, len(first)), order="F")
+    Xb[:, rank] = uniq.T
+    return Xb, w
+
+
+def infinite_proj_estim(gpT: GPE, gpC: GPE, border, region_rings, maxdist: float, gridspace: float, density=None,
+                        part_start=(), ring_start=()) -> Normal:
+    """infinite_proj_estim (src/border_projection.jl:104-116)."""
+    Xb, w = infinite_proj_sentinels(gpT, gpC, border, region_rings, maxdist, gridspace, density, part_start, ring_start)
+    mu, S = cliff_face(gpT, gpC, Xb)
+    return weighted_mean(mu, S, w)
+
+
+def weights_geo(gpT: GPE, gpC: GPE, border, region_rings, maxdist: float, gridspace: float, **kw):
+    """weights_geo (src/weight_at_units.jl:58-64)."""
+    Xb, wb = infinite_proj_sentinels(gpT, gpC, border, region_rings, maxdist, gridspace, None, **kw)
+    return Xb, wb, np.concatenate([weight_at_units(gpT, Xb, wb), -weight_at_units(gpC, Xb, wb)])
+
+
+def weights_pop(gpT: GPE, gpC: GPE, density, border, region_rings, maxdist: float, gridspace: float, **kw):
+    """weights_pop (src/weight_at_units.jl:69-75)."""
+    Xb, wb = infinite_proj_sentinels(gpT, gpC, border, region_rings, maxdist, gridspace, density, **kw)
+    return Xb, wb, np.concatenate([weight_at_units(gpT, Xb, wb), -weight_at_units(gpC, Xb, wb)])
+
+
 # ----------------------------------------------------------------------------------------------
 # Null handle: make_null + draw-independent setup, and the Monte-Carlo tests
 # ----------------------------------------------------------------------------------------------

@@ -121,6 +121,12 @@ GEORDD_API int geordd_solve_general(geordd_ctx* ctx, const double* A, int n, dou
  * columns with dist <= maxdist.  GEOS 3.8 arithmetic restated operation by operation (first minimum wins). */
 GEORDD_API int geordd_projection_points(geordd_ctx* ctx, const double* X, int n, const double* V, int nv, const int* part_start,
                                         int nparts, double* Xproj, double* dist);
+/* LibGEOS.within(point, region) for n points (the grid filter of infinite_proj_sentinels, src/border_projection.jl:44-102;
+ * the reference notes it is "stupidly slow").  R: 2 x nr vertices of all rings of the (Multi)Polygon, each ring closed
+ * (first vertex repeated); ring_start[nrings]: vertex indices at which further rings start.  inside[i] = 1 / 0.
+ * GEOS RayCrossingCounter restated with the orientation test in plain FP64; even-odd over all rings. */
+GEORDD_API int geordd_points_in_region(geordd_ctx* ctx, const double* P, int n, const double* R, int nr, const int* ring_start,
+                                       int nrings, unsigned char* inside);
 
 /* weight_at_units(gp, sentinels, weights) (src/weight_at_units.jl:12-18): w_unit (n). */
 GEORDD_API int geordd_weight_at_units(geordd_gp* gp, const double* Xb, int nb, const double* w_border, double* w_unit);

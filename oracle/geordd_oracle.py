@@ -879,3 +879,73 @@ def proj_estimator(gpT, gpC, border: np.ndarray, maxdist: float, part_start=()):
     Xb = np.hstack([projection_points(gpT.x, border, maxdist, part_start), projection_points(gpC.x, border, maxdist, part_start)])
     mu, Sig = cliff_face(gpT, gpC, np.asfortranarray(Xb))
     return unweighted_mean(mu, Sig)
+
+
+def points_in_region(P: np.ndarray, rings: np.ndarray, ring_start=()) -> np.ndarray:
+    """LibGEOS.within(point, region) for the columns of P (2 x n).  rings: nr x 2 vertices of all (closed) rings of
+    the (Multi)Polygon -- shells and holes; ring_start: vertex indices at which further rings start.  GEOS
+    RayCrossingCounter restated [recalled: GEOS 3.8 algorithm/RayCrossingCounter.cpp] with the orientation
+    determinant in plain FP64; crossing parities combined over all rings (even-odd), boundary points excluded."""
+    P = np.asarray(P, dtype=np.float64)
+    R = np.asarray(rings, dtype=np.float64)
+    nr = R.shape[0]
+    brk = np.zeros(nr, dtype=bool)
+    brk[list(ring_start)] = True
+    qx, qy = P[0], P[1]
+    crossings = np.zeros(P.shape[1], dtype=np.int64)
+    on_b = np.zeros(P.shape[1], dtype=bool)
+    for s in range(nr - 1):
+        if brk[s + 1]:
+            continue
+        p1x, p1y, p2x, p2y = R[s, 0], R[s, 1], R[s + 1, 0], R[s + 1, 1]
+        active = ~((p1x < qx) & (p2x < qx))
+        at_v = active & (qx == p2x) & (qy == p2y)
+        on_b |= at_v
+        active &= ~at_v
+        horiz = active & (p1y == qy) & (p2y == qy)
+        on_b |= horiz & (qx >= min(p1x, p2x)) & (qx <= max(p1x, p2x))
+        active &= ~horiz
+        cross = active & (((p1y > qy) & (p2y <= qy)) | ((p2y > qy) & (p1y <= qy)))
+        det = (p2x - p1x) * (qy - p1y) - (p2y - p1y) * (qx - p1x)
+        sign = np.sign(det).astype(np.int64)
+        on_b |= cross & (sign == 0)
+        if p2y < p1y:
+            sign = -sign
+        crossings += (cross & (sign == 1)).astype(np.int64)
+    return (~on_b) & (crossings % 2 == 1)
+
+
+def infinite_proj_sentinels(border: np.ndarray, rings: np.ndarray, maxdist: float, gridspace: float, density=None,
+                            part_start=(), ring_start=()):
+    """infinite_proj_sentinels (src/border_projection.jl:44-102): grid over the envelope of the region; keep the grid
+    points within maxdist of the border and within the region; project them onto the border; the weight of a
+    projected point is the summed density of the grid points that land on it (exact coordinate match, accumulated in
+    grid order, s1 fastest).  Returns (X_projected 2 x k in first-appearance order, weights k).  The envelope pre-filter
+    (:66) cannot change the result and is omitted; grid coordinates are min + k*step in plain FP64 (Julia's ranges use
+    twice-precision stepping: last-bit differences possible)."""
+    R = np.asarray(rings, dtype=np.float64)
+    x1 = R[:, 0].min() + gridspace * np.arange(int(math.floor((R[:, 0].max() - R[:, 0].min()) / gridspace)) + 1)
+    x2 = R[:, 1].min() + gridspace * np.arange(int(math.floor((R[:, 1].max() - R[:, 1].min()) / gridspace)) + 1)
+    S1, S2 = np.meshgrid(x1, x2, indexing="ij")
+    P = np.vstack([S1.ravel(order="F"), S2.ravel(order="F")])            # s1 fastest, as Iterators.product
+    Xp, d = projection_points_all(P, border, part_start)
+    keep = (d <= maxdist) & points_in_region(P, R, ring_start)
+    Pk, Xk = P[:, keep], Xp[:, keep]
+    rho = np.ones(Pk.shape[1]) if density is None else np.array([float(density(a, b)) for a, b in zip(Pk[0], Pk[1])])
+    keys, order, w = {}, [], []
+    for j in range(Xk.shape[1]):
+        k = (Xk[0, j], Xk[1, j])
+        if k in keys:
+            w[keys[k]] += rho[j]
+        else:
+            keys[k] = len(order)
+            order.append(k)
+            w.append(rho[j])
+    return np.asfortranarray(np.array(order).T.reshape(2, -1)), np.array(w)
+
+
+def infinite_proj_estim(gpT, gpC, border, rings, maxdist, gridspace, density=None, part_start=(), ring_start=()):
+    """infinite_proj_estim (src/border_projection.jl:104-116)."""
+    Xb, w = infinite_proj_sentinels(border, rings, maxdist, gridspace, density, part_start, ring_start)
+    mu, Sig = cliff_face(gpT, gpC, Xb)
+    return weighted_mean(mu, Sig, w)

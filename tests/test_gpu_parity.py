@@ -520,6 +520,39 @@ def test_proj_estimator_and_weights_proj(G, O, ctx):
     assert relerr(wur, wo) < 1e-8
 
 
+def test_points_in_region_and_infinite_proj(G, O, ctx):
+    """Device within(point, region) == the oracle's ray-crossing restatement bit for bit (holes, several polygons,
+    ring starts inside and at tile boundaries), and infinite_proj_sentinels / infinite_proj_estim / weights_geo match."""
+    rng = np.random.default_rng(3)
+    th = np.linspace(0.0, 2 * np.pi, 1301)
+    shell = np.column_stack([1.0 + 0.9 * np.cos(th), 1.0 + 0.9 * np.sin(th) * (1 + 0.2 * np.sin(5 * th))]); shell[-1] = shell[0]
+    th2 = np.linspace(0.0, 2 * np.pi, 200)
+    hole = np.column_stack([1.0 + 0.2 * np.cos(-th2), 1.2 + 0.2 * np.sin(-th2)]); hole[-1] = hole[0]
+    tri = np.array([[2.5, 0.0], [3.5, 0.0], [3.0, 1.0], [2.5, 0.0]])
+    rings = np.vstack([shell, hole, tri])
+    starts = (len(shell), len(shell) + len(hole))
+    P = rng.random((2, 20000)) * np.array([[4.0], [2.5]]) - 0.2
+    P[:, 0] = shell[10]                                   # on a vertex: boundary, not within
+    got = G.points_in_region(P, rings, starts, ctx=ctx)
+    want = O.points_in_region(P, rings, starts)
+    assert np.array_equal(got, want) and 0.2 < got.mean() < 0.6 and not got[0]
+    d, (oT, oC), (gT, gC) = _pair(G, O, m=200, nb=20, kind=0)
+    r = np.hypot(d["Xb"][0, 0], d["Xb"][1, 0])
+    tb = np.linspace(0.0, np.pi / 2, 400)
+    border = np.column_stack([r * np.cos(tb), r * np.sin(tb)])
+    region = np.array([[0.0, 0.0], [1.0, 0.0], [1.0, 1.0], [0.0, 1.0], [0.0, 0.0]])
+    Xb, w = G.infinite_proj_sentinels(gT, gC, border, region, 0.1, 0.04)
+    Xo, wo = O.infinite_proj_sentinels(border, region, 0.1, 0.04)
+    assert np.array_equal(Xb, Xo) and np.array_equal(w, wo) and Xb.shape[1] > 20
+    est = G.infinite_proj_estim(gT, gC, border, region, 0.1, 0.04, density=lambda a, b: 1.0 + b)
+    ref = O.infinite_proj_estim(oT, oC, border, region, 0.1, 0.04, density=lambda a, b: 1.0 + b)
+    assert abs(est.mu - ref.mu) < 1e-9 * max(1.0, abs(ref.mu)) and abs(est.sigma - ref.sigma) < 1e-9 * ref.sigma
+    Xg, wg, wu = G.weights_geo(gT, gC, border, region, 0.1, 0.04)
+    y = np.concatenate([gT.y, gC.y])
+    eg = G.infinite_proj_estim(gT, gC, border, region, 0.1, 0.04)
+    assert abs(float(wu @ y) - eg.mu) < 1e-8 * max(1.0, abs(eg.mu))
+
+
 def test_mll_forward_only_mode_matches_stepwise(G, O, ctx):
     """Opt-in |L^-1 (y-m)|^2 / z'z evaluation of the mll quadratic forms == the stepwise reference evaluation to
     rounding, same exceedance count, also with non-zero means and unequal region sizes."""

@@ -276,3 +276,34 @@ def test_projection_points_is_the_nearest_point_on_the_polyline(O):
     assert dq[0] == 1.0 and q[1, 0] == 0.0
     keep = O.projection_points(X, border, 0.1, part_start)
     assert keep.shape[1] == int((d <= 0.1).sum()) and np.array_equal(keep, Xp[:, d <= 0.1])
+
+
+def test_points_in_region_known_answers(O):
+    """Square with a square hole plus a second (triangular) polygon: interior / hole / exterior / boundary answers
+    are known analytically (boundary points are not `within`)."""
+    shell = [[0, 0], [4, 0], [4, 4], [0, 4], [0, 0]]
+    hole = [[1, 1], [1, 3], [3, 3], [3, 1], [1, 1]]
+    tri = [[6, 0], [8, 0], [7, 2], [6, 0]]
+    rings = np.array(shell + hole + tri, dtype=float)
+    starts = (5, 10)
+    P = np.array([[0.5, 0.5], [2.0, 2.0], [3.5, 2.0], [5.0, 1.0], [7.0, 0.5], [7.0, 3.0], [0.0, 2.0], [4.0, 4.0], [2.0, 1.0],
+                  [7.0, 0.0], [-1.0, 2.0], [2.0, 0.5]]).T
+    want = np.array([True, False, True, False, True, False, False, False, False, False, False, True])
+    assert np.array_equal(O.points_in_region(P, rings, starts), want)
+    rng = np.random.default_rng(0)
+    Q = rng.random((2, 5000)) * 9.0 - 0.5
+    truth = ((Q[0] > 0) & (Q[0] < 4) & (Q[1] > 0) & (Q[1] < 4) & ~((Q[0] >= 1) & (Q[0] <= 3) & (Q[1] >= 1) & (Q[1] <= 3))) | \
+            ((Q[1] > 0) & (Q[1] < 2 * (Q[0] - 6)) & (Q[1] < 2 * (8 - Q[0])))
+    assert np.array_equal(O.points_in_region(Q, rings, starts), truth)
+
+
+def test_infinite_proj_sentinels_weights(O):
+    """Grid points of a square region within maxdist of a straight border project to distinct border points whose
+    weights count the grid columns (constant density) -- total weight == number of kept grid points."""
+    border = np.array([[0.0, 1.0], [2.0, 1.0]])
+    rings = np.array([[0, 0], [2, 0], [2, 2], [0, 2], [0, 0]], dtype=float)
+    Xb, w = O.infinite_proj_sentinels(border, rings, 0.25, 0.1)
+    assert Xb.shape[0] == 2 and np.all(Xb[1] == 1.0)
+    assert len(np.unique(Xb[0])) == Xb.shape[1] and np.all(w == w[0]) and w[0] in (5.0, 6.0)
+    Xb2, w2 = O.infinite_proj_sentinels(border, rings, 0.25, 0.1, density=lambda a, b: 2.0)
+    assert np.array_equal(Xb, Xb2) and np.allclose(w2, 2.0 * w)
