@@ -398,6 +398,13 @@ def test_simulated_end_to_end(G, O, ctx):
     mu, S = G.cliff_face(gpr[True], gpr[False], d["Xb"])
     t = G.inverse_variance(mu, S)
     assert t.quantile(0.001) < tau < t.quantile(0.999)
+    # test/test_simulated.jl:55-63: the projected estimator with maxdist = 2 ell along the quarter-circle border
+    ell = math.exp(mg.kernel.kleft.ll) if hasattr(mg.kernel, "kleft") else 0.3
+    r = math.hypot(d["Xb"][0, 0], d["Xb"][1, 0])
+    th = np.linspace(0.0, math.pi / 2, 1000)
+    border = np.column_stack([r * np.cos(th), r * np.sin(th)])
+    tp = G.proj_estimator(gpr[True], gpr[False], border, 2 * ell)
+    assert tp.quantile(0.001) < tau < tp.quantile(0.999)
     assert G.pval_invvar_calib(gpr[True], gpr[False], d["Xb"]) < 0.05
 
 
