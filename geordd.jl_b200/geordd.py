@@ -675,12 +675,32 @@ def nsim_chi(gpT: GPE, gpC: GPE, gpNull: NullGPE, Xb, nsim: int, *, seed: int = 
     return (stats, cnt.value) if return_count else stats
 
 
+def _draw_shard(nsim: int, kw: dict):
+    """Multi-GPU boot_* drivers: when the caller runs one process per GPU under torch.distributed, every
+    rank simulates its contiguous shard of the draw indices and the exceedance tallies are summed with one all-reduce;
+    draws are keyed by (seed, index), so the p-value does not depend on the number of GPUs.  Returns
+    (local nsim, kwargs with draw0 / Z adjusted, reducer)."""
+    import sys
+    dist = sys.modules.get("torch.distributed")
+    if dist is None or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return nsim, kw, (lambda cnt: cnt)
+    from . import parallel
+    lo, cnt = parallel.shard_draws(nsim, dist.get_rank(), dist.get_world_size())
+    kw = dict(kw)
+    kw["draw0"] = int(kw.get("draw0", 0)) + lo
+    if kw.get("Z") is not None:
+        kw["Z"] = np.asarray(kw["Z"])[:, lo:lo + cnt]
+    return cnt, kw, (lambda c: parallel.allreduce_tallies([c])[0])
+
+
 def boot_chi2test(gpT: GPE, gpC: GPE, Xb, nsim: int, **kw) -> float:
     """boot_chi2test(gpT, gpC, Xb, nsim) (src/hypotest_chi2.jl:54-59): mean(chi_sims .> chi_obs)."""
     gpNull = make_null(gpT, gpC)
     chi_obs = chistat(gpT, gpC, Xb)
-    sims, cnt = nsim_chi(gpT, gpC, gpNull, Xb, nsim, chi_obs=chi_obs, return_count=True, **kw)
-    return cnt / sims.shape[0]
+    total = np.asarray(kw["Z"]).shape[1] if kw.get("Z") is not None else int(nsim)
+    local, kw, reduce_ = _draw_shard(total, kw)
+    _, cnt = nsim_chi(gpT, gpC, gpNull, Xb, local, chi_obs=chi_obs, return_count=True, **kw)
+    return reduce_(cnt) / total
 
 
 def pval_invvar_uncalib(gpT: GPE, gpC: GPE, Xb, nugget: float = 1e-10) -> float:
@@ -710,8 +730,10 @@ def nsim_invvar_pval_uncalib(gpT: GPE, gpC: GPE, Xb, nsim: int, nugget: float = 
 def boot_invvar(gpT: GPE, gpC: GPE, Xb, nsim: int, nugget: float = 1e-10, **kw) -> float:
     """boot_invvar (src/hypotest_invvar.jl:65-69): mean(pval_sims .< pval_obs)."""
     pobs = pval_invvar_uncalib(gpT, gpC, Xb, nugget)
-    sims, cnt = nsim_invvar_pval_uncalib(gpT, gpC, Xb, nsim, nugget, pval_obs=pobs, return_count=True, **kw)
-    return cnt / sims.shape[0]
+    total = np.asarray(kw["Z"]).shape[1] if kw.get("Z") is not None else int(nsim)
+    local, kw, reduce_ = _draw_shard(total, kw)
+    _, cnt = nsim_invvar_pval_uncalib(gpT, gpC, Xb, local, nugget, pval_obs=pobs, return_count=True, **kw)
+    return reduce_(cnt) / total
 
 
 def pval_invvar_calib(gpT: GPE, gpC: GPE, Xb, nugget: float = 1e-10) -> float:
@@ -760,8 +782,10 @@ def boot_mlltest(gpT: GPE, gpC: GPE, nsim: int, **kw) -> float:
     mll_alt = gpT.mll + gpC.mll
     gpNull = make_null(gpT, gpC)
     d_obs = mll_alt - gpNull.mll
-    _, cnt, mnull, _ = nsim_logP(gpT, gpC, gpNull, nsim, dmll_obs=d_obs, return_count=True, **kw)
-    return cnt / mnull.shape[0]
+    total = np.asarray(kw["Z"]).shape[1] if kw.get("Z") is not None else int(nsim)
+    local, kw, reduce_ = _draw_shard(total, kw)
+    _, cnt, _, _ = nsim_logP(gpT, gpC, gpNull, local, dmll_obs=d_obs, return_count=True, **kw)
+    return reduce_(cnt) / total
 
 
 def nsim_power(gpT: GPE, gpC: GPE, tau: float, Xb, chi_null, mll_null, pval_invvar_null, nsim: int, *,

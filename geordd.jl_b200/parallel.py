@@ -18,11 +18,22 @@ def shard_draws(nsim: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, hi - lo
 
 
+def _auto_device(device):
+    """NCCL moves device tensors only: default to this rank's current CUDA device under the nccl backend."""
+    if device is not None:
+        return device
+    import torch
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return None
+
+
 def allreduce_tallies(counts: Sequence[int], device=None):
     """Sum integer tallies over all ranks (torch.distributed; backend chosen by the caller's init)."""
     import torch
     import torch.distributed as dist
-    t = torch.tensor(list(counts), dtype=torch.int64, device=device)
+    t = torch.tensor(list(counts), dtype=torch.int64, device=_auto_device(device))
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return [int(v) for v in t.cpu().tolist()]
@@ -36,10 +47,11 @@ def gather_stats(local, nsim: int, device=None):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return np.asarray(local)
     world = dist.get_world_size()
+    device = _auto_device(device)
     sizes = [shard_draws(nsim, r, world)[1] for r in range(world)]
     mx = max(sizes)
     buf = torch.zeros(mx, dtype=torch.float64, device=device)
-    buf[: len(local)] = torch.as_tensor(np.asarray(local), dtype=torch.float64)
+    buf[: len(local)] = torch.as_tensor(np.asarray(local), dtype=torch.float64).to(buf.device)
     out = [torch.zeros(mx, dtype=torch.float64, device=device) for _ in range(world)]
     dist.all_gather(out, buf)
     return np.concatenate([o[:s].cpu().numpy() for o, s in zip(out, sizes)])
