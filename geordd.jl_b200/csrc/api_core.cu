@@ -180,12 +180,15 @@ void gemm(geordd_ctx* c, bool a_mc, bool b_nc, int M, int N, int K, double alpha
     launch_gemm(c->stream, a_mc, b_nc, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, splitk, c->ws.p, b_xb);
 }
 
-int make_posdef(geordd_ctx* c, double* K, double* L, long ld, int n, int npad, int* rounds) {
+int make_posdef(geordd_ctx* c, double* K, double* L, long ld, int n, int npad, int* rounds, const double* Lpre, int npad_pre,
+                int ptiles) {
     int nr = 0;
     for (int attempt = 0; attempt <= 10; ++attempt) {
         {
             ProfScope ps(c, PC_POTRF);
-            launch_potrf(c->stream, c->sched, K, L, ld, npad);
+            // the known leading block is only valid for the un-jittered matrix (first attempt)
+            if (attempt == 0) launch_potrf(c->stream, c->sched, K, L, ld, npad, Lpre, npad_pre, ptiles);
+            else launch_potrf(c->stream, c->sched, K, L, ld, npad);
         }
         GD_CUDA(cudaMemcpyAsync(c->h_info, c->sched.abort_word, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         GD_CUDA(cudaStreamSynchronize(c->stream));
@@ -258,7 +261,7 @@ static void gp_set_resid(geordd_gp* gp, const double* y) {
 }
 
 geordd_gp* gp_create(geordd_ctx* c, const geordd_kernel* k, const double* X, int dim, int n, const double* y,
-                     double log_noise, int* info_out) {
+                     double log_noise, int* info_out, const geordd_gp* lead) {
     check_kernel(k);
     if (!X || !y || n <= 0 || dim <= 0 || dim > 8) throw ApiError(GEORDD_ERR_ARG, "gp_fit: bad X / y / n / dim (1..8)");
     geordd_gp* gp = new geordd_gp();
@@ -279,7 +282,16 @@ geordd_gp* gp_create(geordd_ctx* c, const geordd_kernel* k, const double* X, int
             launch_cov(c->stream, to_dev(*k), gp->dX, n, gp->dX, n, dim, true, false, noise, gp->dK, np, gp->npad,
                        gp->npad, false);
         }
-        int info = make_posdef(c, gp->dK, gp->dL, np, n, gp->npad, &gp->jitter_rounds);
+        // leading block already factored?  Same units, kernel and noise, and that fit needed no jitter.
+        const double* Lpre = nullptr;
+        int ptiles = 0;
+        if (lead && lead->ctx == c && lead->dim == dim && lead->n <= n && lead->jitter_rounds == 0 && lead->log_noise == log_noise &&
+            lead->k.kind == k->kind && lead->k.ell == k->ell && lead->k.sigma2 == k->sigma2 && lead->k.const_sigma2 == k->const_sigma2 &&
+            std::memcmp(lead->X.data(), X, (size_t)dim * lead->n * sizeof(double)) == 0) {
+            Lpre = lead->dL;
+            ptiles = lead->n / TILE;   // tiles entirely inside the leading block
+        }
+        int info = make_posdef(c, gp->dK, gp->dL, np, n, gp->npad, &gp->jitter_rounds, Lpre, lead ? lead->npad : 0, ptiles);
         if (info_out) *info_out = info;
         if (info != 0) {
             gp_free(gp);

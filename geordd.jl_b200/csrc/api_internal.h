@@ -159,7 +159,8 @@ void ensure_ws(geordd_ctx* c, size_t count);
 KernelSpecDev to_dev(const geordd_kernel& k);
 // make_posdef!(K) -> L (App. A.5).  K (npad x npad, lower tiles valid, logical size n) is jittered in
 // place.  Returns 0 or the LAPACK info after the 11th failed attempt.
-int make_posdef(geordd_ctx* c, double* K, double* L, long ld, int n, int npad, int* rounds);
+int make_posdef(geordd_ctx* c, double* K, double* L, long ld, int n, int npad, int* rounds, const double* Lpre = nullptr,
+                int npad_pre = 0, int ptiles = 0);
 // B <- L^-T L^-1 B (ncols multiple of 64) with optional fused epilogue on the backward pass.
 void pd_solve(geordd_ctx* c, const double* L, int npad, double* B, long ldb, int ncols, const SolveEpilogue& epi_bwd,
               int live_cols = 0);
@@ -167,8 +168,10 @@ void gemm(geordd_ctx* c, bool a_mc, bool b_nc, int M, int N, int K, double alpha
           const double* B, long ldb, double beta, double* C, long ldc, int splitk, bool b_xb = false);
 int pick_splitk(geordd_ctx* c, int M, int N, int K);
 
+// `lead` (optional): a fitted GP over the FIRST lead->n units of X with the same kernel and noise and no jitter; the tiles
+// of its factor that lie inside the leading block are reused (make_null: pooled = [treated control]).
 geordd_gp* gp_create(geordd_ctx* c, const geordd_kernel* k, const double* X, int dim, int n, const double* y,
-                     double log_noise, int* info_out);
+                     double log_noise, int* info_out, const geordd_gp* lead = nullptr);
 void gp_update_alpha(geordd_gp* gp);   // alpha from dR, mll
 void gp_free(geordd_gp* gp);
 void gp_ensure_full_K(geordd_gp* gp);

@@ -283,19 +283,21 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
             // forward and backward solves of all GPs as ONE persistent kernel (solve.cu, fused solve sequence)
             SolveEpilogue none;
             none.xb = true;
+            // order: the pooled (largest) solve first in each phase, so that the kernel's final tail comes from the
+            // shortest jobs
             SolveSeqItem it[SOLVE_SEQ_MAX];
-            int ns = 0;
-            it[ns++] = SolveSeqItem{SOLVE_FWD, T->dL, mTp, h->AT.p, none, -1};
-            it[ns++] = SolveSeqItem{SOLVE_FWD, C->dL, mCp, h->AC.p, none, -1};
-            if (rq.want_mll) it[ns++] = SolveSeqItem{SOLVE_FWD, N->dL, npN, h->AN.p, none, -1};
-            it[ns++] = SolveSeqItem{SOLVE_BWD, T->dL, mTp, h->AT.p, eT, 0};
-            it[ns++] = SolveSeqItem{SOLVE_BWD, C->dL, mCp, h->AC.p, eC, 1};
+            int ns = 0, iN = -1;
+            if (rq.want_mll) { iN = ns; it[ns++] = SolveSeqItem{SOLVE_FWD, N->dL, npN, h->AN.p, none, -1}; }
+            const int iT = ns; it[ns++] = SolveSeqItem{SOLVE_FWD, T->dL, mTp, h->AT.p, none, -1};
+            const int iC = ns; it[ns++] = SolveSeqItem{SOLVE_FWD, C->dL, mCp, h->AC.p, none, -1};
             if (rq.want_mll) {
                 SolveEpilogue eN;
                 eN.xb = true;
                 eN.wmat = h->RN.p; eN.ldw = npN; eN.dot0 = h->partN.p;
-                it[ns++] = SolveSeqItem{SOLVE_BWD, N->dL, npN, h->AN.p, eN, 2};
+                it[ns++] = SolveSeqItem{SOLVE_BWD, N->dL, npN, h->AN.p, eN, iN};
             }
+            it[ns++] = SolveSeqItem{SOLVE_BWD, T->dL, mTp, h->AT.p, eT, iT};
+            it[ns++] = SolveSeqItem{SOLVE_BWD, C->dL, mCp, h->AC.p, eC, iC};
             ProfScope ps(c, PC_SEQ);
             launch_solve_seq(st, c->sched, it, ns, ncols);
         }
@@ -788,7 +790,7 @@ int geordd_null_prepare(geordd_gp* T, geordd_gp* C, const double* Xb, int nb, do
         std::copy(C->X.begin(), C->X.end(), X.begin() + (size_t)dim * T->n);
         std::copy(T->y.begin(), T->y.end(), y.begin());
         std::copy(C->y.begin(), C->y.end(), y.begin() + T->n);
-        h->N = gp_create(c__, &T->k, X.data(), dim, n, y.data(), T->log_noise, &info);
+        h->N = gp_create(c__, &T->k, X.data(), dim, n, y.data(), T->log_noise, &info, T);
         if (!h->N) {
             null_free(h);
             c__->err = "pooled null covariance is not positive definite";

@@ -51,6 +51,7 @@ struct Sched {
     int2* jobs;          // device job table scratch
     size_t jobs_cap;
     int jobs_T = 0;      // tile count the cached potrf job table was built for
+    int jobs_P = 0;      // ... and its number of prefilled leading tiles
     int num_sms;
 };
 
@@ -73,7 +74,12 @@ void launch_cov(cudaStream_t st, const KernelSpecDev& spec, const double* X1, in
 // triangle is read.  L: TBP storage (factor_elems(npad) doubles); the strict upper triangle of the diagonal
 // tiles is zeroed, upper tiles are written only by launch_mirror_factor.
 // Result code is left in sched.abort_word (0 ok, k>0: pivot k non-positive, <0 watchdog).
-void launch_potrf(cudaStream_t st, Sched& sched, const double* A, double* L, long ld, int npad);
+// Lpre / npad_pre / ptiles (optional): the leading ptiles x ptiles tile block of the factor is already known -- it is the
+// factor Lpre (TBP, npad_pre) of the leading principal submatrix (make_null: the pooled matrix starts with the treated
+// block, whose factor the treated GP holds).  Those tiles are copied instead of recomputed; the left-looking tile jobs
+// are deterministic, so the result is bit-identical to a full factorisation.
+void launch_potrf(cudaStream_t st, Sched& sched, const double* A, double* L, long ld, int npad, const double* Lpre = nullptr,
+                  int npad_pre = 0, int ptiles = 0);
 // dense (n x n column-major, ldd) lower triangle -> TBP factor with identity padding; and back (optionally transposed).
 void launch_factor_pack(cudaStream_t st, const double* dense, long ldd, int n, double* L, int npad);
 void launch_factor_unpack(cudaStream_t st, const double* L, int npad, double* dense, long ldd, int n, bool transpose);

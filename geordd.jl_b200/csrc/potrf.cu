@@ -125,31 +125,51 @@ potrf_dataflow_kernel(const double* __restrict__ A, double* __restrict__ L, long
     }
 }
 
-static void build_potrf_jobs(int T, int2* host) {
+static int build_potrf_jobs(int T, int P, int2* host) {
     int p = 0;
     for (int j = 0; j < T; ++j)
-        for (int i = j; i < T; ++i) host[p++] = make_int2(i, j);
+        for (int i = j; i < T; ++i)
+            if (!(i < P && j < P)) host[p++] = make_int2(i, j);   // tiles of the prefilled leading block are not jobs
+    return p;
 }
 
-void launch_potrf(cudaStream_t st, Sched& sched, const double* A, double* L, long ld, int npad) {
+// One CTA per tile (i, j), j <= i < P: copy the tile image from the known factor and publish its flag.
+__global__ void __launch_bounds__(256) potrf_prefill_kernel(const double* __restrict__ Lpre, int Tpre, double* __restrict__ L, int T,
+                                                            int P, unsigned* flags, unsigned epoch) {
+    const int i = blockIdx.x % P, j = blockIdx.x / P;
+    if (i < j) return;
+    const double2* src = reinterpret_cast<const double2*>(Lpre + tile_off(i, j, Tpre));
+    double2* dst = reinterpret_cast<double2*>(L + tile_off(i, j, T));
+    for (int t = threadIdx.x; t < (int)(TSZ / 2); t += blockDim.x) dst[t] = src[t];
+    if (threadIdx.x == 0) flags[(long)i * T + j] = epoch;
+}
+
+void launch_potrf(cudaStream_t st, Sched& sched, const double* A, double* L, long ld, int npad, const double* Lpre, int npad_pre,
+                  int ptiles) {
     const int T = npad / TILE;
-    const int njobs = T * (T + 1) / 2;
+    const int P = (Lpre && ptiles > 0 && ptiles <= T && ptiles <= npad_pre / TILE) ? ptiles : 0;
+    const int njobs = T * (T + 1) / 2 - P * (P + 1) / 2;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(potrf_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM);
         attr_set = true;
     }
-    if (sched.jobs_T != T) {   // job table cached per tile count
-        int2* hjobs = (int2*)malloc(sizeof(int2) * njobs);
-        build_potrf_jobs(T, hjobs);
+    if (sched.jobs_T != T || sched.jobs_P != P) {   // job table cached per (tile count, prefilled tiles)
+        int2* hjobs = (int2*)malloc(sizeof(int2) * (njobs > 0 ? njobs : 1));
+        build_potrf_jobs(T, P, hjobs);
         cudaMemcpyAsync(sched.jobs, hjobs, sizeof(int2) * njobs, cudaMemcpyHostToDevice, st);
         cudaStreamSynchronize(st);   // hjobs is pageable: complete the copy before free
         free(hjobs);
         sched.jobs_T = T;
+        sched.jobs_P = P;
     }
     cudaMemsetAsync(sched.counter, 0, sizeof(unsigned), st);
     cudaMemsetAsync(sched.abort_word, 0, sizeof(int), st);
     sched.epoch++;
+    if (P > 0) {
+        potrf_prefill_kernel<<<P * P, 256, 0, st>>>(Lpre, npad_pre / TILE, L, T, P, sched.flags, sched.epoch); ++g_kernel_launches;
+    }
+    if (njobs == 0) return;
     int grid = njobs < sched.num_sms ? njobs : sched.num_sms;
     potrf_dataflow_kernel<<<grid, NTHREADS, POTRF_SMEM, st>>>(A, L, ld, T, sched.jobs, njobs, sched.flags, sched.epoch,
                                                               sched.counter, sched.abort_word); ++g_kernel_launches;

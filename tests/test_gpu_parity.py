@@ -560,6 +560,24 @@ def test_points_in_region_and_infinite_proj(G, O, ctx):
     assert abs(float(wu @ y) - eg.mu) < 1e-8 * max(1.0, abs(eg.mu))
 
 
+@pytest.mark.parametrize("mT,mC", [(300, 280), (128, 200), (100, 150), (640, 1)])
+def test_null_fit_reuses_treated_factor_bit_exact(G, O, ctx, mT, mC):
+    """make_null: the pooled matrix starts with the treated block, so the tiles of the treated GP's factor inside that
+    block are copied instead of recomputed (potrf prefill).  The pooled fit must equal a from-scratch fit of the
+    pooled data BIT FOR BIT."""
+    d = O.synth_two_region(max(mT, mC), 8, seed=6)
+    XT, YT = d["XT"][:, :mT], d["YT"][:mT]
+    XC, YC = d["XC"][:, :mC], d["YC"][:mC]
+    k = G.Mat32Iso(math.log(0.3), 0.0) + G.Const(math.log(20.0))
+    ln = math.log(0.3)
+    gT, gC = G.GPE(XT, YT, G.MeanZero(), k, ln), G.GPE(XC, YC, G.MeanZero(), k, ln)
+    gN = G.make_null(gT, gC)
+    scratch = G.GPE(np.hstack([XT, XC]), np.concatenate([YT, YC]), G.MeanZero(), k, ln)
+    assert gN.mll == scratch.mll                     # -(y'alpha + logdet + n log 2pi)/2: every tile of the factor enters
+    oN = O.gp_fit(O.KernelSpec(O.MAT32, 0.3, 1.0, 400.0), np.hstack([XT, XC]), np.concatenate([YT, YC]), ln)
+    assert abs(gN.mll - oN.mll) < 1e-9 * abs(oN.mll)
+
+
 def test_mll_forward_only_mode_matches_stepwise(G, O, ctx):
     """Opt-in |L^-1 (y-m)|^2 / z'z evaluation of the mll quadratic forms == the stepwise reference evaluation to
     rounding, same exceedance count, also with non-zero means and unequal region sizes."""
