@@ -113,6 +113,40 @@ def test_make_posdef_jitter_and_failure(G, O, ctx):
         G.GPE(X, y, G.MeanZero(), G.LinIso(0.0), 0.0)          # ArgumentError: unsupported kernel
 
 
+def test_abi_argument_errors_and_edge_sizes(G, O, ctx):
+    """Error behaviour at the ABI (rc -1 -> ArgumentError): empty inputs, zero draws, missing sentinels, NULL handles,
+    incompatible GP pairs, bad borders; and the smallest legal sizes (one unit, one sentinel, one draw)."""
+    import ctypes as C
+    lib = ctx.lib
+    k = G.SEIso(math.log(0.3), 0.0)
+    rng = np.random.default_rng(0)
+    X, y = rng.random((2, 5)), rng.standard_normal(5)
+    with pytest.raises(ValueError):
+        G.GPE(np.zeros((2, 0)), np.zeros(0), G.MeanZero(), k, 0.0)              # no units
+    assert lib.geordd_cliff_face(None, None, None, 0, None, None) == -1          # NULL handles never dereferenced
+    assert lib.geordd_null_mll(None, 10, 0, 0, None, 0.0, None, None, None, None, None) == -1
+    g1 = G.GPE(X[:, :1], y[:1], G.MeanZero(), k, 0.0)                            # a single unit
+    g4 = G.GPE(X[:, 1:], y[1:], G.MeanZero(), k, 0.0)
+    assert abs(g1.mll - O.gp_fit(O.KernelSpec(0, 0.3, 1.0, 0.0), X[:, :1], y[:1], 0.0).mll) < 1e-12
+    mu, S = G.cliff_face(g1, g4, X[:, :1])                                       # one sentinel
+    assert mu.shape == (1,) and S.shape == (1, 1) and S[0, 0] > 0
+    gN = G.make_null(g1, g4)
+    with pytest.raises(ValueError):
+        G.nsim_logP(g1, g4, gN, 0)                                               # zero draws
+    cnt = C.c_longlong()
+    assert lib.geordd_null_chi2(gN._h, 5, 0, 0, None, 0.0, None, C.byref(cnt)) == -1   # no sentinels attached
+    one = G.nsim_chi(g1, g4, gN, X[:, :2], 1, seed=1)                            # one draw, two sentinels
+    assert one.shape == (1,) and np.isfinite(one[0]) and one[0] >= 0
+    g3d = G.GPE(rng.random((3, 4)), y[:4], G.MeanZero(), k, 0.0)
+    with pytest.raises(ValueError):
+        G.make_null(g1, g3d)                                                     # 2-d and 3-d GPs do not pool
+    with pytest.raises(ValueError):
+        G.projection_points_all(X, np.array([[0.0, 0.0]]), ctx=ctx)              # a border needs a segment
+    with pytest.raises(ValueError):
+        G.projection_points_all(X, np.array([[0.0, 0.0], [1.0, 1.0]]), part_start=(1,), ctx=ctx)   # ... a real one
+    assert "segment" in lib.geordd_last_error(ctx._h).decode()
+
+
 def test_prior_rand(G, O, ctx):
     d, (oT, oC), (gT, gC) = _pair(G, O, m=90, nb=10, mean=(0.4, 0.0))
     Z = np.random.default_rng(1).standard_normal((90, 5))
