@@ -321,25 +321,34 @@ def main():
         finally:
             ctx.set_mll_forward_only(False)
 
-        solve_ms = prof["solve_seq"][0] + prof["solve_fwd"][0] + prof["solve_bwd"][0] + prof["trmm"][0]
-        solve_n = prof["solve_seq"][1] + prof["solve_fwd"][1] + prof["solve_bwd"][1] + prof["trmm"][1]
-        algo_flops_per_launch = flops_per_mll_draw(M_SIDE) * S * args.steps / max(solve_n, 1)
-        achieved = flops_per_mll_draw(M_SIDE) * S * args.steps / (solve_ms * 1e-3) / 1e12
+        # Dominant kernel: the fused forward/backward solve sequence = 12 m^2 of the 16 m^2 flop of a draw (2 m^2 per
+        # triangular-solve pair against L_T and L_C, 8 m^2 against L_N); the triangular multiply (4 m^2) is reported beside it.
+        seq_ms, seq_n = prof["solve_seq"]
+        trmm_ms, trmm_n = prof["trmm"]
+        dmma_ms = seq_ms + trmm_ms + prof["solve_fwd"][0] + prof["solve_bwd"][0]
+        seq_flops = 12.0 * M_SIDE * M_SIDE * S            # per launch (one launch per step)
+        trmm_flops = 4.0 * M_SIDE * M_SIDE * S
+        achieved = seq_flops * seq_n / (seq_ms * 1e-3) / 1e12
         traffic = None
-        try:   # per-launch DRAM traffic of the dominant kernel family from the committed ncu capture (same draw count only)
+        try:   # per-launch DRAM traffic of that kernel from the committed ncu capture (same draw count only)
             tj = json.load(open(os.path.join(ROOT, "profiles", "r01d_traffic.json")))
             if tj.get("draws") == S:
-                traffic = tj["dram_gbytes_per_launch"] * 1e9
+                traffic = tj["dram_gbytes"]["solve_seq_kernel"] * 1e9
         except Exception:
             pass
-        roofline = {"bound": "tensor", "kernel": "solve_seq_kernel (6 fused forward/backward solves) + solve_dataflow_kernel<TRMM> (FP64 DMMA)",
+        roofline = {"bound": "tensor", "kernel": "solve_seq_kernel (forward + backward solves against L_T, L_C, L_N of one batch of draws, FP64 DMMA)",
                     "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak,
-                    "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read+write, avg over the DMMA launches of a step)",
-                    "launches": int(solve_n), "avg_launch_ms": solve_ms / max(solve_n, 1),
-                    "algorithmic_flops_per_launch": algo_flops_per_launch,
+                    "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                    "launches": int(seq_n), "avg_launch_ms": seq_ms / max(seq_n, 1),
+                    "algorithmic_flops_per_launch": seq_flops,
                     "peak_source": "max(live register-resident mma.sync.m8n8k4.f64 probe, 37.07 = the same probe unthrottled on this pool); "
                                    "MEASURED_PEAKS.json has no FP64 figure", "peak_live": dmma_live,
-                    "share_of_step": solve_ms / ms}
+                    "share_of_step": seq_ms / ms,
+                    "also": {"kernel": "solve_dataflow_kernel<TRMM> (prior_rand, 4 m^2 flop/draw)",
+                             "achieved": trmm_flops * trmm_n / (trmm_ms * 1e-3) / 1e12, "avg_launch_ms": trmm_ms / max(trmm_n, 1),
+                             "share_of_step": trmm_ms / ms},
+                    "all_dmma_launches": {"achieved": flops_per_mll_draw(M_SIDE) * S * args.steps / (dmma_ms * 1e-3) / 1e12,
+                                          "share_of_step": dmma_ms / ms}}
         cpu = None
         if not args.no_cpu_baseline:
             rate, setup_s, dt = cpu_reference_rate(16)
@@ -353,7 +362,7 @@ def main():
                                        "hypotest_mll null, 20000 draws per GPU per step",
                            "m_per_side": M_SIDE, "n": 2 * M_SIDE, "sentinels": NB, "draws_per_gpu_per_step": S,
                            "rng": "device Philox-4x32-10 + Box-Muller", "parallelism": f"draw-sharded x{world}",
-                           "l2": "inputs larger than L2 (factors 768 MB + 5 GB of draw buffers per step)"},
+                           "l2": "inputs larger than L2 (factors 768 MB + 6.6 GB of draw buffers per step)"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "what": "per step: GPE(T), GPE(C), make_null from pinned host X/y + 20000 mll draws + D2H of both "
