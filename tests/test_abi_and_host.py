@@ -136,3 +136,24 @@ def test_two_rank_tally_allreduce_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+def _build_c_driver(tmp_path):
+    exe = str(tmp_path / "c_driver")
+    libdir = os.path.join(ROOT, "geordd.jl_b200", "lib")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "c_driver.c"), "-L" + libdir, "-lgeordd_b200", "-Wl,-rpath," + libdir, "-lm", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_header_is_plain_c_and_links(G, tmp_path):
+    """include/geordd_b200.h compiles as strict C99 and a plain-C consumer links against the library (the boundary
+    carries no C++ / torch / Python types).  Without a GPU the driver exits with its "no context" code."""
+    G.capi.load_library()
+    exe = _build_c_driver(tmp_path)
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 2 and "no usable GPU" in r.stderr

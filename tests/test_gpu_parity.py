@@ -147,6 +147,34 @@ def test_abi_argument_errors_and_edge_sizes(G, O, ctx):
     assert "segment" in lib.geordd_last_error(ctx._h).decode()
 
 
+def test_plain_c_consumer_matches_python_path(G, O, ctx, tmp_path):
+    """examples/c_driver.c (gcc -std=c99, links only libgeordd_b200.so) reproduces the Python path's numbers."""
+    import subprocess
+    from test_abi_and_host import _build_c_driver
+    exe = _build_c_driver(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = np.array([float(v) for v in r.stdout.split()])
+    M, s = 60, 12345
+    XT, XC = np.zeros((2, M), order="F"), np.zeros((2, M), order="F")
+    def lcg():
+        nonlocal s
+        s = (s * 1664525 + 1013904223) % 2 ** 32
+        return (s >> 8) / 16777216.0
+    for i in range(M):
+        XT[0, i] = 0.5 * lcg(); XT[1, i] = lcg(); XC[0, i] = 0.5 + 0.5 * lcg(); XC[1, i] = lcg()
+    YT = np.sin(3.0 * XT[0]) + XT[1] + 0.4
+    YC = np.sin(3.0 * XC[0]) + XC[1]
+    Xb = np.asfortranarray(np.array([[0.5, 0.5, 0.5], [0.25, 0.5, 0.75]]))
+    k = G.SEIso(math.log(0.3), 0.0)
+    gT, gC = G.GPE(XT, YT, G.MeanZero(), k, math.log(0.1)), G.GPE(XC, YC, G.MeanZero(), k, math.log(0.1))
+    mu, S = G.cliff_face(gT, gC, Xb)
+    chi = G.chistat(gT, gC, Xb)
+    p = G.boot_chi2test(gT, gC, Xb, 2000, seed=1)
+    want = np.array([mu[0], mu[1], mu[2], S[0, 0], chi, p])
+    assert np.allclose(got, want, rtol=1e-12, atol=0) and got[5] == want[5]
+
+
 def test_prior_rand(G, O, ctx):
     d, (oT, oC), (gT, gC) = _pair(G, O, m=90, nb=10, mean=(0.4, 0.0))
     Z = np.random.default_rng(1).standard_normal((90, 5))
