@@ -4,24 +4,35 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 ``--impl reference`` legs may import this module.  The product path
 (``geordd.jl_b200``) never imports it and has no CPU fallback.
 
-PARITY UNPINNED: the reference (maximerischard/GeoRDD.jl @ /root/reference) ships no
-golden vectors for any GP quantity, Julia is not installed, and
-the arithmetic lives in un-vendored third-party packages (GaussianProcesses.jl 0.11.2,
-PDMats 0.9.12, Distributions 0.22.6, Distances 0.8.2 -- Manifest.toml:222-226,376-380,
-140-144,130-134).  This file restates, in NumPy/SciPy float64 calling the same
-BLAS/LAPACK routines in the same order, the algorithm of
+PARITY STATUS.  The reference (maximerischard/GeoRDD.jl @ /root/reference) ships no golden vectors, Julia is not
+installed, and the arithmetic lives in un-vendored third-party packages (GaussianProcesses.jl 0.11.2, PDMats
+0.9.12, Distributions 0.22.6, Distances 0.8.2 -- Manifest.toml:222-226,376-380,140-144,130-134).  What pins this
+oracle to the reference's own outputs:
+
+  PINNED by the printed outputs of notebooks/Mississippi_sharp_null_sims.ipynb (Julia 1.4.0, cells 11-16), replayed
+  with the restated Julia MersenneTwister / randn of oracle/julia_rng.py (tests/test_oracle.py::
+  test_reference_notebook_outputs_pin_the_oracle, fixture tests/golden/julia_notebook.npz):
+    * make_null, prior_rand, update_alpha!, mll of the treated / control / pooled GPs, nsim_logP, boot_mlltest:
+      the printed p-value 0.0354 = 354 exceedances of 10 000, reproduced EXACTLY;
+    * nsim_chi (cliff-face mean at the sentinels, the make_posdef!-factored sentinel system): the two printed
+      boot_chi2test values 0.0754 and 0.0759 are reproduced for one common observed statistic within 0.11 % of this
+      oracle's (that statistic is an LU solve at condition number 1.8e14 and is not reproducible to more digits);
+    * pval_invvar_uncalib / pval_invvar_calib: within the noise of the same ill-conditioned solve (1 % / 16 %);
+  PINNED STATISTICALLY by the size / power table of the same notebook (cell 28);
+  PARITY UNPINNED by the reference for everything else (cliff-face covariance values, inverse-variance estimates,
+  the analytic calibration formula, MultiGPCovars mll / gradient / postmean_beta, weights, projections): those are
+  cross-checked only independently of the reference -- a 50-digit mpmath variant, identities (y'K^-1 y = z'z for
+  y = Lz), analytic gradient vs finite differences (the reference's own test style,
+  test/test_gprealisations.jl:12-40), the reference's statistical acceptance tests (test/test_simulated.jl:53-71).
+
+This file restates, in NumPy/SciPy float64 calling the same BLAS/LAPACK routines in the same order, the algorithm of
 
     src/gp_utils.jl, src/hypotest.jl, src/cliff_face.jl:3-9, src/hypotest_chi2.jl:4-59,
     src/hypotest_invvar.jl:1-137, src/hypotest_mll.jl:1-45, src/power.jl,
     src/average_treatment_effect.jl, src/GPrealisationsCovars.jl:101-193,284-344,
-    src/GPrealisations.jl:21-109, src/region_gp_fit.jl, src/weight_at_units.jl:12-18
+    src/GPrealisations.jl:21-109, src/region_gp_fit.jl, src/weight_at_units.jl, src/border_projection.jl
 
-plus the published semantics of the third-party calls those files make (SURVEY.md
-App. A).  It is cross-checked independently in tests/test_oracle.py: a 50-digit mpmath
-variant, identities (y'K^-1 y = z'z for y = Lz), analytic gradient vs finite
-differences (the reference's own test style, test/test_gprealisations.jl:12-40), the
-reference's statistical acceptance tests (test/test_simulated.jl:53-71) and the
-published Mississippi size table (notebooks/Mississippi_sharp_null_sims.ipynb cell 28).
+plus the published semantics of the third-party calls those files make.
 
 Conventions (Julia): all matrices column-major in spirit; coordinates are dim x n
 (unit i = column i); D is p x n; sentinels are 2 x nb; Cholesky factors are UPPER

@@ -9,7 +9,14 @@ mississippi.npz  -- the reference's own fixture (notebooks/Mississippi_data/{X_M
                     (DATA, not source code); the notebook draws Y from the null prior.
 oracle_small.npz -- outputs of the CPU oracle on a seeded synthetic two-region problem (SURVEY §8d shapes,
                     scaled down), used to detect drift of the oracle itself and as a second target for
-                    the GPU parity tests.  NOT reference outputs: parity is unpinned by the reference.
+                    the GPU parity tests.  NOT reference outputs.
+julia_notebook.npz -- the REFERENCE'S OWN printed outputs of notebooks/Mississippi_sharp_null_sims.ipynb (Julia 1.4.0,
+                    executed top to bottom: cells 11-16) together with what is needed to replay them without Julia:
+                    `Random.seed!(4); Ysim = prior_rand(gpNull)` and the three bootstrap tests that follow consume the
+                    global MersenneTwister stream; oracle/julia_rng.py restates that generator, this fixture stores the
+                    replayed Ysim and checksums of the three blocks of 10 000 x 146 normals (so a drift of the restated
+                    generator is detected), and the printed numbers: pval_invvar_uncalib 0.006981840916959539,
+                    pval_invvar_calib 0.01977244834968639, boot_chi2test 0.0754 and 0.0759, boot_mlltest 0.0354.
 """
 import math
 import os
@@ -61,6 +68,31 @@ def oracle_small():
     print("oracle_small.npz", len(out), "arrays")
 
 
+def julia_notebook():
+    import julia_rng as J
+    ms = np.load(os.path.join(HERE, "mississippi.npz"))
+    n = ms["X_MS"].shape[1] + ms["X_LA"].shape[1]
+    spec = O.KernelSpec(O.SE_ISO, 100e3, 1.0, 100.0 ** 2, 0.0)          # SEIso(log(100e3), 0) + Const(log(100)), cell 9
+    g0T = O.gp_fit(spec, np.asfortranarray(ms["X_MS"]), np.zeros(82), 0.0)   # cell 10: GP(X, zeros, MeanZero(), k2, 0.0)
+    g0C = O.gp_fit(spec, np.asfortranarray(ms["X_LA"]), np.zeros(64), 0.0)
+    g0N = O.make_null(g0T, g0C)
+    rng = J.MersenneTwister(4)                                             # cell 11
+    z0 = J.randn_array(rng, n, bulk=False)
+    y = g0N.U.T @ z0
+    y = y - np.mean(y)
+    y[:82] += 1.2
+    sums = []
+    for _ in range(3):                                                     # cells 14, 15 (chi2) and 16 (mll)
+        z = J.randn_array(rng, n * 10000, bulk=False)
+        sums.append([z.sum(), (z * z).sum(), z[0], z[1], z[-2], z[-1]])
+    np.savez_compressed(os.path.join(HERE, "julia_notebook.npz"), seed=4, tau=1.2, z0=z0, Ysim=y,
+                        block_checksums=np.array(sums), pval_invvar_uncalib=0.006981840916959539,
+                        pval_invvar_calib=0.01977244834968639, boot_chi2=np.array([0.0754, 0.0759]), boot_mll=0.0354,
+                        nsim=10000)
+    print("julia_notebook.npz", y.shape, np.array(sums)[:, :2])
+
+
 if __name__ == "__main__":
     mississippi()
     oracle_small()
+    julia_notebook()

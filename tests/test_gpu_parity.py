@@ -640,6 +640,33 @@ def test_null_fit_reuses_treated_factor_bit_exact(G, O, ctx, mT, mC):
     assert abs(gN.mll - oN.mll) < 1e-9 * abs(oN.mll)
 
 
+def test_reference_notebook_outputs_through_the_gpu_path(G, O, golden, julia_replay, ctx):
+    """The reference notebook's printed bootstrap results (see tests/test_oracle.py::
+    test_reference_notebook_outputs_pin_the_oracle) through the CUDA path, with the notebook's own normals passed as
+    host Z: boot_mlltest count 354 / 10 000 exactly; both chi2 counts (754, 759) for one common observed statistic
+    within the (ill-conditioned, 2 %) noise of the device's own chistat; statistics equal to the oracle's."""
+    ms, jn = golden["mississippi"], golden["julia_notebook"]
+    k = G.SEIso(math.log(100e3), 0.0) + G.Const(math.log(100.0))
+    y, Xb = julia_replay["Ysim"], ms["sentinels"]
+    gT = G.GPE(ms["X_MS"], y[:82].copy(), G.MeanZero(), k, 0.0)
+    gC = G.GPE(ms["X_LA"], y[82:].copy(), G.MeanZero(), k, 0.0)
+    assert G.boot_mlltest(gT, gC, 10000, Z=julia_replay["Z_mll"]) == float(jn["boot_mll"]) == 0.0354
+    gN = G.make_null(gT, gC)
+    sa = np.sort(G.nsim_chi(gT, gC, gN, Xb, 0, Z=julia_replay["Z_chi_a"]))[::-1]
+    sb = np.sort(G.nsim_chi(gT, gC, gN, Xb, 0, Z=julia_replay["Z_chi_b"]))[::-1]
+    lo, hi = max(sa[754], sb[759]), min(sa[753], sb[758])
+    assert lo < hi
+    # the observed statistic is an LU solve against the raw cliff covariance (cond 1.8e14): Julia's value must have been
+    # ~15.7495, LAPACK gives 15.767, the device's LU 15.88 -- each within the noise of that solve
+    assert abs(0.5 * (lo + hi) - G.chistat(gT, gC, Xb)) < 2e-2 * G.chistat(gT, gC, Xb)
+    spec = O.KernelSpec(O.SE_ISO, 100e3, 1.0, 100.0 ** 2, 0.0)
+    oT = O.gp_fit(spec, np.asfortranarray(ms["X_MS"]), y[:82].copy(), 0.0)
+    oC = O.gp_fit(spec, np.asfortranarray(ms["X_LA"]), y[82:].copy(), 0.0)
+    so = O.nsim_chi(oT, oC, O.make_null(oT, oC), Xb, julia_replay["Z_chi_a"][:, :64])
+    sg = G.nsim_chi(gT, gC, gN, Xb, 0, Z=julia_replay["Z_chi_a"][:, :64])
+    assert relerr(sg, so) < 1e-6        # ill-conditioned sentinel system (cond 1e14 before the make_posdef! jitter)
+
+
 def test_mll_forward_only_mode_matches_stepwise(G, O, ctx):
     """Opt-in |L^-1 (y-m)|^2 / z'z evaluation of the mll quadratic forms == the stepwise reference evaluation to
     rounding, same exceedance count, also with non-zero means and unequal region sizes."""

@@ -307,3 +307,40 @@ def test_infinite_proj_sentinels_weights(O):
     assert len(np.unique(Xb[0])) == Xb.shape[1] and np.all(w == w[0]) and w[0] in (5.0, 6.0)
     Xb2, w2 = O.infinite_proj_sentinels(border, rings, 0.25, 0.1, density=lambda a, b: 2.0)
     assert np.array_equal(Xb, Xb2) and np.allclose(w2, 2.0 * w)
+
+
+def test_reference_notebook_outputs_pin_the_oracle(O, golden, julia_replay):
+    """GOLDEN PIN FROM THE REFERENCE ITSELF.  notebooks/Mississippi_sharp_null_sims.ipynb (Julia 1.4.0, run top to
+    bottom) prints, after `Random.seed!(4)`:
+        cell 12  pval_invvar_uncalib = 0.006981840916959539      cell 13  pval_invvar_calib = 0.01977244834968639
+        cells 14, 15  boot_chi2test(.., 10000) = 0.0754, 0.0759   cell 16  boot_mlltest(.., 10000) = 0.0354
+    With Julia's MersenneTwister / randn restated (oracle/julia_rng.py) the oracle reproduces
+      * the mll bootstrap count EXACTLY: 354 of 10 000 (the 2.92 million normals drawn before and during that cell
+        must all be right, and so must make_null, prior_rand, update_alpha! and mll of the three GPs);
+      * both chi2 bootstrap counts for one common observed statistic within 0.2 % of its own -- the observed
+        statistic is an LU solve against the raw 200 x 200 cliff covariance, cond 1.8e14, so it cannot be reproduced
+        to more digits across BLAS builds, but the two vectors of 10 000 simulated statistics are pinned jointly;
+      * the two analytic p-values within the noise of that same ill-conditioned solve (1 % and 16 %; a single wrong
+        normal moves them by up to a factor 3)."""
+    ms, jn = golden["mississippi"], golden["julia_notebook"]
+    spec = O.KernelSpec(O.SE_ISO, 100e3, 1.0, 100.0 ** 2, 0.0)
+    y, Xb = julia_replay["Ysim"], ms["sentinels"]
+    gT = O.gp_fit(spec, np.asfortranarray(ms["X_MS"]), y[:82].copy(), 0.0)
+    gC = O.gp_fit(spec, np.asfortranarray(ms["X_LA"]), y[82:].copy(), 0.0)
+    gN = O.make_null(gT, gC)
+    # cell 16
+    d_obs = gT.mll + gC.mll - gN.mll                       # before the simulations: like the reference, they leave the
+    chi_obs = O.chistat_obs(gT, gC, Xb)                    # GPs at the last draw
+    mn, ma = O.nsim_logP(O.modifiable(gT), O.modifiable(gC), gN, julia_replay["Z_mll"])
+    assert int(np.sum((ma - mn) > d_obs)) == round(float(jn["boot_mll"]) * 10000) == 354
+    assert np.min(np.abs((ma - mn) - d_obs)) > 1e-6          # no draw anywhere near the threshold: the count is robust
+    # cells 14, 15
+    sa = np.sort(O.nsim_chi(gT, gC, gN, Xb, julia_replay["Z_chi_a"]))[::-1]
+    sb = np.sort(O.nsim_chi(gT, gC, gN, Xb, julia_replay["Z_chi_b"]))[::-1]
+    ca, cb = (int(round(v * 10000)) for v in jn["boot_chi2"])
+    lo, hi = max(sa[ca], sb[cb]), min(sa[ca - 1], sb[cb - 1])    # thresholds t with #{sa > t} == 754 and #{sb > t} == 759
+    assert lo < hi, "no common observed statistic reproduces both printed chi2 p-values"
+    assert abs(0.5 * (lo + hi) - chi_obs) < 2e-3 * chi_obs
+    # cells 12, 13
+    assert abs(O.pval_invvar_uncalib_obs(gT, gC, Xb) - float(jn["pval_invvar_uncalib"])) < 0.02 * float(jn["pval_invvar_uncalib"])
+    assert abs(O.pval_invvar_calib(gT, gC, Xb) - float(jn["pval_invvar_calib"])) < 0.25 * float(jn["pval_invvar_calib"])
