@@ -1,8 +1,8 @@
 """TEST INFRASTRUCTURE (oracle/): Julia 1.4's MersenneTwister + randn, restated so that the reference notebook
-`notebooks/Mississippi_sharp_null_sims.ipynb` (cells 11-13: `Random.seed!(4); Ysim = prior_rand(gpNull)` and the two
-printed p-values) can be replayed without Julia.  Only tests/ and tests/golden/make_golden.py import this.
+`notebooks/Mississippi_sharp_null_sims.ipynb` (cells 11-16: `Random.seed!(4); Ysim = prior_rand(gpNull)`, the two analytic
+p-values and the three bootstrap tests that follow) can be replayed without Julia.  Only tests/ and tests/golden/make_golden.py import this.
 
-What is restated [recalled from the published algorithms; pinned by the notebook's printed 16-digit outputs]:
+What is restated [recalled from the published algorithms; pinned by the notebook's printed outputs]:
   * dSFMT-19937 (Saito & Matsumoto, dSFMT 2.2): `dsfmt_init_by_array`, the 128-bit recursion, doubles in [1, 2);
   * Random.MersenneTwister: `seed!(rng, n)` -> `init_by_array(UInt32[n])`, a cache of 1002 doubles refilled by
     `dsfmt_fill_array_close1_open2!` (same sequence as successive generation);
