@@ -255,6 +255,32 @@ function proj_estimator(gpT::B200GPE, gpC::B200GPE, border, maxdist::Float64)
 end
 
 """
+    within_region(ctx, P, region)
+
+`LibGEOS.within(point, region)` for every column of `P` (2 x n) on the device -- the grid filter of
+`infinite_proj_sentinels` (src/border_projection.jl:44-102).  The (Multi)Polygon crosses the ABI as the vertex arrays
+of its closed rings.
+"""
+function within_region(ctx, P::Matrix{Float64}, region)
+    polys = region isa LibGEOS.MultiPolygon ? GeoInterface.coordinates(region) : [GeoInterface.coordinates(region)]
+    rings = [ring for poly in polys for ring in poly]
+    R = Matrix{Float64}(undef, 2, sum(length, rings)); starts = Cint[]; v = 0
+    for (k, ring) in enumerate(rings)
+        k > 1 && push!(starts, v)
+        for p in ring
+            v += 1; R[1, v] = p[1]; R[2, v] = p[2]
+        end
+    end
+    n = size(P, 2); inside = Vector{UInt8}(undef, n)
+    GC.@preserve P R starts inside begin
+        check(ctx, ccall((:geordd_points_in_region, LIB), Cint,
+                         (Ptr{Cvoid}, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Cint, Ptr{Cint}, Cint, Ptr{UInt8}),
+                         ctx.ptr, P, n, R, size(R, 2), starts, length(starts), inside))
+    end
+    return inside .!= 0
+end
+
+"""
     set_mll_forward_only!(ctx, on)
 
 Opt-in (default off): evaluate the quadratic forms of `nsim_logP` / `boot_mlltest` as |L⁻¹(y-m)|² (and z'z for the
