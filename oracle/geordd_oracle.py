@@ -18,7 +18,9 @@ oracle to the reference's own outputs:
       boot_chi2test values 0.0754 and 0.0759 are reproduced for one common observed statistic within 0.11 % of this
       oracle's (that statistic is an LU solve at condition number 1.8e14 and is not reproducible to more digits);
     * pval_invvar_uncalib / pval_invvar_calib: within the noise of the same ill-conditioned solve (1 % / 16 %);
-  PINNED STATISTICALLY by the size / power table of the same notebook (cell 28);
+    * the published size / power table (cells 19-28): all ten entries reproduced by an exact replay
+      (scripts/replay_mississippi_table.py -> tests/golden/julia_table_replay.json): nsim_invvar_pval_uncalib, nsim_logP,
+      nsim_chi, nsim_power with the corrected analytic calibration;
   PARITY UNPINNED by the reference for everything else (cliff-face covariance values, inverse-variance estimates,
   the analytic calibration formula, MultiGPCovars mll / gradient / postmean_beta, weights, projections): those are
   cross-checked only independently of the reference -- a 50-digit mpmath variant, identities (y'K^-1 y = z'z for

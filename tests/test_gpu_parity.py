@@ -7,6 +7,7 @@ exceedance counts and p-values bit-exact.  Bit-exact counts are certified by the
 min_s |stat_s - obs| / |obs| being far above the 1e-8 agreement level (SURVEY §7 hard part 2).
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -665,6 +666,20 @@ def test_reference_notebook_outputs_through_the_gpu_path(G, O, golden, julia_rep
     so = O.nsim_chi(oT, oC, O.make_null(oT, oC), Xb, julia_replay["Z_chi_a"][:, :64])
     sg = G.nsim_chi(gT, gC, gN, Xb, 0, Z=julia_replay["Z_chi_a"][:, :64])
     assert relerr(sg, so) < 1e-6        # ill-conditioned sentinel system (cond 1e14 before the make_posdef! jitter)
+
+
+def test_reference_notebook_table_through_the_gpu_path():
+    """scripts/gpu_replay_mississippi_table.py: the published size / power table of the reference notebook (ten
+    rejection rates over 10 000 power draws each, against 3 x 100 000 null statistics) through the CUDA path with the
+    notebook's own normals -- equal to the notebook's table and, to all printed digits, to the oracle's replay."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "gpu_replay_mississippi_table.py")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "GPU TABLE == NOTEBOOK TABLE" in r.stdout, r.stdout
+    lines = {ln.split()[0]: ln[ln.index("{"):ln.rindex("}") + 1] for ln in r.stdout.splitlines()
+             if ln.split() and ln.split()[0] in ("GPU", "oracle") and "{" in ln}
+    assert lines["GPU"] == lines["oracle"]
 
 
 def test_mll_forward_only_mode_matches_stepwise(G, O, ctx):
