@@ -1,0 +1,268 @@
+"""GPU parity tests AT THE SIZES BASELINE.json NAMES (C2, C3, C4, C5) and the replay of the reference notebook
+notebooks/SimulatedExample.ipynb through the product path.  Every comparison is CUDA path (through the C ABI) vs the CPU
+oracle on identical inputs -- host standard normals `Z`, so that the draws are the same numbers on both sides.
+
+Tolerances: north_star -- posterior quantities and null statistics 1e-8 relative given identical draws; exceedance counts
+exact (certified by the minimum margin between any simulated statistic and the threshold).
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-8
+
+
+def _margin(sims, obs):
+    return float(np.min(np.abs(sims - obs)) / abs(obs))
+
+
+# ---------------------------------------------------------------------------------------------
+# notebooks/SimulatedExample.ipynb through the GPU path (pins a3-a7, a11, a12, f2, f4 to the reference's printed outputs)
+# ---------------------------------------------------------------------------------------------
+def test_simulated_example_notebook_through_the_gpu_path(G, O, ctx):
+    """The notebook's data (Random.seed!(1), replayed bit for bit: tests/golden/simulated_example.npz, checked against
+    oracle/julia_rng.py in tests/test_oracle.py) through MultiGPCovars -> optimize! -> postmean_beta -> residuals_data ->
+    GPRealisations -> sentinels -> cliff_face -> inverse_variance / proj_estimator / pval_invvar_uncalib /
+    pval_invvar_calib ON THE GPU, against the numbers the notebook prints (cells 10, 11, 15, 17, 18).  D is the reference's
+    604-column full-dummy design (p = 2n + 4 > n: SURVEY App. B-6 exercised on the device).  The optimiser's end point in
+    the notebook has the Const kernel switched off (see tests/test_oracle.py), so it is held at exp(-12) with fix()."""
+    import simulated_example as SE
+    NB = SE.NOTEBOOK
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "simulated_example.npz"))
+    X, Y, treat = np.asfortranarray(fx["X"]), fx["Y"], fx["treat"]
+    D = SE.full_dummy_design(fx["covarA"], fx["covarB"], fx["categ"])
+    assert D.shape == (604, 300)
+    geordd = {False: G.RegionData(np.asfortranarray(X[:, ~treat]), Y[~treat].copy(), np.asfortranarray(D[:, ~treat])),
+              True: G.RegionData(np.asfortranarray(X[:, treat]), Y[treat].copy(), np.asfortranarray(D[:, treat]))}
+    kern = G.SEIso(math.log(0.5), 0.0) + G.fix(G.Const(-12.0))
+    mg = G.MultiGPCovars(geordd, kern, G.LinIso(0.0), 1.0, groupKeys=[False, True])     # cell 9 (initial point of cell 10)
+    # the joint mll / gradient at the initial point equal the oracle's with p > n
+    Xo, Yo, Do, off = SE.grouped({k: fx[k] for k in fx.files})
+    om = O.MultiGP(D=Do, y=Yo, X=Xo, group_off=off, spec=O.KernelSpec(O.SE_ISO, 0.5, 1.0, math.exp(-24.0)), lin_ell2=1.0,
+                   log_noise=1.0)
+    go = O.multigp_update_mll_and_dmll(om, noise=True, domean=False, kern=True, beta=True)
+    gg = G.update_mll_and_dmll(mg, noise=True, domean=False, kern=True, beta=True)
+    assert abs(mg.mll - om.mll) < TOL * abs(om.mll)
+    assert len(gg) == 4 and relerr(gg, go[[0, 1, 2, 4]]) < 1e-7
+    # cell 10: optimize!(mgpcv, noise=true, kern=true, domean=false, beta=true)
+    G.optimize(mg, noise=True, kern=True, domean=False, beta=True, method="BFGS", options=dict(gtol=1e-7, maxiter=500))
+    assert abs(-mg.mll - NB["minimum"]) < 5e-5                                            # "Minimum: 1.231640e+02"
+    sy, ell = math.exp(mg.logNoise), math.sqrt(mg.kernel.kleft.ell2)
+    sf, sb = math.sqrt(mg.kernel.kleft.sigma2), 1.0 / math.sqrt(mg.betakern.ell2)
+    for got, want in ((sy, NB["sigma_y"]), (sf, NB["sigma_f"]), (ell, NB["ell"]), (sb, NB["sigma_beta"])):   # cell 11
+        assert abs(got - want) < 1.5e-4, (got, want)
+    # cell 12
+    beta = G.postmean_beta(mg)
+    assert beta.shape == (604,)
+    res = {k: G.residuals_data(rd, beta) for k, rd in geordd.items()}
+    gpr = G.GPRealisations(res, mg.kernel, mg.logNoise, groupKeys=[False, True])
+    # cell 13, 15, 17, 18
+    border = SE.border_vertices()
+    Xb = G.sentinels(border, 100)
+    mu, S = G.cliff_face(gpr[True], gpr[False], Xb)
+    ti = G.inverse_variance(mu, S)
+    tp = G.proj_estimator(gpr[True], gpr[False], border, 2.0 * ell)
+    assert (round(ti.mu, 3), round(ti.sigma, 3)) == NB["tau_inv"] and round(100 * ti.cdf(0.0), 3) == NB["tau_inv_cdf0_pct"]
+    assert (round(tp.mu, 3), round(tp.sigma, 3)) == NB["tau_proj"] and round(100 * tp.cdf(0.0), 3) == NB["tau_proj_cdf0_pct"]
+    pu = G.pval_invvar_uncalib(gpr[True], gpr[False], Xb)
+    pc = G.pval_invvar_calib(gpr[True], gpr[False], Xb)
+    assert abs(pu / NB["pval_invvar_uncalib"] - 1.0) < 2e-4, pu
+    assert abs(pc / NB["pval_invvar_calib"] - 1.0) < 2e-4, pc
+    # ... and the same quantities from the oracle at the SAME hyper-parameters agree to the parity tolerance
+    spec = O.KernelSpec(O.SE_ISO, ell, sf * sf, math.exp(-24.0), 0.0)
+    om = O.MultiGP(Do, Yo, Xo, off, spec, mg.betakern.ell2, mg.logNoise)
+    O.multigp_update_mll(om)
+    bo = O.multigp_postmean_beta(om)
+    r = O.residuals(Yo, Do, bo)
+    oC, oT = O.gp_fit(spec, Xo[:, :150], r[:150], mg.logNoise), O.gp_fit(spec, Xo[:, 150:], r[150:], mg.logNoise)
+    mo, So = O.cliff_face(oT, oC, O.polyline_sentinels(border, 100))
+    assert relerr(Xb, O.polyline_sentinels(border, 100)) < 1e-14
+    assert relerr(mu, mo) < 1e-7 and relerr(S, So) < 1e-7      # through beta_hat: a p x p = 604 x 604 LU solve upstream
+    assert abs(pu - O.pval_invvar_uncalib_obs(oT, oC, Xb)) < 1e-6 * pu
+    assert abs(pc - O.pval_invvar_calib(oT, oC, Xb)) < 1e-6 * pc
+
+
+# ---------------------------------------------------------------------------------------------
+# C4: 4 000 units/side, Matern-3/2 + Const, hypotest_mll (the headline bench configuration)
+# ---------------------------------------------------------------------------------------------
+def test_c4_mll_and_chi2_against_oracle_at_full_size(G, O, ctx):
+    """32 mll draws (mll_null AND mll_alt, 1e-8) and the exceedance count for host Z at m = 4 000; 8 chi2 / inverse-variance
+    draws with 100 sentinels on the same fits."""
+    m, nb, S = 4000, 100, 32
+    d = O.synth_two_region(m, nb, seed=1)
+    ln = math.log(0.3)
+    k = G.Mat32Iso(math.log(0.3), 0.0) + G.Const(math.log(20.0))
+    spec = O.KernelSpec(O.MAT32, 0.3, 1.0, 400.0)
+    oT, oC = O.gp_fit(spec, d["XT"], d["YT"], ln), O.gp_fit(spec, d["XC"], d["YC"], ln)
+    gT, gC = G.GPE(d["XT"], d["YT"], G.MeanZero(), k, ln), G.GPE(d["XC"], d["YC"], G.MeanZero(), k, ln)
+    assert abs(gT.mll - oT.mll) < TOL * abs(oT.mll) and abs(gC.mll - oC.mll) < TOL * abs(oC.mll)
+    assert relerr(gT.alpha, oT.alpha) < TOL and relerr(gC.alpha, oC.alpha) < TOL
+    Z = np.asfortranarray(np.random.default_rng(2).standard_normal((2 * m, S)))
+    oN = O.make_null(oT, oC)
+    gN = G.NullGPE(gT, gC, d["Xb"], 0.0)
+    assert abs(gN.mll - oN.mll) < TOL * abs(oN.mll)
+    d_obs = oT.mll + oC.mll - oN.mll
+    mn_o, ma_o = O.nsim_logP(oT, oC, oN, Z)
+    thr = float(np.median(ma_o - mn_o))                    # a threshold in the middle of the draws: a non-trivial count
+    _, cnt, mn, ma = G.nsim_logP(gT, gC, gN, S, Z=Z, dmll_obs=thr, return_count=True)
+    assert np.max(np.abs(mn - mn_o) / np.abs(mn_o)) < TOL and np.max(np.abs(ma - ma_o) / np.abs(ma_o)) < TOL
+    # the test statistic is a difference of three mll's of size ~1e4: it agrees to 1e-8 of THAT scale, and the count is
+    # certified by the distance of every simulated statistic from the threshold being 100x the observed disagreement
+    err = float(np.max(np.abs((ma - mn) - (ma_o - mn_o))))
+    assert err < TOL * float(np.max(np.abs(mn_o)))
+    assert float(np.min(np.abs((ma_o - mn_o) - thr))) > 100.0 * err and cnt == int(np.sum((ma_o - mn_o) > thr))
+    assert abs((gT.mll + gC.mll - gN.mll) - d_obs) < TOL * (abs(oT.mll) + abs(oC.mll) + abs(oN.mll))
+    # chi2 and inverse variance on 8 of the draws
+    Zc = np.asfortranarray(Z[:, :8])
+    so = O.nsim_chi(oT, oC, O.make_null(oT, oC), d["Xb"], Zc)
+    sg = G.nsim_chi(gT, gC, gN, d["Xb"], 8, Z=Zc)
+    assert np.max(np.abs(sg - so) / so) < TOL
+    po = O.nsim_invvar_pval_uncalib(oT, oC, d["Xb"], Zc)
+    pg = G.nsim_invvar_pval_uncalib(gT, gC, d["Xb"], 8, Z=Zc, gpNull=gN)
+    assert np.max(np.abs(pg - po)) < TOL
+    # cliff face at full size
+    mu, Sg = G.cliff_face(gT, gC, d["Xb"])
+    mo, So = O.cliff_face(oT, oC, d["Xb"])
+    assert relerr(mu, mo) < TOL and relerr(Sg, So) < TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# C3: Mississippi-shaped sweep, 1 000 units/side, 200 sentinels, hypotest_chi2 + hypotest_invvar
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,const_s2", [(2, 400.0), (0, 1.0e4)])
+def test_c3_chi2_and_invvar_against_oracle_nb200(G, O, ctx, kind, const_s2):
+    """m = 1 000 per side, nb = 200 (C3), 512 host-Z draws: every chi2 statistic and inverse-variance p-value against the
+    oracle, both exceedance counts exact.  Two kernels: Matern-3/2 + Const(20) (cond(Sigma_cliff) ~ 1e6: the 1e-8 gate
+    applies) and the Mississippi-style SEIso + Const(100), whose 200 x 200 cliff covariance is numerically singular
+    (make_posdef! adds jitter; cond after jitter ~ 1e8-1e9): there the statistics can only agree to cond * eps, so the
+    gate is 1e-6 and the counts are certified by a correspondingly larger margin."""
+    m, nb, S = 1000, 200, 512
+    d = O.synth_two_region(m, nb, seed=3)
+    ln = math.log(0.3)
+    k = (G.Mat32Iso if kind == 2 else G.SEIso)(math.log(0.3), 0.0) + G.Const(0.5 * math.log(const_s2))
+    spec = O.KernelSpec(kind, 0.3, 1.0, const_s2)
+    tol = TOL if kind == 2 else 1e-6
+    oT, oC = O.gp_fit(spec, d["XT"], d["YT"], ln), O.gp_fit(spec, d["XC"], d["YC"], ln)
+    gT, gC = G.GPE(d["XT"], d["YT"], G.MeanZero(), k, ln), G.GPE(d["XC"], d["YC"], G.MeanZero(), k, ln)
+    Z = np.asfortranarray(np.random.default_rng(7).standard_normal((2 * m, S)))
+    ns = O.null_setup(oT, oC, d["Xb"], 0.0)
+    gN = G.NullGPE(gT, gC, d["Xb"], 0.0)
+    assert gN.jitter_rounds == ns.jitter_rounds
+    so = O.nsim_chi(oT, oC, O.make_null(oT, oC), d["Xb"], Z)
+    thr = float(np.quantile(so, 0.9))
+    sg, cnt = G.nsim_chi(gT, gC, gN, d["Xb"], S, Z=Z, chi_obs=thr, return_count=True)
+    assert np.max(np.abs(sg - so) / so) < tol, float(np.max(np.abs(sg - so) / so))
+    assert _margin(so, thr) > 100 * tol and cnt == int(np.sum(so > thr))
+    po = O.nsim_invvar_pval_uncalib(oT, oC, d["Xb"], Z)
+    ns2 = O.null_setup(oT, oC, d["Xb"], 1e-10)
+    pthr = float(np.quantile(po, 0.1))
+    pg, cnti = G.nsim_invvar_pval_uncalib(gT, gC, d["Xb"], S, Z=Z, pval_obs=pthr, return_count=True)
+    assert np.max(np.abs(pg - po)) < tol, float(np.max(np.abs(pg - po)))
+    assert _margin(po, pthr) > 100 * tol and cnti == int(np.sum(po < pthr))
+    assert ns2.jitter_rounds >= 0
+
+
+# ---------------------------------------------------------------------------------------------
+# C2: SimulatedExample-shaped joint fit, 2 000 units/side, covariates
+# ---------------------------------------------------------------------------------------------
+def test_c2_multigp_at_full_size(G, O, ctx):
+    """MultiGPCovars at n = 4 000, p = 6 (2 real covariates + 3-level categorical + intercept): mll, alpha, all five
+    gradient entries and postmean_beta against the oracle; then cliff face + inverse-variance LATE on the residual GPs."""
+    m = 2000
+    d = O.synth_two_region(m, 100, seed=2)
+    rdict = {True: G.RegionData(d["XT"], d["YT"], d["D"][:, :m]), False: G.RegionData(d["XC"], d["YC"], d["D"][:, m:])}
+    ln, lin_ll = math.log(0.3), math.log(10.0)                                  # sigma_beta = 0.1
+    mg = G.MultiGPCovars(rdict, G.SEIso(math.log(0.3), 0.0) + G.Const(math.log(20.0)), G.LinIso(lin_ll), ln,
+                         groupKeys=[True, False])
+    om = O.MultiGP(D=d["D"], y=d["Y"], X=d["X"], group_off=[0, m, 2 * m], spec=O.KernelSpec(O.SE_ISO, 0.3, 1.0, 400.0),
+                   lin_ell2=100.0, log_noise=ln)
+    go = O.multigp_update_mll_and_dmll(om, noise=True, domean=False, kern=True, beta=True)
+    gg = G.update_mll_and_dmll(mg, noise=True, domean=False, kern=True, beta=True)
+    assert abs(mg.mll - om.mll) < TOL * abs(om.mll)
+    assert len(gg) == len(go) == 5 and np.max(np.abs(gg - go) / (np.abs(go) + 1e-6 * np.max(np.abs(go)))) < 1e-6
+    G.update_mll(mg)
+    assert relerr(mg.alpha, om.alpha) < 1e-7
+    bg, bo = G.postmean_beta(mg), O.multigp_postmean_beta(om)
+    assert relerr(bg, bo) < 1e-7
+    res = {k_: G.residuals_data(rd, bg) for k_, rd in rdict.items()}
+    gpr = G.GPRealisations(res, mg.kernel, mg.logNoise, groupKeys=[True, False])
+    r = O.residuals(d["Y"], d["D"], bo)
+    spec = O.KernelSpec(O.SE_ISO, 0.3, 1.0, 400.0)
+    oT, oC = O.gp_fit(spec, d["XT"], r[:m], ln), O.gp_fit(spec, d["XC"], r[m:], ln)
+    mu, S = G.cliff_face(gpr[True], gpr[False], d["Xb"])
+    mo, So = O.cliff_face(oT, oC, d["Xb"])
+    assert relerr(mu, mo) < 1e-7 and relerr(S, So) < 1e-7
+    tg, to = G.inverse_variance(mu, S), O.inverse_variance(mo, So)
+    assert abs(tg.mu - to.mu) < 1e-6 * abs(to.mu) and abs(tg.sigma - to.sigma) < 1e-6 * to.sigma
+
+
+def test_multigp_with_more_covariate_columns_than_units(G, O, ctx):
+    """SURVEY App. B-6 at size: the reference's full-dummy design has p = 2n + 4 columns.  n = 1 200, p = 2 404."""
+    import simulated_example as SE
+    m = 600
+    d = O.synth_two_region(m, 50, seed=6)
+    n = 2 * m
+    categ = np.argmax(d["D"][3:], axis=0) + 1
+    D = SE.full_dummy_design(d["D"][1], d["D"][2], categ)
+    assert D.shape == (2 * n + 4, n)
+    rdict = {True: G.RegionData(d["XT"], d["YT"], np.asfortranarray(D[:, :m])),
+             False: G.RegionData(d["XC"], d["YC"], np.asfortranarray(D[:, m:]))}
+    mg = G.MultiGPCovars(rdict, G.Mat32Iso(math.log(0.3), 0.0) + G.Const(math.log(20.0)), G.LinIso(math.log(5.0)), math.log(0.3),
+                         groupKeys=[True, False])
+    om = O.MultiGP(D=D, y=d["Y"], X=d["X"], group_off=[0, m, n], spec=O.KernelSpec(O.MAT32, 0.3, 1.0, 400.0), lin_ell2=25.0,
+                   log_noise=math.log(0.3))
+    go = O.multigp_update_mll_and_dmll(om, noise=True, domean=False, kern=True, beta=True)
+    gg = G.update_mll_and_dmll(mg, noise=True, domean=False, kern=True, beta=True)
+    assert abs(mg.mll - om.mll) < TOL * abs(om.mll) and relerr(gg, go) < 1e-7
+    assert relerr(G.postmean_beta(mg), O.multigp_postmean_beta(om)) < 1e-7
+
+
+# ---------------------------------------------------------------------------------------------
+# C5: power study shape, 16 000 units in total
+# ---------------------------------------------------------------------------------------------
+def test_c5_power_study_against_oracle_at_full_size(G, O, ctx):
+    """n = 16 000 (8 000 per side), SEIso + Const, 100 sentinels: 8 host-Z draws of nsim_logP / nsim_chi /
+    nsim_invvar_pval_uncalib and 8 alternative draws of nsim_power (tau = 0.3; five p-values each) against the oracle,
+    plus the z'z identity on 1 000 device draws."""
+    m, nb = 8000, 100
+    d = O.synth_two_region(m, nb, seed=1)
+    ln = math.log(0.3)
+    k = G.SEIso(math.log(0.3), 0.0) + G.Const(math.log(20.0))
+    spec = O.KernelSpec(O.SE_ISO, 0.3, 1.0, 400.0)
+    oT, oC = O.gp_fit(spec, d["XT"], d["YT"], ln), O.gp_fit(spec, d["XC"], d["YC"], ln)
+    gT, gC = G.GPE(d["XT"], d["YT"], G.MeanZero(), k, ln), G.GPE(d["XC"], d["YC"], G.MeanZero(), k, ln)
+    assert abs(gT.mll - oT.mll) < TOL * abs(oT.mll) and abs(gC.mll - oC.mll) < TOL * abs(oC.mll)
+    gN = G.NullGPE(gT, gC, d["Xb"], 0.0)
+    ns = O.null_setup(oT, oC, d["Xb"], 0.0)
+    assert abs(gN.mll - ns.gpN.mll) < TOL * abs(ns.gpN.mll) and gN.jitter_rounds == ns.jitter_rounds
+    rng = np.random.default_rng(9)
+    Z = np.asfortranarray(rng.standard_normal((2 * m, 8)))
+    mn_o, ma_o = O.nsim_logP(oT, oC, O.make_null(oT, oC), Z)
+    _, _, mn, ma = G.nsim_logP(gT, gC, gN, 8, Z=Z, return_count=True)
+    assert np.max(np.abs(mn - mn_o) / np.abs(mn_o)) < TOL and np.max(np.abs(ma - ma_o) / np.abs(ma_o)) < TOL
+    so = O.nsim_chi(oT, oC, O.make_null(oT, oC), d["Xb"], Z)
+    sg = G.nsim_chi(gT, gC, gN, d["Xb"], 8, Z=Z)
+    # SEIso cliff covariance at nb = 100 is jittered (cond ~ 1e8 after jitter): statistics agree to cond * eps
+    assert np.max(np.abs(sg - so) / so) < 1e-6
+    po = O.nsim_invvar_pval_uncalib(oT, oC, d["Xb"], Z)
+    pg = G.nsim_invvar_pval_uncalib(gT, gC, d["Xb"], 8, Z=Z)
+    assert np.max(np.abs(pg - po)) < 1e-6
+    # power: null reference vectors (any numbers do: they are inputs), 8 alternative draws
+    chi_null = np.sort(rng.chisquare(20, 1000)); mll_null = rng.standard_normal(1000) * 3.0; pinv_null = rng.random(1000)
+    Zp = np.asfortranarray(rng.standard_normal((2 * m, 8)))
+    pw_o = O.nsim_power(oT, oC, 0.3, d["Xb"], chi_null, mll_null, pinv_null, Zp)
+    pw_g = G.nsim_power(gT, gC, 0.3, d["Xb"], chi_null, mll_null, pinv_null, 8, Z=Zp)
+    assert np.array_equal(pw_g[:, [0, 1, 3]], pw_o[:, [0, 1, 3]])
+    assert np.max(np.abs(pw_g[:, 2] - pw_o[:, 2])) < 1e-6 and np.max(np.abs(pw_g[:, 4] - pw_o[:, 4])) < 1e-6
+    # identity on device draws at this size
+    S = 1000
+    _, _, mnull, malt = G.nsim_logP(gT, gC, gN, S, seed=3, return_count=True)
+    Zd = np.zeros((2 * m, S), order="F")
+    ctx.check(ctx.lib.geordd_dbg_normals(ctx._h, 3, 0, S, 2 * m, G.capi.dptr(Zd)))
+    v = mnull + np.sum(Zd * Zd, axis=0) / 2.0
+    assert np.max(np.abs(v - np.median(v))) < 1e-8 * abs(np.median(v)) and np.isfinite(malt).all()

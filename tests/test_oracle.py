@@ -373,3 +373,73 @@ def test_julia_rng_known_answers():
     r = J.MersenneTwister(1234)
     assert [J.randn(r) for _ in range(3)] == [0.8673472019495624, -0.9017438158537787, -0.4944787535006291]
     assert J.MersenneTwister(1).rand() == 0.23603334566204692
+
+
+def _simulated_example_fit(O, SE, Xo, Yo, Do, off, log_const, x0):
+    """Stationary point of -mll over (logNoise, log ell, log sigma_f, LinIso ll) with the Const kernel held at
+    exp(log_const): what `optimize!` (src/GPrealisationsCovars.jl:224-279) converges to, optimiser-independent."""
+    from scipy.optimize import minimize
+
+    def fg(h):
+        spec = O.KernelSpec(O.SE_ISO, math.exp(h[1]), math.exp(2 * h[2]), math.exp(2 * log_const), 0.0)
+        mg = O.MultiGP(Do, Yo, Xo, off, spec, math.exp(2 * h[3]), h[0])
+        g = O.multigp_update_mll_and_dmll(mg, noise=True, domean=False, kern=True, beta=True)
+        return -mg.mll, -np.array([g[0], g[1], g[2], g[4]])
+
+    return minimize(fg, np.asarray(x0, dtype=float), jac=True, method="BFGS", options=dict(gtol=1e-9, maxiter=500))
+
+
+def test_simulated_example_notebook_pins_the_oracle(O):
+    """SECOND GOLDEN PIN FROM THE REFERENCE ITSELF: notebooks/SimulatedExample.ipynb (Julia 1.4.0, committed with outputs).
+    The data of cell 5 (`Random.seed!(1)`; rand(2, n), randn(n) x3, rand(["A","B","C"], n)) are replayed bit for bit
+    (oracle/julia_rng.py, oracle/simulated_example.py; fixture tests/golden/simulated_example.npz); the oracle then
+    reproduces every number the notebook prints:
+        cell 10  Minimum 1.231640e+02                      -> 123.16398 (all 7 printed digits)
+        cell 11  sigma_y .3008 sigma_f 2.2089 ell .9949 sigma_beta .0981   -> .30084 2.20881 .99484 .09809 (the notebook's CG
+                 stopped at |g| = 5e-4, |x - x'| = 2e-5: agreement to 1e-4 is agreement)
+        cell 15  tau_inv ~ N(0.314, 0.090), P(tau<0) 0.025 %; tau_proj ~ N(0.398, 0.116), P(tau<0) 0.031 %
+        cell 17  pval_invvar_uncalib 0.0005060443694744312 -> 0.00050608 (7e-5 relative)
+        cell 18  pval_invvar_calib   0.00031629020838950655 -> 0.00031632 (9e-5 relative)
+    This pins MultiGPCovars' mll and gradient, postmean_beta, residuals_data, GPRealisations, cliff_face, inverse_variance,
+    sentinels / projection_points / proj_estimator and the 3-argument pval_invvar_calib to the reference (SURVEY §8 a3-a7,
+    a11, a12, f4), and settles App. B-6: D is the 604-column full-dummy design (the 6-column design gives 116.47)."""
+    import simulated_example as SE
+    NB = SE.NOTEBOOK
+    d = SE.notebook_data()
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "simulated_example.npz"))
+    for k in ("X", "Y", "treat", "covarA", "covarB", "categ"):
+        assert np.array_equal(d[k], fx[k]), k
+    assert [float(v) for v in d["X"][:, :2].ravel(order="F")] == [0.23603334566204692, 0.34651701419196046,
+                                                                  0.3127069683360675, 0.00790928339056074]
+    Xo, Yo, Do, off = SE.grouped(d)
+    assert Do.shape == (604, 300) and off == [0, 150, 300]
+    # cell 10 / 11: the optimiser's end point has the Const kernel switched off (-mll(sigma_c) at the printed
+    # hyper-parameters equals the printed 123.1640 only for log sigma_c <= -4; at log sigma_c = -2 it is 123.1626)
+    x0 = [math.log(NB["sigma_y"]), math.log(NB["ell"]), math.log(NB["sigma_f"]), -math.log(NB["sigma_beta"])]
+    res = _simulated_example_fit(O, SE, Xo, Yo, Do, off, -12.0, x0)
+    assert abs(res.fun - NB["minimum"]) < 5e-5
+    sy, ell, sf, sb = math.exp(res.x[0]), math.exp(res.x[1]), math.exp(res.x[2]), math.exp(-res.x[3])
+    assert abs(sy - NB["sigma_y"]) < 1.5e-4 and abs(sf - NB["sigma_f"]) < 1.5e-4
+    assert abs(ell - NB["ell"]) < 1.5e-4 and abs(sb - NB["sigma_beta"]) < 1.5e-4
+    assert abs(res.x[0] - NB["minimizer_head"][0]) < 5e-3 and abs(res.x[1] - NB["minimizer_head"][1]) < 5e-5 and \
+        abs(res.x[2] - NB["minimizer_head"][2]) < 5e-4
+    # the 6-column reading of the formula (intercept, two slopes, 3-level one-hot) is NOT what the reference fitted
+    D6 = np.asfortranarray(np.vstack([Do[0], d["covarA"][np.r_[np.where(~d["treat"])[0], np.where(d["treat"])[0]]],
+                                      d["covarB"][np.r_[np.where(~d["treat"])[0], np.where(d["treat"])[0]]], Do[-3:]]))
+    res6 = _simulated_example_fit(O, SE, Xo, Yo, D6, off, -12.0, x0)
+    assert abs(res6.fun - NB["minimum"]) > 1.0
+    # cells 12-18 at the stationary point
+    spec = O.KernelSpec(O.SE_ISO, ell, sf * sf, math.exp(-24.0), 0.0)
+    mg = O.MultiGP(Do, Yo, Xo, off, spec, 1.0 / sb ** 2, math.log(sy))
+    O.multigp_update_mll(mg)
+    r = O.residuals(Yo, Do, O.multigp_postmean_beta(mg))
+    gC, gT = O.gp_fit(spec, Xo[:, :150], r[:150], math.log(sy)), O.gp_fit(spec, Xo[:, 150:], r[150:], math.log(sy))
+    border = SE.border_vertices()
+    Xb = O.polyline_sentinels(border, 100)
+    mu, S = O.cliff_face(gT, gC, Xb)
+    ti, tp = O.inverse_variance(mu, S), O.proj_estimator(gT, gC, border, 2.0 * ell)
+    assert (round(ti.mu, 3), round(ti.sigma, 3)) == NB["tau_inv"] and round(100 * ti.cdf(0.0), 3) == NB["tau_inv_cdf0_pct"]
+    assert (round(tp.mu, 3), round(tp.sigma, 3)) == NB["tau_proj"] and round(100 * tp.cdf(0.0), 3) == NB["tau_proj_cdf0_pct"]
+    pu, pc = O.pval_invvar_uncalib_obs(gT, gC, Xb), O.pval_invvar_calib(gT, gC, Xb)
+    assert abs(pu / NB["pval_invvar_uncalib"] - 1.0) < 2e-4
+    assert abs(pc / NB["pval_invvar_calib"] - 1.0) < 2e-4
