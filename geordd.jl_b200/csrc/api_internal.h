@@ -111,16 +111,19 @@ struct geordd_null {
     double* dKbT = nullptr;     // nbp x mpadT : cov(kernel_T, Xb, X_T)
     double* dKbC = nullptr;     // nbp x mpadC
     double* dSig = nullptr;     // nbp x nbp raw cliff covariance (+ nugget, + jitter) = Sigma_raw
+    double* dSigRaw = nullptr;  // nbp x nbp cliff covariance + nugget BEFORE make_posdef! jitter (LU solves of the calibration)
     double* dLSig = nullptr;    // its lower factor
     double* dOnes = nullptr;    // nbp (1 on rows < nb)
     double denom = 0.0;         // sum(Sigma \ 1) with the PD factor
     // hoisted draw-independent part of the analytic calibration (src/hypotest_invvar.jl:121-131)
     bool calib_ready[2] = {false, false};
     double cov_mu_tau[2] = {0.0, 0.0};   // [0] corrected, [1] as shipped
+    bool calib_lu_ready = false;         // 3-argument pval_invvar_calib (:74-105): LU of Sigma + nugget, corrected formula
+    double cov_mu_tau_lu = 0.0;
     // simulation buffers, sized for cap_cols draws
     long cap_cols = 0;
     geordd::DevBuf Z, RN, AN, AT, AC, M, W, partN, partT, partC, partChi, partNum;
-    geordd::DevBuf oChi, oPval, oNum, oNull, oAlt;   // per-call output staging (nsim)
+    geordd::DevBuf oChi, oPval, oNum, oNull, oAlt, oNumLU;   // per-call output staging (nsim)
 };
 
 struct geordd_multigp {

@@ -150,7 +150,8 @@ static void calib_cov_mu_delta(geordd_gp* T, geordd_gp* C, const double* dXb, in
 static void null_free(geordd_null* h) {
     if (!h) return;
     if (h->N) gp_free(h->N);
-    dfree(h->dXb); dfree(h->dKbT); dfree(h->dKbC); dfree(h->dSig); dfree(h->dLSig); dfree(h->dOnes);
+    dfree(h->dXb); dfree(h->dKbT); dfree(h->dKbC); dfree(h->dSig); dfree(h->dSigRaw); dfree(h->dLSig); dfree(h->dOnes);
+    h->oNumLU.release();
     h->Z.release(); h->RN.release(); h->AN.release(); h->AT.release(); h->AC.release(); h->M.release(); h->W.release();
     h->partN.release(); h->partT.release(); h->partC.release(); h->partChi.release(); h->partNum.release();
     h->oChi.release(); h->oPval.release(); h->oNum.release(); h->oNull.release(); h->oAlt.release();
@@ -159,13 +160,14 @@ static void null_free(geordd_null* h) {
 
 struct SimRequest {
     bool want_cliff = false, want_mll = false;
+    bool want_lunum = false;   // also sum(lu(Sigma + nugget I) \ mu_b) per draw (sim_invvar_calib!, src/hypotest_invvar.jl:101)
     double tau = 0.0;
     long nsim = 0;
     unsigned long long seed = 0, draw0 = 0;
     const double* Z = nullptr;
     double chi_obs = 0.0, pval_obs = 0.0, dmll_obs = 0.0;
     // host outputs (nullable)
-    double *chi = nullptr, *pval = nullptr, *num = nullptr, *mll_null = nullptr, *mll_alt = nullptr;
+    double *chi = nullptr, *pval = nullptr, *num = nullptr, *numlu = nullptr, *mll_null = nullptr, *mll_alt = nullptr;
     double *last_y = nullptr, *last_alpha = nullptr;
     // device-resident outputs are left in h->oChi / oPval / oNum / oNull / oAlt as well
     long long n_chi = 0, n_inv = 0, n_mll = 0;
@@ -225,6 +227,7 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
         h->oChi.ensure(rq.nsim, st, false);
         h->oPval.ensure(rq.nsim, st, false);
         h->oNum.ensure(rq.nsim, st, false);
+        if (rq.want_lunum) h->oNumLU.ensure(rq.nsim, st, false);
     }
     if (rq.want_mll) {
         h->oNull.ensure(rq.nsim, st, false);
@@ -277,8 +280,8 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
             SolveEpilogue eT, eC;
             eT.xb = eC.xb = true;
             if (rq.want_mll) {
-                eT.wmat = h->RN.p; eT.ldw = npN; eT.wshift = mN - mTc; eT.wrows = mT; eT.dot0 = h->partT.p;
-                eC.wmat = h->RN.p; eC.wrow0 = mT; eC.ldw = npN; eC.wshift = mN - mCc; eC.wrows = mC; eC.dot0 = h->partC.p;
+                eT.wmat = h->RN.p; eT.ldw = npN; eT.wshift = mN - mTc; eT.wrows = mT; eT.wlive = mT; eT.dot0 = h->partT.p;
+                eC.wmat = h->RN.p; eC.wrow0 = mT; eC.ldw = npN; eC.wshift = mN - mCc; eC.wrows = mC; eC.wlive = mC; eC.dot0 = h->partC.p;
             }
             // forward and backward solves of all GPs as ONE persistent kernel (solve.cu, fused solve sequence)
             SolveEpilogue none;
@@ -319,6 +322,20 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
             gemm(c, true, false, nbp, ncols, mCp, -1.0, h->dKbC, nbp, h->AC.p, mCp, 1.0, h->M.p, nbp, 1, /*b_xb=*/true);
             launch_add_const(st, h->M.p, nbp, nb, ncols, mTc - mCc);
             GD_CUDA(cudaMemcpyAsync(h->W.p, h->M.p, (size_t)nbp * ncols * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            if (rq.want_lunum) {
+                // the reference's per-draw `Sigma_b \ mu_b` with Sigma_b a plain Matrix = LU with partial pivoting of the
+                // un-jittered Sigma + nugget I; the matrix is the same for every draw, each CTA refactors it for its chunk
+                constexpr int kColsPerCta = 128;
+                const size_t ctas = (size_t)((live + kColsPerCta - 1) / kColsPerCta);
+                c->tmp3.ensure((size_t)nbp * ncols + ctas * nb * nb, st, false);
+                GD_CUDA(cudaMemcpyAsync(c->tmp3.p, h->M.p, (size_t)nbp * ncols * sizeof(double), cudaMemcpyDeviceToDevice, st));
+                {
+                    ProfScope ps(c, PC_LU);
+                    launch_lu_solve_multi(st, h->dSigRaw, nbp, nb, c->tmp3.p + (size_t)nbp * ncols, c->tmp3.p, nbp, live, kColsPerCta,
+                                          c->d_info);
+                }
+                launch_colsum(st, c->tmp3.p, nbp, nb, live, h->oNumLU.p + done);
+            }
             SolveEpilogue e;
             e.wmat = h->M.p; e.ldw = nbp; e.dot0 = h->partChi.p;
             e.wvec = h->dOnes; e.dot1 = h->partNum.p;
@@ -351,6 +368,7 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
         if (rq.chi) GD_CUDA(cudaMemcpyAsync(rq.chi, h->oChi.p, bytes, cudaMemcpyDeviceToHost, st));
         if (rq.pval) GD_CUDA(cudaMemcpyAsync(rq.pval, h->oPval.p, bytes, cudaMemcpyDeviceToHost, st));
         if (rq.num) GD_CUDA(cudaMemcpyAsync(rq.num, h->oNum.p, bytes, cudaMemcpyDeviceToHost, st));
+        if (rq.numlu && rq.want_lunum) GD_CUDA(cudaMemcpyAsync(rq.numlu, h->oNumLU.p, bytes, cudaMemcpyDeviceToHost, st));
     }
     if (rq.want_mll) {
         if (rq.mll_null) GD_CUDA(cudaMemcpyAsync(rq.mll_null, h->oNull.p, bytes, cudaMemcpyDeviceToHost, st));
@@ -663,26 +681,24 @@ int geordd_weight_at_units(geordd_gp* gp, const double* Xb, int nb, const double
     API_END
 }
 
-int geordd_invvar_calib(geordd_gp* T, geordd_gp* C, const double* Xb, int nb, double nugget, double* pval) {
-    if (!T) return GEORDD_ERR_ARG;
-    API_BEGIN(T->ctx)
-    check_pair(T, C);
-    if (!pval) throw ApiError(GEORDD_ERR_ARG, "invvar_calib: output is NULL");
-    CliffTmp t;
-    cliff_tmp(T, C, Xb, nb, t);
-    const int nbp = t.nbp;
+// The 3-argument pval_invvar_calib (src/hypotest_invvar.jl:74-105) on device data: Sigma_b = dSig + nugget I solved by LU
+// (generic `\\` on a Matrix), cov_mu_tau = sum((Sigma_b \\ cov_mu_delta) * (Sigma_b \\ ones)), numerator sum(Sigma_b \\ mu_b).
+// dSig is consumed.  dMu may be NULL (numerator not wanted).
+static void invvar_calib_lu(geordd_gp* T, geordd_gp* C, const double* dXb, int nb, int nbp, double* dSig, double nugget,
+                            const double* dMu, double* cov_mu_tau, double* numer) {
+    geordd_ctx* c = T->ctx;
     // rhs = [cov_mu_delta (nb cols) | ones | mu_b]  solved with LU of (Sigma_b + nugget I)
-    double* rhs = dalloc((size_t)nbp * (nbp + 2), c__->stream, true);
+    double* rhs = dalloc((size_t)nbp * (nbp + 2), c->stream, true);
     try {
-        calib_cov_mu_delta(T, C, t.dXb, nb, nbp, false, rhs);
-        launch_fill(c__->stream, rhs + (size_t)nbp * nb, nb, 1.0);
-        GD_CUDA(cudaMemcpyAsync(rhs + (size_t)nbp * (nb + 1), t.dMu, (size_t)nb * sizeof(double), cudaMemcpyDeviceToDevice,
-                                c__->stream));
-        lu_solve_dev(c__, t.dSig, nb, nbp, nugget, rhs, nb + 2);
+        calib_cov_mu_delta(T, C, dXb, nb, nbp, false, rhs);
+        launch_fill(c->stream, rhs + (size_t)nbp * nb, nb, 1.0);
+        if (dMu) GD_CUDA(cudaMemcpyAsync(rhs + (size_t)nbp * (nb + 1), dMu, (size_t)nb * sizeof(double), cudaMemcpyDeviceToDevice,
+                                         c->stream));
+        lu_solve_dev(c, dSig, nb, nbp, nugget, rhs, nb + 2);
         std::vector<double> hr((size_t)nb * (nb + 2));
-        download2d(c__, hr.data(), nb, rhs, nbp, nb, nb + 2);
-        check_abort(c__);
-        // cov_mu_tau = sum((Sigma\cmd) * (Sigma\1)) ; numerator = sum(Sigma \ mu)   (tiny: nb^2 flops)
+        download2d(c, hr.data(), nb, rhs, nbp, nb, nb + 2);
+        check_abort(c);
+        // (tiny: nb^2 flops) row sums of (Sigma\\cmd) * (Sigma\\1), then the total
         const double* s1 = hr.data() + (size_t)nb * nb;
         const double* sm = hr.data() + (size_t)nb * (nb + 1);
         double cov_mt = 0.0, num = 0.0;
@@ -692,13 +708,26 @@ int geordd_invvar_calib(geordd_gp* T, geordd_gp* C, const double* Xb, int nb, do
             cov_mt += row;
         }
         for (int i = 0; i < nb; ++i) num += sm[i];
-        double z = std::fabs(num) / std::sqrt(cov_mt);
-        *pval = 2.0 * (std::erfc(z * 0.7071067811865476) / 2.0);
+        *cov_mu_tau = cov_mt;
+        if (numer) *numer = num;
     } catch (...) {
         dfree(rhs);
         throw;
     }
     dfree(rhs);
+}
+
+int geordd_invvar_calib(geordd_gp* T, geordd_gp* C, const double* Xb, int nb, double nugget, double* pval) {
+    if (!T) return GEORDD_ERR_ARG;
+    API_BEGIN(T->ctx)
+    check_pair(T, C);
+    if (!pval) throw ApiError(GEORDD_ERR_ARG, "invvar_calib: output is NULL");
+    CliffTmp t;
+    cliff_tmp(T, C, Xb, nb, t);
+    double cov_mt = 0.0, num = 0.0;
+    invvar_calib_lu(T, C, t.dXb, nb, t.nbp, t.dSig, nugget, t.dMu, &cov_mt, &num);
+    double z = std::fabs(num) / std::sqrt(cov_mt);
+    *pval = 2.0 * (std::erfc(z * 0.7071067811865476) / 2.0);
     API_END
 }
 
@@ -707,8 +736,9 @@ static int null_set_sentinels(geordd_null* h, const double* Xb, int nb, double n
     geordd_gp *T = h->T, *C = h->C;
     check_pair(T, C);
     if (!Xb || nb <= 0) throw ApiError(GEORDD_ERR_ARG, "sentinels missing");
-    dfree(h->dXb); dfree(h->dKbT); dfree(h->dKbC); dfree(h->dSig); dfree(h->dLSig); dfree(h->dOnes);
-    h->dXb = h->dKbT = h->dKbC = h->dSig = h->dLSig = h->dOnes = nullptr;
+    dfree(h->dXb); dfree(h->dKbT); dfree(h->dKbC); dfree(h->dSig); dfree(h->dSigRaw); dfree(h->dLSig); dfree(h->dOnes);
+    h->dXb = h->dKbT = h->dKbC = h->dSig = h->dSigRaw = h->dLSig = h->dOnes = nullptr;
+    h->calib_lu_ready = false;
     if (round_up(nb, TILE) != h->nbp) {   // sentinel-sized simulation buffers must be re-made
         h->M.release(); h->W.release(); h->partChi.release(); h->partNum.release();
         h->cap_cols = 0;
@@ -731,6 +761,9 @@ static int null_set_sentinels(geordd_null* h, const double* Xb, int nb, double n
     }
     dfree(mu);
     if (nugget != 0.0) launch_add_diag(c->stream, h->dSig, nbp, nb, nugget);
+    // keep Sigma + nugget I as it is BEFORE make_posdef! may jitter it: the analytic calibration solves against it by LU
+    h->dSigRaw = dalloc((size_t)nbp * nbp, c->stream, false);
+    GD_CUDA(cudaMemcpyAsync(h->dSigRaw, h->dSig, (size_t)nbp * nbp * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     int info = make_posdef(c, h->dSig, h->dLSig, nbp, nb, nbp, &h->jitter_rounds);
     if (info != 0) {
         c->err = "cliff-face covariance is not positive definite after 10 jitter rounds";
@@ -962,13 +995,31 @@ int geordd_null_invvar_calib(geordd_null* h, long nsim, unsigned long long seed,
     if (!h) return GEORDD_ERR_ARG;
     API_BEGIN(h->ctx)
     if (!pvals) throw ApiError(GEORDD_ERR_ARG, "null_invvar_calib: output is NULL");
+    if (h->nb <= 0) throw ApiError(GEORDD_ERR_ARG, "null_invvar_calib: null handle prepared without sentinels");
+    // Per draw the reference evaluates the 3-argument pval_invvar_calib(gpT, gpC, Xb) (src/hypotest_invvar.jl:138-147):
+    // only mu_b changes between draws; Sigma_b, its LU and cov_mu_tau are recomputed there to the same values every time
+    // and are computed ONCE here, by the same LU solves.
+    if (!h->calib_lu_ready) {
+        const size_t sq = (size_t)h->nbp * h->nbp;
+        double* sig = dalloc(sq, c__->stream, false);
+        try {
+            GD_CUDA(cudaMemcpyAsync(sig, h->dSigRaw, sq * sizeof(double), cudaMemcpyDeviceToDevice, c__->stream));
+            invvar_calib_lu(h->T, h->C, h->dXb, h->nb, h->nbp, sig, 0.0 /* nugget already inside dSigRaw */, nullptr,
+                            &h->cov_mu_tau_lu, nullptr);
+        } catch (...) {
+            dfree(sig);
+            throw;
+        }
+        dfree(sig);
+        h->calib_lu_ready = true;
+    }
     SimRequest rq;
-    rq.want_cliff = true; rq.nsim = nsim; rq.seed = seed; rq.draw0 = draw0; rq.Z = Z;
+    rq.want_cliff = true; rq.want_lunum = true; rq.nsim = nsim; rq.seed = seed; rq.draw0 = draw0; rq.Z = Z;
     rq.chi_obs = INFINITY; rq.pval_obs = -1.0;
     std::vector<double> num(nsim);
-    rq.num = num.data();
+    rq.numlu = num.data();
     run_sims(h, rq);
-    const double sd = std::sqrt(null_cov_mu_tau(h, false));   // draw independent (hoisted)
+    const double sd = std::sqrt(h->cov_mu_tau_lu);
     for (long s = 0; s < nsim; ++s) pvals[s] = 2.0 * (std::erfc(std::fabs(num[s]) / sd * 0.7071067811865476) / 2.0);
     API_END
 }

@@ -73,12 +73,8 @@ template <bool A_MC, bool B_NC, bool B_XB = false>
 static void launch_t(cudaStream_t st, int M, int N, int K, double alpha, const double* A, long lda, const double* B,
                      long ldb, double beta, double* C, long ldc, int splitk, double* ws) {
     using ML = Mainloop<64, A_MC, B_NC, 3, ROWS_TMA, B_XB ? BLK_TMA : ROWS_TMA>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(gemm_kernel<A_MC, B_NC, B_XB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(ML::SMEM_BYTES + ML::BAR_WORDS * 8));
-        attr_set = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};
+    ensure_dyn_smem(gemm_kernel<A_MC, B_NC, B_XB>, ML::SMEM_BYTES + ML::BAR_WORDS * 8, attr_done);
     dim3 grid(M / TILE, N / 64, splitk);
     long ws_stride = (long)ldc * N;
     gemm_kernel<A_MC, B_NC, B_XB><<<grid, NTHREADS, ML::SMEM_BYTES + ML::BAR_WORDS * 8, st>>>(K, alpha, A, lda, B, ldb, beta, C, ldc, splitk, ws,

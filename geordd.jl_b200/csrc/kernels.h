@@ -3,6 +3,7 @@
 // TILE (128) in both dimensions unless noted.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 
 namespace geordd {
 
@@ -60,6 +61,19 @@ extern long long g_kernel_launches;
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device only, and one process may hold contexts on
+// several GPUs (geordd_ctx_create(out, device), the multi-device group of api_multi.cu): remember it per device, thread-safe.
+template <class F>
+inline void ensure_dyn_smem(F* fn, size_t bytes, std::atomic<unsigned long long>& done_mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(done_mask.load(std::memory_order_acquire) & bit)) {
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        done_mask.fetch_or(bit, std::memory_order_release);
+    }
+}
+
 // ---- cov.cu ---------------------------------------------------------------------------------------
 // K(i,j) = k(|x1_i - x2_j|) (+ diag_add on i==j when sym).  X1: dim x n1, X2: dim x n2 (column =
 // unit).  Output leading dimension ldk; rows/cols beyond n1/n2 up to the padded size (n1p, n2p) are
@@ -103,7 +117,10 @@ struct SolveEpilogue {
     //   dot0[rb*ncols + c] = sum_{r in block rb} (wmat(r,c) + (r < wrows ? wshift : 0)) * X(r,c)
     //   dot1[rb*ncols + c] = sum_{r in block rb} wvec[r] * X(r,c)
     //   dot_self: dot0 uses X itself as the weight (sum of squares of the solved block; wmat ignored)
-    const double* wmat = nullptr; long ldw = 0; double wshift = 0.0; int wrows = 0;
+    //   wlive: rows r >= wlive of this solve have NO row in the wmat buffer (the treated / control block of the pooled
+    //   residuals ends at m_T / m_C while the solve runs over the padded row count): they are not loaded, weight 0 --
+    //   the solution is exactly 0 there, so the partials are unchanged.
+    const double* wmat = nullptr; long ldw = 0; double wshift = 0.0; int wrows = 0; int wlive = 0x7fffffff;
     bool dot_self = false;
     double* dot0 = nullptr;
     const double* wvec = nullptr;

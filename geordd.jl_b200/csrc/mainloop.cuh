@@ -252,10 +252,18 @@ struct Mainloop {
             if (!mbar_wait(ring.full + s, (it_use / STAGES) & 1u, ring.abort_word)) return false;
             const unsigned token = compute(smem, s, acc);
             __syncwarp();
+#ifdef GEORDD_RELEASE_FENCE
+            // Textbook ordering (documented PTX): a proxy fence between this warp's generic-proxy fragment loads and the
+            // async-proxy refill that its arrival permits.  1-4 % slower than the data dependency below (round 1), kept as a
+            // build option (-DGEORDD_RELEASE_FENCE) for toolkits whose scheduling the dependency trick has not been checked on.
+            if (ANY_TMA) fence_proxy_async();
+            if (lane == 0) mbar_arrive(ring.empty + s);
+#else
             if (lane == 0) {
                 if (ANY_TMA) mbar_arrive_after(ring.empty + s, token & ring.zero);
                 else mbar_arrive(ring.empty + s);
             }
+#endif
             ++it_use;
             // Refill AFTER computing: the stage to refill held chunk kc-1, which the other warps have had a whole
             // chunk time to release -- refilling before the compute made every producer wait for the slowest warp

@@ -149,11 +149,8 @@ void launch_potrf(cudaStream_t st, Sched& sched, const double* A, double* L, lon
     const int T = npad / TILE;
     const int P = (Lpre && ptiles > 0 && ptiles <= T && ptiles <= npad_pre / TILE) ? ptiles : 0;
     const int njobs = T * (T + 1) / 2 - P * (P + 1) / 2;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(potrf_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM);
-        attr_set = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};
+    ensure_dyn_smem(potrf_dataflow_kernel, POTRF_SMEM, attr_done);
     if (sched.jobs_T != T || sched.jobs_P != P) {   // job table cached per (tile count, prefilled tiles)
         int2* hjobs = (int2*)malloc(sizeof(int2) * (njobs > 0 ? njobs : 1));
         build_potrf_jobs(T, P, hjobs);

@@ -33,6 +33,10 @@ void launch_finish_cliff(cudaStream_t st, const FinishCliff& f);
 void launch_frac_compare(cudaStream_t st, const double* ref, long nref, const double* x, long n, bool greater,
                          double* out);
 void launch_lu_solve(cudaStream_t st, double* A, long lda, int n, double* B, long ldb, int nrhs, int* info);
+// The same n x n system against nrhs right-hand sides split over CTAs; scratch: ceil(nrhs / cols_per_cta) * n * n doubles.
+void launch_lu_solve_multi(cudaStream_t st, const double* A, long lda, int n, double* scratch, double* B, long ldb, long nrhs,
+                           int cols_per_cta, int* info);
+void launch_colsum(cudaStream_t st, const double* M, long ld, int rows, long cols, double* out);
 void launch_fill(cudaStream_t st, double* p, long n, double v);
 void launch_copy2d(cudaStream_t st, double* dst, long ldd, const double* src, long lds, int rows, int cols, bool trans);
 void launch_add_diag(cudaStream_t st, double* A, long ld, int n, double v);

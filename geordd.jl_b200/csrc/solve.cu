@@ -196,7 +196,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) solve_dataflow_kernel(SolveParams
                     if (e.dot0) {
                         double w = x;
                         if (!e.dot_self) {
-                            w = __ldg(XB ? e.wmat + zb_off(r + e.wrow0, col, (int)e.ldw) : e.wmat + col * e.ldw + r);
+                            w = 0.0;
+                            if (r < e.wlive) w = __ldg(XB ? e.wmat + zb_off(r + e.wrow0, col, (int)e.ldw) : e.wmat + col * e.ldw + r);
                             if (r < e.wrows) w += e.wshift;
                         }
                         s0 += w * x;
@@ -222,11 +223,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) solve_dataflow_kernel(SolveParams
 
 template <int MODE, bool XB>
 static void launch_mode(cudaStream_t st, Sched& sched, const SolveParams& p) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(solve_dataflow_kernel<MODE, XB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM);
-        attr_set = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};
+    ensure_dyn_smem(solve_dataflow_kernel<MODE, XB>, SOLVE_SMEM, attr_done);
     int njobs = p.T * p.nslabs;
     int grid = 2 * sched.num_sms;
     if (grid > njobs) grid = njobs;
@@ -366,7 +364,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) solve_seq_kernel(const __grid_con
                 if (e.dot0) {
                     double w = x;
                     if (!e.dot_self) {
-                        w = __ldg(e.wmat + zb_off(r + e.wrow0, col, (int)e.ldw));
+                        w = 0.0;
+                        if (r < e.wlive) w = __ldg(e.wmat + zb_off(r + e.wrow0, col, (int)e.ldw));
                         if (r < e.wrows) w += e.wshift;
                     }
                     s0 += w * x;
@@ -390,11 +389,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) solve_seq_kernel(const __grid_con
 }
 
 void launch_solve_seq(cudaStream_t st, Sched& sched, const SolveSeqItem* items, int n, int ncols) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(solve_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM);
-        attr_set = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};
+    ensure_dyn_smem(solve_seq_kernel, SOLVE_SMEM, attr_done);
     SeqParams p;
     p.nsolves = n; p.nslabs = ncols / SLAB;
     p.flags = sched.flags; p.counter = sched.counter; p.abort_word = sched.abort_word;

@@ -230,11 +230,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_narrow_kernel(NarrowParams 
 
 template <int MODE>
 static void launch_narrow_mode(cudaStream_t st, Sched& sched, const NarrowParams& p) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(solve_narrow_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NARROW_SMEM);
-        attr_set = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};
+    ensure_dyn_smem(solve_narrow_kernel<MODE>, NARROW_SMEM, attr_done);
     int njobs = p.T * p.nslabs;
     int grid = sched.num_sms < njobs ? sched.num_sms : njobs;
     solve_narrow_kernel<MODE><<<grid, NTHREADS, NARROW_SMEM, st>>>(p); ++g_kernel_launches;

@@ -213,8 +213,19 @@ void launch_frac_compare(cudaStream_t st, const double* ref, long nref, const do
 // overwritten by its LU factors, B (n x nrhs) by the solution.  Partial pivoting picks the first
 // row of maximum modulus (idamax), scaling multiplies by the reciprocal pivot (dgetf2).
 // ---------------------------------------------------------------------------------------------------
+// Multi-CTA form (Asrc != nullptr): every CTA copies the same n x n matrix into its own scratch block, factors it
+// redundantly (identical pivots, identical factors: the elimination is deterministic) and solves its own chunk of
+// `cols_per_cta` right-hand sides -- lu(Sigma) \ mu_b for thousands of null draws (sim_invvar_calib!, src/hypotest_invvar.jl:138-147).
 __global__ void __launch_bounds__(1024) lu_solve_kernel(double* A, long lda, int n, double* B, long ldb, int nrhs,
-                                                        int* info) {
+                                                        int* info, const double* Asrc, long ldsrc, int cols_per_cta) {
+    if (Asrc) {
+        A += (long)blockIdx.x * lda * n;
+        for (long idx = threadIdx.x; idx < (long)n * n; idx += blockDim.x) A[(idx / n) * lda + idx % n] = Asrc[(idx / n) * ldsrc + idx % n];
+        B += (long)blockIdx.x * cols_per_cta * ldb;
+        nrhs = min(cols_per_cta, nrhs - (int)blockIdx.x * cols_per_cta);
+        if (blockIdx.x != 0) info = nullptr;
+        __syncthreads();
+    }
     __shared__ double sval[32];
     __shared__ int sidx[32];
     __shared__ int spiv;
@@ -243,7 +254,7 @@ __global__ void __launch_bounds__(1024) lu_solve_kernel(double* A, long lda, int
             }
             if (tid == 0) {
                 spiv = bi;
-                if (!(best > 0.0) && *info == 0) *info = k + 1;
+                if (info && !(best > 0.0) && *info == 0) *info = k + 1;
             }
         }
         __syncthreads();
@@ -297,7 +308,25 @@ __global__ void __launch_bounds__(1024) lu_solve_kernel(double* A, long lda, int
 }
 void launch_lu_solve(cudaStream_t st, double* A, long lda, int n, double* B, long ldb, int nrhs, int* info) {
     cudaMemsetAsync(info, 0, sizeof(int), st);
-    lu_solve_kernel<<<1, 1024, 0, st>>>(A, lda, n, B, ldb, nrhs, info); ++g_kernel_launches;
+    lu_solve_kernel<<<1, 1024, 0, st>>>(A, lda, n, B, ldb, nrhs, info, nullptr, 0, 0); ++g_kernel_launches;
+}
+void launch_lu_solve_multi(cudaStream_t st, const double* A, long lda, int n, double* scratch, double* B, long ldb, long nrhs,
+                           int cols_per_cta, int* info) {
+    cudaMemsetAsync(info, 0, sizeof(int), st);
+    const int ctas = (int)((nrhs + cols_per_cta - 1) / cols_per_cta);
+    lu_solve_kernel<<<ctas, 1024, 0, st>>>(scratch, n, n, B, ldb, (int)nrhs, info, A, lda, cols_per_cta); ++g_kernel_launches;
+}
+
+// out[c] = sum_{r < rows} M(r, c), rows summed in order (one thread per column; rows <= a few hundred)
+__global__ void colsum_kernel(const double* __restrict__ M, long ld, int rows, long cols, double* __restrict__ out) {
+    long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    double s = 0.0;
+    for (int r = 0; r < rows; ++r) s += M[c * ld + r];
+    out[c] = s;
+}
+void launch_colsum(cudaStream_t st, const double* M, long ld, int rows, long cols, double* out) {
+    if (cols > 0) colsum_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, st>>>(M, ld, rows, cols, out); ++g_kernel_launches;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -699,7 +699,9 @@ def boot_chi2test(gpT: GPE, gpC: GPE, Xb, nsim: int, **kw) -> float:
     chi_obs = chistat(gpT, gpC, Xb)
     total = np.asarray(kw["Z"]).shape[1] if kw.get("Z") is not None else int(nsim)
     local, kw, reduce_ = _draw_shard(total, kw)
-    _, cnt = nsim_chi(gpT, gpC, gpNull, Xb, local, chi_obs=chi_obs, return_count=True, **kw)
+    cnt = 0                                   # a rank whose shard is empty (world > nsim) still joins the all-reduce
+    if local > 0:
+        _, cnt = nsim_chi(gpT, gpC, gpNull, Xb, local, chi_obs=chi_obs, return_count=True, **kw)
     return reduce_(cnt) / total
 
 
@@ -732,7 +734,9 @@ def boot_invvar(gpT: GPE, gpC: GPE, Xb, nsim: int, nugget: float = 1e-10, **kw) 
     pobs = pval_invvar_uncalib(gpT, gpC, Xb, nugget)
     total = np.asarray(kw["Z"]).shape[1] if kw.get("Z") is not None else int(nsim)
     local, kw, reduce_ = _draw_shard(total, kw)
-    _, cnt = nsim_invvar_pval_uncalib(gpT, gpC, Xb, local, nugget, pval_obs=pobs, return_count=True, **kw)
+    cnt = 0
+    if local > 0:
+        _, cnt = nsim_invvar_pval_uncalib(gpT, gpC, Xb, local, nugget, pval_obs=pobs, return_count=True, **kw)
     return reduce_(cnt) / total
 
 
@@ -746,8 +750,9 @@ def pval_invvar_calib(gpT: GPE, gpC: GPE, Xb, nugget: float = 1e-10) -> float:
 
 def nsim_invvar_calib(gpT: GPE, gpC: GPE, Xb, nsim: int, nugget: float = 1e-10, *, seed: int = 0, draw0: int = 0, Z=None,
                       gpNull: Optional[NullGPE] = None) -> np.ndarray:
-    """nsim_invvar_calib(gpT, gpC, Xb, nsim) (src/hypotest_invvar.jl:138-160): the analytically calibrated p-value of
-    every null draw (the draw-independent covariance term is computed once)."""
+    """nsim_invvar_calib(gpT, gpC, Xb, nsim) (src/hypotest_invvar.jl:138-160): the analytically calibrated p-value
+    (3-argument pval_invvar_calib: LU of Sigma_b + nugget) of every null draw; the draw-independent LU and covariance
+    term are computed once instead of per draw, by the same solves."""
     gpNull = gpNull or make_null(gpT, gpC)
     gpNull._ensure(Xb, nugget)
     Zf, nz = _zarg(Z, gpNull.nobs)
@@ -784,7 +789,9 @@ def boot_mlltest(gpT: GPE, gpC: GPE, nsim: int, **kw) -> float:
     d_obs = mll_alt - gpNull.mll
     total = np.asarray(kw["Z"]).shape[1] if kw.get("Z") is not None else int(nsim)
     local, kw, reduce_ = _draw_shard(total, kw)
-    _, cnt, _, _ = nsim_logP(gpT, gpC, gpNull, local, dmll_obs=d_obs, return_count=True, **kw)
+    cnt = 0
+    if local > 0:
+        _, cnt, _, _ = nsim_logP(gpT, gpC, gpNull, local, dmll_obs=d_obs, return_count=True, **kw)
     return reduce_(cnt) / total
 
 
@@ -1037,8 +1044,51 @@ class GPRealisations:
 # Placebo drivers (src/placebo_geometry.jl + src/hypotest_*.jl placebo_*): O(n) host geometry feeding the
 # GPU tests.  Thin wrappers, SURVEY §8 a15.
 # ----------------------------------------------------------------------------------------------
-def _tand(a):
-    return math.tan(math.radians(a))
+def _sind(x: float) -> float:
+    """Base.sind: argument reduction in DEGREES, so that multiples of 90 are exact (sind(180) == 0)."""
+    rx = math.copysign(math.fmod(x, 360.0), x)
+    arx = abs(rx)
+    if rx == 0.0:
+        return rx
+    if arx < 45.0:
+        return math.sin(math.radians(rx))
+    if arx <= 135.0:
+        return math.copysign(math.cos(math.radians(90.0 - arx)), rx)
+    if arx == 180.0:
+        return math.copysign(0.0, rx)
+    if arx < 225.0:
+        return math.sin(math.radians((180.0 - arx) * math.copysign(1.0, rx)))
+    if arx <= 315.0:
+        return -math.copysign(math.cos(math.radians(270.0 - arx)), rx)
+    return math.sin(math.radians(rx - math.copysign(360.0, rx)))
+
+
+def _cosd(x: float) -> float:
+    """Base.cosd: cosd(90) == cosd(270) == 0 exactly."""
+    rx = abs(math.fmod(x, 360.0))
+    if rx <= 45.0:
+        return math.cos(math.radians(rx))
+    if rx < 135.0:
+        return math.sin(math.radians(90.0 - rx))
+    if rx <= 225.0:
+        return -math.cos(math.radians(180.0 - rx))
+    if rx < 315.0:
+        return math.sin(math.radians(rx - 270.0))
+    return math.cos(math.radians(360.0 - rx))
+
+
+def _tand(x: float) -> float:
+    """Base.tand = sind / cosd: tand(45) == 1.0 exactly (the `abs(dydx) < 1` branch of left_points depends on it),
+    tand(90) == Inf."""
+    s, c = _sind(x), _cosd(x)
+    if c == 0.0:
+        return math.copysign(math.inf, s) if s != 0.0 else math.nan
+    return s / c
+
+
+def _placebo_direction(angle: float) -> float:
+    d = _cosd(angle + 90.0)
+    return 1.0 if d == 0.0 else math.copysign(1.0, d)
 
 
 def left_points(angle: float, shift: float, X) -> np.ndarray:
@@ -1046,11 +1096,9 @@ def left_points(angle: float, shift: float, X) -> np.ndarray:
     X = np.asarray(X)
     dydx = _tand(angle)
     meanx, meany = float(np.mean(X[0])), float(np.mean(X[1]))
-    direction = np.sign(math.cos(math.radians(angle + 90)))
-    if direction == 0.0:
-        direction = 1.0
-    sx = shift * math.cos(math.radians(angle + 90)) * direction
-    sy = shift * math.sin(math.radians(angle + 90)) * direction
+    direction = _placebo_direction(angle)
+    sx = shift * _cosd(angle + 90.0) * direction
+    sy = shift * _sind(angle + 90.0) * direction
     ax, ay = meanx + sx, meany + sy
     if abs(dydx) < 1.0:
         dx, dy = 1.0, dydx
@@ -1095,16 +1143,16 @@ def placebo_sentinels(angle: float, shift: float, X, npoints: int) -> np.ndarray
     minx, maxx = float(X[0].min()), float(X[0].max())
     miny, maxy = float(X[1].min()), float(X[1].max())
     dydx = _tand(angle)
-    direction = np.sign(math.cos(math.radians(angle + 90))) or 1.0
-    cx = meanx + shift * math.cos(math.radians(angle + 90)) * direction
-    cy = meany + shift * math.sin(math.radians(angle + 90)) * direction
+    direction = _placebo_direction(angle)
+    cx = meanx + shift * _cosd(angle + 90.0) * direction
+    cy = meany + shift * _sind(angle + 90.0) * direction
     ext = []
     y0, y1 = cy + dydx * (minx - cx), cy + dydx * (maxx - cx)
     if miny < y0 < maxy:
         ext.append((minx, y0))
     if miny < y1 < maxy:
         ext.append((maxx, y1))
-    if dydx != 0.0:
+    if dydx != 0.0:                       # the reference divides unconditionally: +-Inf / NaN fail both comparisons
         x0, x1 = cx + (miny - cy) / dydx, cx + (maxy - cy) / dydx
         if minx < x0 < maxx:
             ext.append((x0, miny))

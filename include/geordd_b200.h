@@ -165,9 +165,11 @@ GEORDD_API int geordd_null_chi2(geordd_null* h, long nsim, unsigned long long se
 /* nsim_invvar_pval_uncalib / boot_invvar (src/hypotest_invvar.jl:11-69): pvals, n_below = #{p < pval_obs}. */
 GEORDD_API int geordd_null_invvar(geordd_null* h, long nsim, unsigned long long seed, unsigned long long draw0, const double* Z,
                        double pval_obs, double* pvals, long long* n_below);
-/* sim_invvar_calib! / nsim_invvar_calib (src/hypotest_invvar.jl:138-160): analytically calibrated p-value of every
- * draw, 2 ccdf(Normal(0, sqrt(cov_mu_tau)), |sum(Sigma_b \ mu_b)|).  The draw-independent cov_mu_tau (:88-99) is
- * computed once; Sigma_b is the handle's make_posdef!-factored (Sigma + nugget I) (prepare with nugget = 1e-10). */
+/* sim_invvar_calib! / nsim_invvar_calib (src/hypotest_invvar.jl:138-160): the 3-argument pval_invvar_calib (:74-105) of
+ * every null draw, 2 ccdf(Normal(0, sqrt(cov_mu_tau)), |sum(Sigma_b \ mu_b)|), with Sigma_b the un-jittered cliff covariance
+ * + nugget solved by LU exactly as the reference's generic `\` does.  Only mu_b depends on the draw: the LU of Sigma_b is
+ * formed once per CTA and cov_mu_tau (:88-99) once per handle (the reference recomputes both per draw, to the same values).
+ * Prepare the handle with nugget = 1e-10 (the reference's default). */
 GEORDD_API int geordd_null_invvar_calib(geordd_null* h, long nsim, unsigned long long seed, unsigned long long draw0,
                              const double* Z, double* pvals);
 /* sim_logP! / nsim_logP / boot_mlltest (src/hypotest_mll.jl:1-45): mll_null, mll_alt (nsim, nullable),

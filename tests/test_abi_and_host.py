@@ -76,6 +76,25 @@ def test_placebo_geometry(G):
         assert side.sum() in (int(left.sum()), 401 - int(left.sum()))
 
 
+def test_placebo_geometry_matches_oracle_and_exact_degree_trig(G, O):
+    """src/placebo_geometry.jl uses tand / cosd / sind: exact at the special angles the notebook sweep `1:2:180` hits
+    (tand(45) == 1 puts 45 deg in the `else` branch of left_points; cosd(90) == 0 makes `direction` fall back to 1).
+    The host mirror (libm on the degree-reduced argument) against the oracle (mpmath on the exact degree value)."""
+    assert G.geordd._tand(45.0) == 1.0 == O.tand(45.0) and G.geordd._tand(135.0) == -1.0 == O.tand(135.0)
+    assert G.geordd._cosd(90.0) == 0.0 == O.cosd(90.0) and G.geordd._cosd(270.0) == 0.0 and G.geordd._sind(180.0) == 0.0
+    assert G.geordd._tand(90.0) == math.inf == O.tand(90.0) and G.geordd._sind(30.0) == pytest.approx(0.5, abs=1e-16)
+    for a in np.arange(-30.0, 400.0, 7.5):
+        assert G.geordd._sind(a) == pytest.approx(O.sind(a), abs=2e-16) and G.geordd._cosd(a) == pytest.approx(O.cosd(a), abs=2e-16)
+    rng = np.random.default_rng(5)
+    X = np.asfortranarray(rng.random((2, 260)) * np.array([[3.0], [1.0]]) + np.array([[10.0], [-2.0]]))
+    for angle in [float(a) for a in range(1, 180, 2)] + [0.0, 90.0, 180.0, 44.99]:
+        sg, so = G.shift_for_even_split(angle, X), O.shift_for_even_split(angle, X)
+        assert sg == so, (angle, sg, so)
+        assert np.array_equal(G.left_points(angle, sg, X), O.left_points(angle, so, X))
+        bg, bo = G.placebo_sentinels(angle, sg, X, 100), O.placebo_sentinels(angle, so, X, 100)
+        assert np.max(np.abs(bg - bo)) < 1e-14
+
+
 def test_residuals_and_normal(G):
     rd = G.RegionData(np.zeros((2, 3)), np.array([1.0, 2.0, 3.0]), np.array([[1.0, 1.0, 1.0], [0.0, 1.0, 2.0]]))
     r = G.residuals_data(rd, [0.5, 1.0])
