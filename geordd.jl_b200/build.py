@@ -18,10 +18,12 @@ def _newer(src, dst):
     return (not os.path.exists(dst)) or os.path.getmtime(src) > os.path.getmtime(dst)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), suffix=""):
+    """defines / suffix: kernel experiments -- e.g. build(defines=["GEORDD_POTRF_NO_LOOKAHEAD"], suffix="_nola") makes
+    lib/libgeordd_b200_nola.so beside the product library (select it at run time with GEORDD_B200_LIB)."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" + suffix)
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(HERE, "..", "include", "geordd_b200.h"))
@@ -32,7 +34,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(objdir, s.replace(".cu", ".o"))
         objs.append(obj)
         if force or _newer(src, obj) or hdr_time > os.path.getmtime(obj):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for s, p in procs:
         out, _ = p.communicate()
@@ -40,11 +42,12 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {s}")
-    if procs or not os.path.exists(LIB):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static",
+    lib = LIB if not suffix else LIB.replace(".so", suffix + ".so")
+    if procs or not os.path.exists(lib):
+        cmd = [nvcc, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static",
                                                       "-Xcompiler", "-fPIC"]
         subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

@@ -58,6 +58,9 @@ _SIGS = {
                                    c_double_p]),
     "geordd_gp_fit": (C.c_int, [C.c_void_p, C.POINTER(Kernel), c_double_p, C.c_int, C.c_int, c_double_p, C.c_double,
                                 c_void_pp, c_double_p, c_double_p, c_double_p, c_int_p]),
+    "geordd_gp_fit_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Kernel), C.POINTER(c_double_p), C.c_int, c_int_p,
+                                      C.POINTER(c_double_p), c_double_p, c_void_pp, C.POINTER(c_double_p), c_double_p, c_int_p,
+                                      c_int_p]),
     "geordd_gp_set_y": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p]),
     "geordd_gp_predict_mu": (C.c_int, [C.c_void_p, c_double_p, C.c_int, c_double_p]),
     "geordd_gp_get_K": (C.c_int, [C.c_void_p, c_double_p]),

@@ -260,10 +260,10 @@ static void gp_set_resid(geordd_gp* gp, const double* y) {
     GD_CUDA(cudaStreamSynchronize(c->stream));
 }
 
-geordd_gp* gp_create(geordd_ctx* c, const geordd_kernel* k, const double* X, int dim, int n, const double* y,
-                     double log_noise, int* info_out, const geordd_gp* lead) {
+// Phase 1 of a fit: allocate, upload the coordinates, assemble K + (exp(2 logNoise) + eps) I  (K1).
+static geordd_gp* gp_alloc_assemble(geordd_ctx* c, const geordd_kernel* k, const double* X, int dim, int n, double log_noise) {
     check_kernel(k);
-    if (!X || !y || n <= 0 || dim <= 0 || dim > 8) throw ApiError(GEORDD_ERR_ARG, "gp_fit: bad X / y / n / dim (1..8)");
+    if (!X || n <= 0 || dim <= 0 || dim > 8) throw ApiError(GEORDD_ERR_ARG, "gp_fit: bad X / y / n / dim (1..8)");
     geordd_gp* gp = new geordd_gp();
     try {
         gp->ctx = c; gp->k = *k; gp->log_noise = log_noise; gp->n = n; gp->dim = dim;
@@ -277,11 +277,29 @@ geordd_gp* gp_create(geordd_ctx* c, const geordd_kernel* k, const double* X, int
         gp->dAlpha = dalloc(np * 64, c->stream, true);
         GD_CUDA(cudaMemcpyAsync(gp->dX, X, (size_t)dim * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         const double noise = std::exp(2.0 * log_noise) + 2.220446049250313e-16;   // exp(2 logNoise) + eps()
-        {
-            ProfScope ps(c, PC_COV);
-            launch_cov(c->stream, to_dev(*k), gp->dX, n, gp->dX, n, dim, true, false, noise, gp->dK, np, gp->npad,
-                       gp->npad, false);
-        }
+        ProfScope ps(c, PC_COV);
+        launch_cov(c->stream, to_dev(*k), gp->dX, n, gp->dX, n, dim, true, false, noise, gp->dK, np, gp->npad, gp->npad, false);
+    } catch (...) {
+        gp_free(gp);
+        throw;
+    }
+    return gp;
+}
+
+// Phase 3: log-determinant, alpha = cK \ (y - m), mll.
+static void gp_finish(geordd_gp* gp, const double* y) {
+    geordd_ctx* c = gp->ctx;
+    launch_logdiag_sum(c->stream, gp->dL, gp->npad, gp->n, c->d_scal + 1);
+    gp->logdet = 2.0 * read_scalar(c, c->d_scal + 1);
+    gp_set_resid(gp, y);
+    gp_update_alpha(gp);
+}
+
+geordd_gp* gp_create(geordd_ctx* c, const geordd_kernel* k, const double* X, int dim, int n, const double* y,
+                     double log_noise, int* info_out, const geordd_gp* lead) {
+    if (!y) throw ApiError(GEORDD_ERR_ARG, "gp_fit: bad X / y / n / dim (1..8)");
+    geordd_gp* gp = gp_alloc_assemble(c, k, X, dim, n, log_noise);
+    try {
         // leading block already factored?  Same units, kernel and noise, and that fit needed no jitter.
         const double* Lpre = nullptr;
         int ptiles = 0;
@@ -291,21 +309,67 @@ geordd_gp* gp_create(geordd_ctx* c, const geordd_kernel* k, const double* X, int
             Lpre = lead->dL;
             ptiles = lead->n / TILE;   // tiles entirely inside the leading block
         }
-        int info = make_posdef(c, gp->dK, gp->dL, np, n, gp->npad, &gp->jitter_rounds, Lpre, lead ? lead->npad : 0, ptiles);
+        int info = make_posdef(c, gp->dK, gp->dL, gp->npad, n, gp->npad, &gp->jitter_rounds, Lpre, lead ? lead->npad : 0, ptiles);
         if (info_out) *info_out = info;
         if (info != 0) {
             gp_free(gp);
             return nullptr;
         }
-        launch_logdiag_sum(c->stream, gp->dL, np, n, c->d_scal + 1);
-        gp->logdet = 2.0 * read_scalar(c, c->d_scal + 1);
-        gp_set_resid(gp, y);
-        gp_update_alpha(gp);
+        gp_finish(gp, y);
     } catch (...) {
         gp_free(gp);
         throw;
     }
     return gp;
+}
+
+// Several independent fits (the regions of GPRealisations, the halves of a placebo split): all covariance matrices are
+// assembled first, then factored by ONE dataflow launch whose merged job list interleaves their critical paths
+// (potrf.cu).  A batch in which any matrix needs make_posdef! jitter is redone matrix by matrix (rare).
+// On return gps[] holds the fitted GPs; a failed fit leaves nullptr there and its LAPACK info in infos[].
+void gp_create_batch(geordd_ctx* c, int nfit, const geordd_kernel* ks, const double* const* Xs, int dim, const int* ns,
+                     const double* const* ys, const double* log_noise, geordd_gp** gps, int* infos) {
+    for (int f = 0; f < nfit; ++f) { gps[f] = nullptr; infos[f] = 0; }
+    try {
+        for (int f = 0; f < nfit; ++f) {
+            if (!ys[f]) throw ApiError(GEORDD_ERR_ARG, "gp_fit_batch: y is NULL");
+            gps[f] = gp_alloc_assemble(c, &ks[f], Xs[f], dim, ns[f], log_noise[f]);
+        }
+        bool fallback = false;
+        for (int f0 = 0; f0 < nfit && !fallback; f0 += POTRF_MAX_BATCH) {
+            const int nm = std::min(POTRF_MAX_BATCH, nfit - f0);
+            PotrfItem items[POTRF_MAX_BATCH];
+            for (int m = 0; m < nm; ++m) items[m] = PotrfItem{gps[f0 + m]->dK, gps[f0 + m]->dL, gps[f0 + m]->npad, gps[f0 + m]->npad, nullptr, 0, 0};
+            int rc;
+            {
+                ProfScope ps(c, PC_POTRF);
+                rc = launch_potrf_batch(c->stream, c->sched, items, nm);
+            }
+            if (rc != 0) { fallback = true; break; }
+            GD_CUDA(cudaMemcpyAsync(c->h_info, c->sched.abort_word, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            GD_CUDA(cudaStreamSynchronize(c->stream));
+            GD_CUDA(cudaGetLastError());
+            const int info = c->h_info[0];
+            if (info != 0) GD_CUDA(cudaMemsetAsync(c->sched.abort_word, 0, sizeof(int), c->stream));
+            if (info < 0) throw ApiError(GEORDD_ERR_WATCHDOG, "potrf watchdog fired");
+            if (info > 0) fallback = true;
+        }
+        for (int f = 0; f < nfit; ++f) {
+            geordd_gp* gp = gps[f];
+            if (fallback) {
+                infos[f] = make_posdef(c, gp->dK, gp->dL, gp->npad, gp->n, gp->npad, &gp->jitter_rounds);
+                if (infos[f] != 0) { gp_free(gp); gps[f] = nullptr; continue; }
+            } else {
+                gp->jitter_rounds = 0;
+                ProfScope ps(c, PC_MISC);
+                launch_mirror_factor(c->stream, gp->dL, gp->npad);
+            }
+            gp_finish(gp, ys[f]);
+        }
+    } catch (...) {
+        for (int f = 0; f < nfit; ++f) { if (gps[f]) gp_free(gps[f]); gps[f] = nullptr; }
+        throw;
+    }
 }
 
 void gp_ensure_full_K(geordd_gp* gp) {
@@ -526,6 +590,31 @@ int geordd_gp_fit(geordd_ctx* c, const geordd_kernel* k, const double* X, int di
     }
     GD_CUDA(cudaStreamSynchronize(c->stream));
     *out = gp;
+    API_END
+}
+
+int geordd_gp_fit_batch(geordd_ctx* c, int nfit, const geordd_kernel* k, const double* const* X, int dim, const int* n,
+                        const double* const* y, const double* log_noise, geordd_gp** out, double* const* alpha, double* mll,
+                        int* jitter_rounds, int* info) {
+    if (out) for (int f = 0; f < nfit; ++f) out[f] = nullptr;
+    API_BEGIN(c)
+    if (!out || nfit <= 0 || !k || !X || !n || !y || !log_noise) throw ApiError(GEORDD_ERR_ARG, "gp_fit_batch: bad arguments");
+    std::vector<int> infos(nfit, 0);
+    gp_create_batch(c, nfit, k, X, dim, n, y, log_noise, out, infos.data());
+    int first_bad = 0;
+    for (int f = 0; f < nfit; ++f) {
+        if (info) info[f] = infos[f];
+        if (!out[f]) { if (!first_bad) first_bad = infos[f] ? infos[f] : GEORDD_ERR_CUDA; continue; }
+        if (alpha && alpha[f]) GD_CUDA(cudaMemcpyAsync(alpha[f], out[f]->dAlpha, (size_t)n[f] * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if (mll) mll[f] = out[f]->mll;
+        if (jitter_rounds) jitter_rounds[f] = out[f]->jitter_rounds;
+    }
+    GD_CUDA(cudaStreamSynchronize(c->stream));
+    if (first_bad != 0) {   // like GPRealisations' constructor, which throws on the first region that is not positive definite
+        for (int f = 0; f < nfit; ++f) { if (out[f]) gp_free(out[f]); out[f] = nullptr; }
+        c->err = "matrix is not positive definite; Cholesky factorization failed";
+        return first_bad;
+    }
     API_END
 }
 

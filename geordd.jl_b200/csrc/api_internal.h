@@ -175,6 +175,8 @@ int pick_splitk(geordd_ctx* c, int M, int N, int K);
 // of its factor that lie inside the leading block are reused (make_null: pooled = [treated control]).
 geordd_gp* gp_create(geordd_ctx* c, const geordd_kernel* k, const double* X, int dim, int n, const double* y,
                      double log_noise, int* info_out, const geordd_gp* lead = nullptr);
+void gp_create_batch(geordd_ctx* c, int nfit, const geordd_kernel* ks, const double* const* Xs, int dim, const int* ns,
+                     const double* const* ys, const double* log_noise, geordd_gp** gps, int* infos);
 void gp_update_alpha(geordd_gp* gp);   // alpha from dR, mll
 void gp_free(geordd_gp* gp);
 void gp_ensure_full_K(geordd_gp* gp);

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <atomic>
+#include <vector>
 
 namespace geordd {
 
@@ -51,8 +52,8 @@ struct Sched {
     unsigned epoch;      // host-side launch epoch (monotone)
     int2* jobs;          // device job table scratch
     size_t jobs_cap;
-    int jobs_T = 0;      // tile count the cached potrf job table was built for
-    int jobs_P = 0;      // ... and its number of prefilled leading tiles
+    std::vector<int> jobs_key;   // (tiles, prefilled tiles) per matrix of the batch the cached potrf job table was built for
+    int jobs_count = 0;
     int num_sms;
 };
 
@@ -94,6 +95,14 @@ void launch_cov(cudaStream_t st, const KernelSpecDev& spec, const double* X1, in
 // are deterministic, so the result is bit-identical to a full factorisation.
 void launch_potrf(cudaStream_t st, Sched& sched, const double* A, double* L, long ld, int npad, const double* Lpre = nullptr,
                   int npad_pre = 0, int ptiles = 0);
+// Several independent factorisations as ONE launch over a merged job list (their critical paths interleave).  The abort word
+// of a failed batch holds (matrix index << 24) | LAPACK info.  Returns -1 if the batch does not fit the scheduling scratch.
+constexpr int POTRF_MAX_BATCH = 64;
+struct PotrfItem {
+    const double* A; double* L; long ld; int npad;
+    const double* Lpre; int npad_pre; int ptiles;
+};
+int launch_potrf_batch(cudaStream_t st, Sched& sched, const PotrfItem* items, int nm);
 // dense (n x n column-major, ldd) lower triangle -> TBP factor with identity padding; and back (optionally transposed).
 void launch_factor_pack(cudaStream_t st, const double* dense, long ldd, int n, double* L, int npad);
 void launch_factor_unpack(cudaStream_t st, const double* L, int npad, double* dense, long ldd, int n, bool transpose);

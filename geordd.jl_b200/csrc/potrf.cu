@@ -7,9 +7,21 @@
 //     i == j :  L_jj = chol(acc)                (in shared memory)
 //     i >  j :  L_ij = acc * L_jj^-T            (in shared memory)
 // so every tile of L is written exactly once (left-looking per tile).  Jobs are handed out in
-// column-major order by an atomic counter; a job only ever waits (acquire-polling a per-tile flag)
+// column-major order by an atomic counter; a job only ever waits (acquire-polling per-tile flags)
 // on jobs with a smaller index, which are already running on resident CTAs, hence no deadlock and no
 // cooperative launch.  No host round trips, no per-panel launches, natural look-ahead.
+//
+// Round 2, two changes aimed at the critical path (one chain link per tile column: last update of the diagonal tile ->
+// potrf_tile -> right solve of the sub-diagonal tile; 75 us per column in round 1, which bounds every n <= 8k):
+//  * SUB-TILE FLAGS.  Besides its tile flag every tile has four block-column flags.  potrf_tile and trsm_right_tile publish
+//    each 32-column block as soon as it is final (tileops.cuh), the right solve waits per block of the diagonal tile, and
+//    the K loop waits per block (two 16-column chunks) of its operand tiles whenever the whole tile is not complete yet.
+//    The three links of the chain now overlap as a pipeline with four stages per tile.  Arithmetic and its order are
+//    unchanged (same jobs, same tile operations), so factors stay bit-identical to round 1's and to each other.
+//  * BATCHES.  Several independent matrices (the regions of GPRealisations, src/GPrealisations.jl:10-19; the two halves of
+//    a placebo split) are factored by ONE launch over a merged job list: their critical paths interleave on SMs that a
+//    single small factorisation leaves idle.
+#include <vector>
 #include "kernels.h"
 #include "mainloop.cuh"
 #include "tileops.cuh"
@@ -19,14 +31,29 @@ namespace geordd {
 // Flagged dataflow kernel: both operands are moved with generic-proxy block copies (see the stage-release note in mainloop.cuh).
 using PotrfML = Mainloop<128, /*A_MC=*/true, /*B_NC=*/true, 4, BLK_GEN, BLK_GEN>;
 constexpr int CHUNKS_PER_TILE = TILE / BK;
+constexpr int SUBS = TILE / NB;   // block-column flags per tile
+
+struct PotrfMat {
+    const double* A;   // npad x npad column-major, lower triangle read
+    double* L;         // TBP factor storage
+    long ld;
+    int T;             // tiles per dimension
+    int flag_off;      // first flag word of this matrix: T*T tile flags, then T*T*SUBS block-column flags
+};
+struct PotrfBatch {
+    int nm;
+    PotrfMat m[POTRF_MAX_BATCH];
+};
 
 struct PotrfSrc {
     const double* L;
     long lda, ldb;
     int i, j, T;
-    const unsigned* flags;
+    const unsigned* tflags;
+    const unsigned* sflags;
     unsigned epoch;
     int* abort_word;
+    bool tile_ok;   // (per warp) both operand tiles of the current K tile are complete
     // chunk c = columns [16c, 16c+16) of block row i (A) / j (B): 16 consecutive columns of one TBP tile
     __device__ __forceinline__ const double* a_ptr(int c) const {
         return L + tile_off(i, c / CHUNKS_PER_TILE, T) + (long)(c % CHUNKS_PER_TILE) * BK * TLD;
@@ -34,10 +61,17 @@ struct PotrfSrc {
     __device__ __forceinline__ const double* b_ptr(int c) const {
         return L + tile_off(j, c / CHUNKS_PER_TILE, T) + (long)(c % CHUNKS_PER_TILE) * BK * TLD;
     }
-    __device__ __forceinline__ bool ready(int c) const {   // warp level
-        if (c % CHUNKS_PER_TILE != 0) return true;
-        int kt = c / CHUNKS_PER_TILE;
-        return warp_wait_flags(flags + (long)i * T + kt, i != j ? flags + (long)j * T + kt : nullptr, epoch, abort_word);
+    __device__ __forceinline__ bool ready(int c) {   // warp level; chunks are requested in increasing order
+        if (c & 1) return true;
+        const int kt = c / CHUNKS_PER_TILE, b = (c % CHUNKS_PER_TILE) >> 1;
+        const long ta = (long)i * T + kt, tb = (long)j * T + kt;
+        if (b == 0) {   // whole tiles already complete (the common case away from the critical path)?
+            bool ok = ld_acquire(tflags + ta) == epoch;
+            if (i != j) ok = ok && ld_acquire(tflags + tb) == epoch;
+            tile_ok = __all_sync(0xffffffffu, ok) != 0;
+        }
+        if (tile_ok) return true;
+        return warp_wait_flags(sflags + ta * SUBS + b, i != j ? sflags + tb * SUBS + b : nullptr, epoch, abort_word);
     }
 };
 
@@ -45,10 +79,11 @@ constexpr int POTRF_CS_ELEMS = TILE * SC;
 constexpr int POTRF_LP_ELEMS = NB * SC;
 constexpr size_t POTRF_SMEM = (size_t)(POTRF_CS_ELEMS + 2 * POTRF_LP_ELEMS + TILE + PotrfML::BAR_WORDS) * sizeof(double);
 static_assert(PotrfML::SMEM_BYTES <= POTRF_CS_ELEMS * sizeof(double), "stage ring must fit under the C tile");
+static_assert(SC == TLD, "the shared-memory C tile and the stored tile image share one layout");
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-potrf_dataflow_kernel(const double* __restrict__ A, double* __restrict__ L, long ld, int T, const int2* __restrict__ jobs,
-                      int njobs, unsigned* flags, unsigned epoch, unsigned* counter, int* abort_word) {
+potrf_dataflow_kernel(const __grid_constant__ PotrfBatch pb, const int2* __restrict__ jobs, int njobs, unsigned* flags,
+                      unsigned epoch, unsigned* counter, int* abort_word) {
     extern __shared__ __align__(16) double smem[];
     double* Cs = smem;                       // aliases the mainloop stage ring
     double* Lp = smem + POTRF_CS_ELEMS;
@@ -71,7 +106,14 @@ potrf_dataflow_kernel(const double* __restrict__ A, double* __restrict__ L, long
         const int job = sh_job;
         if (job >= njobs) break;
         const int2 ij = jobs[job];
-        const int i = ij.x, j = ij.y;
+        const int mat = ij.x >> 16, i = ij.x & 0xffff, j = ij.y;
+        const PotrfMat& M = pb.m[mat];
+        const double* __restrict__ A = M.A;
+        double* __restrict__ L = M.L;
+        const long ld = M.ld;
+        const int T = M.T;
+        unsigned* tflags = flags + M.flag_off;
+        unsigned* sflags = tflags + (long)T * T;
 
         PotrfML::Acc acc;
         {   // acc = -A_ij  (issued first so the loads overlap the pipeline prologue)
@@ -84,7 +126,7 @@ potrf_dataflow_kernel(const double* __restrict__ A, double* __restrict__ L, long
                     for (int e = 0; e < 2; ++e)
                         acc.v[a][b][e] = -ldcg(Aij + (long)PotrfML::acc_col(b, e) * ld + PotrfML::acc_row(a));
         }
-        PotrfSrc src{L, 0, 0, i, j, T, flags, epoch, abort_word};
+        PotrfSrc src{L, 0, 0, i, j, T, tflags, sflags, epoch, abort_word, false};
         bool ok = PotrfML::run(smem, ring, j * CHUNKS_PER_TILE, src, acc);
         if (__syncthreads_or(!ok)) break;   // also: every warp is done reading the ring before Cs overwrites it
 #pragma unroll
@@ -97,40 +139,30 @@ potrf_dataflow_kernel(const double* __restrict__ A, double* __restrict__ L, long
         __syncthreads();
 
         double* Lij = L + tile_off(i, j, T);   // stored image: (m, n) at n * TLD + m, same as Cs (SC == TLD)
+        unsigned* my_sub = sflags + ((long)i * T + j) * SUBS;
         if (i == j) {
-            potrf_tile(Cs, invd, &sh_info);
+            potrf_tile(Cs, invd, &sh_info, nullptr, Lij, my_sub, epoch);   // writes and publishes its block columns
             __syncthreads();
             if (sh_info != 0) {
-                if (tid == 0) atomicCAS(abort_word, 0, j * TILE + sh_info);
+                if (tid == 0) atomicCAS(abort_word, 0, (mat << 24) | (j * TILE + sh_info));
                 break;
             }
-            for (int idx = tid; idx < TILE * TLD; idx += NTHREADS) {
-                int n = idx / TLD, m = idx % TLD;
-                Lij[idx] = (m < TILE && m >= n) ? Cs[n * SC + m] : 0.0;
-            }
         } else {
-            int okf = 1;
-            if (tid == 0) okf = wait_flag(flags + (long)j * T + j, epoch, abort_word);
-            if (!__syncthreads_and(okf)) break;
-            trsm_right_tile(Cs, Lp, Lp1, invd, L + tile_off(j, j, T), TLD);
-            for (int idx = tid; idx < TILE * TLD; idx += NTHREADS) {
-                int m = idx % TLD;
-                Lij[idx] = (m < TILE) ? Cs[idx] : 0.0;
-            }
+            const long dj = (long)j * T + j;
+            if (!trsm_right_tile(Cs, Lp, Lp1, invd, L + tile_off(j, j, T), TLD, nullptr, tflags + dj, sflags + dj * SUBS, Lij,
+                                 my_sub, epoch, abort_word))
+                break;
         }
-        __threadfence();
-        fence_proxy_async();   // generic smem accesses of the finalize step before the next job's bulk copies
-        __syncthreads();
-        if (tid == 0) st_release(flags + (long)i * T + j, epoch);
+        // all block columns of the tile have been stored (and their stores ordered before a barrier) by the tile operation
+        if (tid == 0) st_release(tflags + (long)i * T + j, epoch);
     }
 }
 
-static int build_potrf_jobs(int T, int P, int2* host) {
-    int p = 0;
+// Column-major job list of one matrix; tiles of a prefilled leading block are not jobs.
+static void build_potrf_jobs(int mat, int T, int P, std::vector<int2>& out) {
     for (int j = 0; j < T; ++j)
         for (int i = j; i < T; ++i)
-            if (!(i < P && j < P)) host[p++] = make_int2(i, j);   // tiles of the prefilled leading block are not jobs
-    return p;
+            if (!(i < P && j < P)) out.push_back(make_int2((mat << 16) | i, j));
 }
 
 // One CTA per tile (i, j), j <= i < P: copy the tile image from the known factor and publish its flag.
@@ -142,34 +174,82 @@ __global__ void __launch_bounds__(256) potrf_prefill_kernel(const double* __rest
     double2* dst = reinterpret_cast<double2*>(L + tile_off(i, j, T));
     for (int t = threadIdx.x; t < (int)(TSZ / 2); t += blockDim.x) dst[t] = src[t];
     if (threadIdx.x == 0) flags[(long)i * T + j] = epoch;
+    // a consumer whose OTHER operand tile is still in flight waits per block column on both tiles
+    if (threadIdx.x < SUBS) flags[(long)T * T + ((long)i * T + j) * SUBS + threadIdx.x] = epoch;
+}
+
+int launch_potrf_batch(cudaStream_t st, Sched& sched, const PotrfItem* items, int nm) {
+    if (nm < 1 || nm > POTRF_MAX_BATCH) return -1;
+    PotrfBatch pb;
+    pb.nm = nm;
+    std::vector<int> key;
+    key.reserve(2 * nm);
+    long off = 0;
+    int Ps[POTRF_MAX_BATCH];
+    for (int m = 0; m < nm; ++m) {
+        const PotrfItem& it = items[m];
+        const int T = it.npad / TILE;
+        if (T > 0xffff) return -1;
+        Ps[m] = (it.Lpre && it.ptiles > 0 && it.ptiles <= T && it.ptiles <= it.npad_pre / TILE) ? it.ptiles : 0;
+        pb.m[m] = PotrfMat{it.A, it.L, it.ld, T, (int)off};
+        off += (long)T * T * (1 + SUBS);
+        key.push_back(T);
+        key.push_back(Ps[m]);
+    }
+    if ((size_t)off > sched.flags_cap) return -1;
+    static std::atomic<unsigned long long> attr_done{0};
+    ensure_dyn_smem(potrf_dataflow_kernel, POTRF_SMEM, attr_done);
+    if (sched.jobs_key != key) {   // merged job table, cached per batch shape
+        std::vector<std::vector<int2>> lists(nm);
+        size_t total = 0;
+        for (int m = 0; m < nm; ++m) {
+            build_potrf_jobs(m, key[2 * m], key[2 * m + 1], lists[m]);
+            total += lists[m].size();
+        }
+        if (total > sched.jobs_cap) return -1;
+        // Proportional merge: every list keeps its own (column-major) order, so a job still waits only on jobs dealt before
+        // it, and all factorisations advance at the same relative pace.
+        std::vector<int2> merged;
+        merged.reserve(total ? total : 1);
+        std::vector<size_t> pos(nm, 0);
+        for (size_t k = 0; k < total; ++k) {
+            int best = -1;
+            double bestkey = 0.0;
+            for (int m = 0; m < nm; ++m) {
+                if (pos[m] >= lists[m].size()) continue;
+                const double kk = ((double)pos[m] + 0.5) / (double)lists[m].size();
+                if (best < 0 || kk < bestkey) { best = m; bestkey = kk; }
+            }
+            merged.push_back(lists[best][pos[best]++]);
+        }
+        if (total) {
+            cudaMemcpyAsync(sched.jobs, merged.data(), sizeof(int2) * total, cudaMemcpyHostToDevice, st);
+            cudaStreamSynchronize(st);   // `merged` is pageable: complete the copy before it goes away
+        }
+        sched.jobs_key = key;
+        sched.jobs_count = (int)total;
+    }
+    const int njobs = sched.jobs_count;
+    cudaMemsetAsync(sched.counter, 0, sizeof(unsigned), st);
+    cudaMemsetAsync(sched.abort_word, 0, sizeof(int), st);
+    sched.epoch++;
+    for (int m = 0; m < nm; ++m) {
+        if (Ps[m] > 0) {
+            potrf_prefill_kernel<<<Ps[m] * Ps[m], 256, 0, st>>>(items[m].Lpre, items[m].npad_pre / TILE, items[m].L, pb.m[m].T, Ps[m],
+                                                               sched.flags + pb.m[m].flag_off, sched.epoch); ++g_kernel_launches;
+        }
+    }
+    if (njobs == 0) return 0;
+    int grid = njobs < sched.num_sms ? njobs : sched.num_sms;
+    potrf_dataflow_kernel<<<grid, NTHREADS, POTRF_SMEM, st>>>(pb, sched.jobs, njobs, sched.flags, sched.epoch, sched.counter,
+                                                              sched.abort_word); ++g_kernel_launches;
+    return 0;
 }
 
 void launch_potrf(cudaStream_t st, Sched& sched, const double* A, double* L, long ld, int npad, const double* Lpre, int npad_pre,
                   int ptiles) {
-    const int T = npad / TILE;
-    const int P = (Lpre && ptiles > 0 && ptiles <= T && ptiles <= npad_pre / TILE) ? ptiles : 0;
-    const int njobs = T * (T + 1) / 2 - P * (P + 1) / 2;
-    static std::atomic<unsigned long long> attr_done{0};
-    ensure_dyn_smem(potrf_dataflow_kernel, POTRF_SMEM, attr_done);
-    if (sched.jobs_T != T || sched.jobs_P != P) {   // job table cached per (tile count, prefilled tiles)
-        int2* hjobs = (int2*)malloc(sizeof(int2) * (njobs > 0 ? njobs : 1));
-        build_potrf_jobs(T, P, hjobs);
-        cudaMemcpyAsync(sched.jobs, hjobs, sizeof(int2) * njobs, cudaMemcpyHostToDevice, st);
-        cudaStreamSynchronize(st);   // hjobs is pageable: complete the copy before free
-        free(hjobs);
-        sched.jobs_T = T;
-        sched.jobs_P = P;
-    }
-    cudaMemsetAsync(sched.counter, 0, sizeof(unsigned), st);
-    cudaMemsetAsync(sched.abort_word, 0, sizeof(int), st);
-    sched.epoch++;
-    if (P > 0) {
-        potrf_prefill_kernel<<<P * P, 256, 0, st>>>(Lpre, npad_pre / TILE, L, T, P, sched.flags, sched.epoch); ++g_kernel_launches;
-    }
-    if (njobs == 0) return;
-    int grid = njobs < sched.num_sms ? njobs : sched.num_sms;
-    potrf_dataflow_kernel<<<grid, NTHREADS, POTRF_SMEM, st>>>(A, L, ld, T, sched.jobs, njobs, sched.flags, sched.epoch,
-                                                              sched.counter, sched.abort_word); ++g_kernel_launches;
+    PotrfItem it{A, L, ld, npad, Lpre, npad_pre, ptiles};
+    launch_potrf_batch(st, sched, &it, 1);
 }
 
 // After the factorisation: store L' in the (otherwise unused) tiles above the diagonal, M(j-block, i-block) =

@@ -104,19 +104,15 @@ __device__ __forceinline__ void tile_update(double* Cs, int m0, int mtiles, int 
     }
 }
 
-// ---- Cholesky of the 128x128 lower triangle held in Cs (in place).  sh_info: shared int, must be
-// 0 on entry; set to (local index + 1) of the first non-positive pivot.  The strict upper triangle
-// is left untouched (caller zeroes it on write-out).  invd[128] receives 1/L(c,c).
-__device__ inline void potrf_tile(double* Cs, double* invd, int* sh_info, long long* prof = nullptr) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    long long tp = prof ? clock64() : 0;
-    auto lap = [&](int k) { if (prof) { long long t = clock64(); if (tid == 0) prof[k] += t - tp; tp = t; } };
-    for (int o = 0; o < TILE; o += NB) {
-        // 1. 32x32 diagonal block, one warp, row per lane, registers + shuffles.  The dependent chain per pivot is
-        //    kept short: every lane tracks its OWN diagonal entry in `diag` (updated with lane-local FMAs) and
-        //    evaluates rsqrt on it each step, so a step costs fma -> rsqrt -> one shuffle -> mul; the column
-        //    shuffles for the off-diagonal updates stay off the chain.  L(c,c) = a * rsqrt(a), 1/L(c,c) = rsqrt(a).
-        if (warp == 0) {
+// Cholesky of the 32x32 diagonal block at offset o of the tile in Cs, by ONE warp (row per lane, registers + shuffles).
+// The dependent chain per pivot is kept short: every lane tracks its OWN diagonal entry in `diag` (updated with lane-local
+// FMAs) and evaluates rsqrt on it each step, so a step costs fma -> rsqrt -> one shuffle -> mul; the column shuffles for the
+// off-diagonal updates stay off the chain.  L(c,c) = a * rsqrt(a), 1/L(c,c) = rsqrt(a).
+// A separate non-inlined function: inlined into the unrolled / rolled block loop of potrf_tile the compiler cannot prove the
+// warp converged and wraps each of the ~1000 shuffles in WARPSYNC.COLLECTIVE / ENDCOLLECTIVE (round 1: ~3x slower per pivot).
+static __device__ __noinline__ void potrf_diag32(double* Cs, double* invd, int* sh_info, int o) {
+    const int lane = threadIdx.x & 31;
+    {
             double a[NB];
 #pragma unroll
             for (int c = 0; c < NB; ++c) a[c] = Cs[(o + c) * SC + o + lane];
@@ -149,11 +145,57 @@ __device__ inline void potrf_tile(double* Cs, double* invd, int* sh_info, long l
             unsigned bad = __ballot_sync(0xffffffffu, first_bad != 0);
             if (bad != 0 && lane == 0) atomicCAS(sh_info, 0, o + __ffs(bad));
         }
+}
+
+// Named barriers (barrier 0 is __syncthreads): producer / consumer hand-over between warp 0 and warps 1..7 inside potrf_tile.
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// ---- Cholesky of the 128x128 lower triangle held in Cs (in place).  sh_info: shared int, must be
+// 0 on entry; set to (local index + 1) of the first non-positive pivot.  The strict upper triangle
+// is left untouched (caller zeroes it on write-out).  invd[128] receives 1/L(c,c).
+//
+// Blocked by 32.  Iteration o: (1) 32x32 diagonal block by warp 0 (a chain of 32 dependent pivots, ~200 cycles each: the
+// one part of the whole factorisation that nothing can be overlapped with on this CTA); (2) the panel below it, one row per
+// thread; (3) the trailing update with DMMA.  LOOK-AHEAD (round 2): warp 0 owns the 32 panel rows that are the NEXT diagonal
+// block's rows, so after (2) it updates just that block and goes straight on to factor it, while warps 1..7 store / publish
+// block column o and run the rest of the trailing update.  The update leaves the chain: 4 x diag + 3 x (panel + 32x32 update).
+//
+// Progressive publication (Lg != nullptr; the dataflow Cholesky): block column b = columns [32b, 32b+32) of the factor is
+// final as soon as iteration b has solved the panel below its diagonal block.  It is then written to the stored tile image
+// Lg (TBP: (m, n) at n*TLD + m, explicit zeros above the diagonal and in the 4 pad rows) and flag sub[b] is released -- the
+// right solves of the tiles below this one start on block column 0 while this CTA is still factoring columns 32..127, so
+// the three links of the critical path (last update -> potrf -> right solve) overlap instead of running back to back.
+// After a non-positive pivot nothing more is published (the caller raises the abort word, which releases every waiter).
+__device__ inline void potrf_tile(double* Cs, double* invd, int* sh_info, long long* prof = nullptr, double* Lg = nullptr,
+                                  unsigned* sub = nullptr, unsigned epoch = 0) {
+    const int tid = threadIdx.x, warp = tid >> 5;
+    long long tp = prof ? clock64() : 0;
+    auto lap = [&](int k) { if (prof) { long long t = clock64(); if (tid == 0) prof[k] += t - tp; tp = t; } };
+    // threads 32..255; rows above the diagonal and pad rows are written as 0
+    auto store_block_col = [&](int o, int t0, int nt) {
+        for (int idx = t0; idx < NB * TLD; idx += nt) {
+            const int n = o + idx / TLD, m = idx % TLD;
+            Lg[(long)n * TLD + m] = (m < TILE && m >= n) ? Cs[n * SC + m] : 0.0;
+        }
+    };
+    bool bad = false;   // a non-positive pivot was seen (uniform)
+#ifdef GEORDD_POTRF_NO_LOOKAHEAD
+    // A/B variant (round 2's first step: progressive publication only): diag -> panel -> full trailing update, in sequence.
+    for (int o = 0; o < TILE; o += NB) {
+        if (warp == 0) potrf_diag32(Cs, invd, sh_info, o);
         __syncthreads();
         lap(0);
+        if (Lg) bad = bad || ld_volatile_int(sh_info) != 0;
         const int rest = TILE - o - NB;
-        if (rest == 0) break;
-        // 2. panel below: X = C * L^-T, one row per thread
+        if (rest == 0) {
+            if (Lg && !bad) {
+                store_block_col(o, tid, NTHREADS);
+                __syncthreads();
+                if (tid == 0) st_release(sub + o / NB, epoch);
+            }
+            break;
+        }
         if (tid < rest) {
             const int r = o + NB + tid;
             double x[NB];
@@ -165,12 +207,137 @@ __device__ inline void potrf_tile(double* Cs, double* invd, int* sh_info, long l
         }
         __syncthreads();
         lap(1);
-        // 3. trailing lower triangle -= P P^T
+        if (Lg && !bad) store_block_col(o, tid, NTHREADS);
         {
-            const double* P = Cs + o * SC + (o + NB);   // P(m,k) at P[k*SC + m]
+            const double* P = Cs + o * SC + (o + NB);
             tile_update(
                 Cs, o + NB, rest / 8, o + NB, rest / 8, [&](int m, int k) { return P[k * SC + m]; },
                 [&](int k, int n) { return P[k * SC + n]; }, true);
+        }
+        __syncthreads();
+        lap(2);
+        if (Lg && !bad && tid == 0) st_release(sub + o / NB, epoch);
+    }
+    return;
+#endif
+    if (warp == 0) potrf_diag32(Cs, invd, sh_info, 0);
+    __syncthreads();
+    lap(0);
+    for (int o = 0; o < TILE; o += NB) {
+        if (Lg) bad = bad || ld_volatile_int(sh_info) != 0;   // uniform: written before the last barrier
+        const int rest = TILE - o - NB;
+        if (rest == 0) {
+            if (Lg && !bad) {
+                store_block_col(o, tid, NTHREADS);
+                __syncthreads();
+                if (tid == 0) st_release(sub + o / NB, epoch);
+            }
+            break;
+        }
+        // 2. panel below: X = C * L^-T, one row per thread (warp 0: rows o+32..o+63 = the next diagonal block's rows)
+        if (tid < rest) {
+            const int r = o + NB + tid;
+            double x[NB];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) x[c] = Cs[(o + c) * SC + r];
+            forward_subst32(x, invd + o, Cs + o * SC + o, SC);
+#pragma unroll
+            for (int c = 0; c < NB; ++c) Cs[(o + c) * SC + r] = x[c];
+        }
+        const double* P = Cs + o * SC + (o + NB);   // panel: P(m,k) at P[k*SC + m], m relative to row o+32
+        if (warp == 0) {
+            named_bar_arrive(1, NTHREADS);   // my panel rows are written (the others need them for their update)
+            __syncwarp();
+            // 3a. next diagonal block -= P0 P0^T (the 10 lower 8x8 tiles), from this warp's own 32 panel rows.  A and B
+            //     fragments coincide (same panel), all ten accumulators are live so the DMMAs issue back to back.
+            const int lane = tid & 31, g = lane >> 2, tq = lane & 3;
+            double acc[10][2];
+            {
+                int t = 0;
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt <= mt; ++nt, ++t) {
+                        const int n = o + NB + nt * 8 + 2 * tq, m = o + NB + mt * 8 + g;
+                        acc[t][0] = -Cs[n * SC + m];
+                        acc[t][1] = -Cs[(n + 1) * SC + m];
+                    }
+            }
+#pragma unroll
+            for (int kk = 0; kk < NB / 4; ++kk) {
+                double f[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) f[q] = P[(kk * 4 + tq) * SC + q * 8 + g];
+                int t = 0;
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt <= mt; ++nt, ++t) dmma(acc[t][0], acc[t][1], f[mt], f[nt]);
+            }
+            {
+                int t = 0;
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt <= mt; ++nt, ++t) {
+                        const int n = o + NB + nt * 8 + 2 * tq, m = o + NB + mt * 8 + g;
+                        Cs[n * SC + m] = -acc[t][0];
+                        Cs[(n + 1) * SC + m] = -acc[t][1];
+                    }
+            }
+            __syncwarp();
+            lap(1);
+            // 1'. factor the next diagonal block while warps 1..7 finish the trailing update
+            potrf_diag32(Cs, invd, sh_info, o + NB);
+            lap(0);
+        } else {
+            named_bar_sync(1, NTHREADS);     // all panel rows of this iteration are in shared memory
+            if (Lg && !bad) {                // block column o is final: store it, publish it
+                store_block_col(o, tid - 32, NTHREADS - 32);
+                named_bar_sync(2, NTHREADS - 32);
+                if (tid == 32) st_release(sub + o / NB, epoch);
+            }
+            // 3b. trailing lower triangle -= P P^T for the rows below the next diagonal block (8x8 m-tiles 4.. of the trailing part)
+            const int mtiles = rest / 8;
+            const int lane = tid & 31, g = lane >> 2, tq = lane & 3;
+            // Warp 4 shares warp 0's SM sub-partition, and scalar FP64 instructions of the pivot chain queue behind DMMAs
+            // issued there (measured: diag32 26.6k -> 31.6k cycles with warp 4 updating): six warps update, warp 4 sits out.
+            const int uw = warp < 4 ? warp - 1 : warp - 2;   // 0..5 for warps 1,2,3,5,6,7
+            if (warp != 4)
+            for (int mt = NB / 8 + uw; mt < mtiles; mt += 6) {
+                double a[NB / 4];
+#pragma unroll
+                for (int kk = 0; kk < NB / 4; ++kk) a[kk] = P[(kk * 4 + tq) * SC + mt * 8 + g];
+                for (int nt0 = 0; nt0 <= mt; nt0 += 4) {
+                    double c[4][2];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int nt = nt0 + u;
+                        if (nt <= mt) {
+                            const int n = o + NB + nt * 8 + 2 * tq, m = o + NB + mt * 8 + g;
+                            c[u][0] = -Cs[n * SC + m];
+                            c[u][1] = -Cs[(n + 1) * SC + m];
+                        }
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < NB / 4; ++kk) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int nt = nt0 + u;
+                            if (nt <= mt) dmma(c[u][0], c[u][1], a[kk], P[(kk * 4 + tq) * SC + nt * 8 + g]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int nt = nt0 + u;
+                        if (nt <= mt) {
+                            const int n = o + NB + nt * 8 + 2 * tq, m = o + NB + mt * 8 + g;
+                            Cs[n * SC + m] = -c[u][0];
+                            Cs[(n + 1) * SC + m] = -c[u][1];
+                        }
+                    }
+                }
+            }
         }
         __syncthreads();
         lap(2);
@@ -213,16 +380,45 @@ __device__ __forceinline__ void load_col_panel_async(double* Lp, const double* L
 // ---- X * Lt^T = C  (C: 128 x 128 in Cs, overwritten by X).  Rows are independent. -------------
 // The column panels of Lt are double-buffered (Lp0 / Lp1, NB*SC doubles each): the copy of the next panel runs under
 // the substitution and update of the current block.
-__device__ inline void trsm_right_tile(double* Cs, double* Lp0, double* Lp1, double* invd, const double* Lt, long ld,
-                                       long long* prof = nullptr) {
+//
+// Dataflow form (dtile != nullptr): Lt is the diagonal tile of this tile column, possibly still being factored by another
+// CTA.  *dtile == epoch says the whole tile is final; otherwise dsub[b] == epoch says block column b is (potrf_tile's
+// progressive publication) and iteration b waits for exactly that.  X's own block columns are final after the substitution
+// of their iteration: they are written to the stored tile image Xg and released through xsub[b], so that the diagonal job
+// of the next tile column consumes them chunk by chunk.  Returns false (uniformly) if a wait was aborted.
+__device__ inline bool trsm_right_tile(double* Cs, double* Lp0, double* Lp1, double* invd, const double* Lt, long ld,
+                                       long long* prof = nullptr, const unsigned* dtile = nullptr, const unsigned* dsub = nullptr,
+                                       double* Xg = nullptr, unsigned* xsub = nullptr, unsigned epoch = 0, int* abort_word = nullptr) {
     const int tid = threadIdx.x;
     long long tp = prof ? clock64() : 0;
     auto lap = [&](int k) { if (prof) { long long t = clock64(); if (tid == 0) prof[k] += t - tp; tp = t; } };
-    load_col_panel_async(Lp0, Lt, ld, 0);
-    for (int o = 0, b = 0; o < TILE; o += NB, b ^= 1) {
-        double* Lp = b ? Lp1 : Lp0;
-        if (o + NB < TILE) {
-            load_col_panel_async(b ? Lp0 : Lp1, Lt, ld, o + NB);
+    bool whole = true;   // the diagonal tile is known to be complete
+    if (dtile) {
+        int w = 1;
+        if (tid == 0) w = ld_acquire(dtile) == epoch;
+        whole = __syncthreads_and(w) != 0;
+    }
+    int loaded = -1;     // highest panel whose copy has been issued
+    for (int o = 0, b = 0; o < TILE; o += NB, ++b) {
+        double* Lp = (b & 1) ? Lp1 : Lp0;
+        if (loaded < b) {
+            if (!whole) {
+                int ok = 1;
+                if (tid == 0) ok = wait_flag(dsub + b, epoch, abort_word);
+                if (!__syncthreads_and(ok)) return false;
+            }
+            load_col_panel_async(Lp, Lt, ld, o);
+            loaded = b;
+        }
+        bool pre = o + NB < TILE;
+        if (pre && !whole) {   // prefetch the next panel only if it has already been published
+            int ok = 1;
+            if (tid == 0) ok = ld_acquire(dsub + b + 1) == epoch;
+            pre = __syncthreads_and(ok) != 0;
+        }
+        if (pre) {
+            load_col_panel_async((b & 1) ? Lp0 : Lp1, Lt, ld, o + NB);
+            loaded = b + 1;
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
@@ -242,6 +438,12 @@ __device__ inline void trsm_right_tile(double* Cs, double* Lp0, double* Lp1, dou
         }
         __syncthreads();
         lap(1);
+        if (Xg) {   // block column b of X is final
+            for (int idx = tid; idx < NB * TLD; idx += NTHREADS) {
+                const int n = o + idx / TLD, m = idx % TLD;
+                Xg[(long)n * TLD + m] = (m < TILE) ? Cs[n * SC + m] : 0.0;
+            }
+        }
         const int rest = TILE - o - NB;
         if (rest > 0) {
             // C(:, n') -= X(:, o..o+NB) * L(n', o..o+NB)^T  for n' >= o+NB
@@ -252,7 +454,9 @@ __device__ inline void trsm_right_tile(double* Cs, double* Lp0, double* Lp1, dou
         }
         __syncthreads();
         lap(2);
+        if (Xg && tid == 0) st_release(xsub + b, epoch);   // every thread's stores precede the barrier above
     }
+    return true;
 }
 
 // ---- Lt * X = C  (forward; C: 128 x ncols in Cs, overwritten).  Columns are independent. -------

@@ -330,6 +330,39 @@ class GPE:
     def from_region(cls, rd: "RegionData", mean, kernel, logNoise, **kw):
         return cls(rd.x, rd.y, mean, kernel, logNoise, **kw)
 
+    @classmethod
+    def fit_many(cls, xs, ys, mean, kernel, logNoise: float, ctx: Optional[Context] = None) -> List["GPE"]:
+        """The independent fits that GPRealisations' constructor (src/GPrealisations.jl:10-19) and the placebo drivers
+        (src/hypotest_chi2.jl:66-69) make one after another, as ONE call (geordd_gp_fit_batch): all factorisations run in
+        a single dataflow launch.  Same results as [GPE(x, y, mean, kernel, logNoise) for ...], bit for bit."""
+        ctx = ctx or default_context()
+        nfit = len(xs)
+        gps = [cls.__new__(cls) for _ in range(nfit)]
+        for g, x, y in zip(gps, xs, ys):
+            g.ctx, g.x, g.y = ctx, fmat(x), np.array(y, dtype=np.float64)
+            g.mean, g.kernel, g.logNoise = mean, kernel, float(logNoise)
+            g.dim, g.nobs = g.x.shape
+            if g.y.shape[0] != g.nobs:
+                raise ValueError("ArgumentError: x and y have incompatible sizes")
+            g._h, g.alpha, g.cholU = C.c_void_p(), np.empty(g.nobs), None
+        if len({g.dim for g in gps}) != 1:
+            raise ValueError("ArgumentError: all regions must have the same spatial dimension")
+        spec = kernel_spec(kernel, mean)
+        specs = (_CKernel * nfit)(*([spec] * nfit))
+        PD = capi.c_double_p
+        Xp = (PD * nfit)(*[dptr(g.x) for g in gps])
+        Yp = (PD * nfit)(*[dptr(g.y) for g in gps])
+        Ap = (PD * nfit)(*[dptr(g.alpha) for g in gps])
+        ns = (C.c_int * nfit)(*[g.nobs for g in gps])
+        lns = (C.c_double * nfit)(*([float(logNoise)] * nfit))
+        hs = (C.c_void_p * nfit)()
+        mll, jr, info = (C.c_double * nfit)(), (C.c_int * nfit)(), (C.c_int * nfit)()
+        rc = ctx.lib.geordd_gp_fit_batch(ctx._h, nfit, specs, Xp, gps[0].dim, ns, Yp, lns, hs, Ap, mll, jr, info)
+        ctx.check(rc)
+        for f, g in enumerate(gps):
+            g._h, g.mll, g.jitter_rounds = C.c_void_p(hs[f]), mll[f], jr[f]
+        return gps
+
     def cK_mat(self) -> np.ndarray:
         K = np.empty((self.nobs, self.nobs), order="F")
         self.ctx.check(self.ctx.lib.geordd_gp_get_K(self._h, dptr(K)))
@@ -663,8 +696,14 @@ def chistat(gpT: GPE, gpC: GPE, Xb) -> float:
 
 
 def nsim_chi(gpT: GPE, gpC: GPE, gpNull: NullGPE, Xb, nsim: int, *, seed: int = 0, draw0: int = 0, Z=None,
-             chi_obs: float = math.inf, return_count: bool = False):
-    """nsim_chi(gpT, gpC, gpNull, Xb, nsim) (src/hypotest_chi2.jl:33-52): vector of nsim chi2 null draws."""
+             chi_obs: float = math.inf, return_count: bool = False, sharded: bool = False):
+    """nsim_chi(gpT, gpC, gpNull, Xb, nsim) (src/hypotest_chi2.jl:33-52): vector of nsim chi2 null draws.
+    sharded=True (under torch.distributed): every rank simulates its shard, the full vector is all-gathered."""
+    if sharded:
+        total = np.asarray(Z).shape[1] if Z is not None else int(nsim)
+        local, kw, gather = _vector_shard(total, dict(seed=seed, draw0=draw0, Z=Z))
+        part = nsim_chi(gpT, gpC, gpNull, Xb, local, chi_obs=chi_obs, **kw) if local > 0 else np.empty(0)
+        return gather(part)
     gpNull._ensure(Xb, 0.0)
     Zf, nz = _zarg(Z, gpNull.nobs)
     nsim = nz if nz is not None else int(nsim)
@@ -693,6 +732,22 @@ def _draw_shard(nsim: int, kw: dict):
     return cnt, kw, (lambda c: parallel.allreduce_tallies([c])[0])
 
 
+def _vector_shard(nsim: int, seed_kw: dict):
+    """Vector-returning nsim_* forms with sharded=True: this rank simulates its contiguous shard of the draw indices and the
+    statistics are assembled with one all-gather (8 * nsim bytes).  Returns (local nsim, kwargs, gather)."""
+    import sys
+    dist = sys.modules.get("torch.distributed")
+    if dist is None or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return nsim, seed_kw, (lambda v: v)
+    from . import parallel
+    lo, cnt = parallel.shard_draws(nsim, dist.get_rank(), dist.get_world_size())
+    kw = dict(seed_kw)
+    kw["draw0"] = int(kw.get("draw0", 0)) + lo
+    if kw.get("Z") is not None:
+        kw["Z"] = np.asarray(kw["Z"])[:, lo:lo + cnt]
+    return cnt, kw, (lambda v: parallel.gather_stats(v, nsim))
+
+
 def boot_chi2test(gpT: GPE, gpC: GPE, Xb, nsim: int, **kw) -> float:
     """boot_chi2test(gpT, gpC, Xb, nsim) (src/hypotest_chi2.jl:54-59): mean(chi_sims .> chi_obs)."""
     gpNull = make_null(gpT, gpC)
@@ -716,9 +771,14 @@ def pval_invvar_uncalib(gpT: GPE, gpC: GPE, Xb, nugget: float = 1e-10) -> float:
 
 def nsim_invvar_pval_uncalib(gpT: GPE, gpC: GPE, Xb, nsim: int, nugget: float = 1e-10, *, seed: int = 0,
                              draw0: int = 0, Z=None, pval_obs: float = -1.0, return_count: bool = False,
-                             gpNull: Optional[NullGPE] = None):
+                             gpNull: Optional[NullGPE] = None, sharded: bool = False):
     """nsim_invvar_pval_uncalib(gpT, gpC, Xb, nsim; nugget) (src/hypotest_invvar.jl:48-63)."""
     gpNull = gpNull or make_null(gpT, gpC)
+    if sharded:
+        total = np.asarray(Z).shape[1] if Z is not None else int(nsim)
+        local, kw, gather = _vector_shard(total, dict(seed=seed, draw0=draw0, Z=Z))
+        part = nsim_invvar_pval_uncalib(gpT, gpC, Xb, local, nugget, pval_obs=pval_obs, gpNull=gpNull, **kw) if local > 0 else np.empty(0)
+        return gather(part)
     gpNull._ensure(Xb, nugget)
     Zf, nz = _zarg(Z, gpNull.nobs)
     nsim = nz if nz is not None else int(nsim)
@@ -763,10 +823,20 @@ def nsim_invvar_calib(gpT: GPE, gpC: GPE, Xb, nsim: int, nugget: float = 1e-10, 
 
 
 def nsim_logP(gpT: GPE, gpC: GPE, gpNull: NullGPE, nsim: int, *, seed: int = 0, draw0: int = 0, Z=None,
-              dmll_obs: float = math.inf, return_count: bool = False):
+              dmll_obs: float = math.inf, return_count: bool = False, sharded: bool = False):
     """nsim_logP(gpT, gpC, gpNull, nsim) (src/hypotest_mll.jl:21-30): list of (mll_null, mll_alt).
     Like the reference it leaves gpNull.y / .alpha / .mll at the last draw (:6,10,14) -- except in the opt-in
     forward-only mode (Context.set_mll_forward_only), which never forms alpha and leaves y / alpha untouched."""
+    if sharded:   # every rank its shard of the draws; both vectors all-gathered (the tally is not meaningful here)
+        total = np.asarray(Z).shape[1] if Z is not None else int(nsim)
+        local, kw, gather = _vector_shard(total, dict(seed=seed, draw0=draw0, Z=Z))
+        if local > 0:
+            _, _, mn, ma = nsim_logP(gpT, gpC, gpNull, local, dmll_obs=dmll_obs, return_count=True, **kw)
+        else:
+            mn, ma = np.empty(0), np.empty(0)
+        mn, ma = gather(mn), gather(ma)
+        sims = list(zip(mn.tolist(), ma.tolist()))
+        return (sims, int(np.sum((ma - mn) > dmll_obs)), mn, ma) if return_count else sims
     Zf, nz = _zarg(Z, gpNull.nobs)
     nsim = nz if nz is not None else int(nsim)
     mnull, malt = np.empty(nsim), np.empty(nsim)
@@ -796,11 +866,27 @@ def boot_mlltest(gpT: GPE, gpC: GPE, nsim: int, **kw) -> float:
 
 
 def nsim_power(gpT: GPE, gpC: GPE, tau: float, Xb, chi_null, mll_null, pval_invvar_null, nsim: int, *,
-               seed: int = 0, draw0: int = 0, Z=None, compat_calib_bug: bool = False) -> np.ndarray:
+               seed: int = 0, draw0: int = 0, Z=None, compat_calib_bug: bool = False, sharded: bool = False,
+               gpNull: Optional[NullGPE] = None) -> np.ndarray:
     """nsim_power (src/power.jl:46-73): nsim x 5 array of (pval_mll, pval_chi2, pval_invvar_obs,
     invvar_bootcalib, invvar_calib).  compat_calib_bug reproduces the as-shipped missing '+' of the
-    7-argument pval_invvar_calib (src/hypotest_invvar.jl:125-128); default is the corrected formula."""
-    gpNull = NullGPE(gpT, gpC, Xb, 0.0)
+    7-argument pval_invvar_calib (src/hypotest_invvar.jl:125-128); default is the CORRECTED formula -- the one that
+    reproduces the reference notebook's published size / power table (tests/golden/julia_table_replay.json); the as-shipped
+    formula never rejects on that fixture.  sharded=True: the alternative draws are sharded over the ranks
+    (torch.distributed) and the five columns all-gathered.  gpNull: reuse a prepared null handle (same sentinels, nugget 0)."""
+    if sharded:
+        total = np.asarray(Z).shape[1] if Z is not None else int(nsim)
+        local, kw, gather = _vector_shard(total, dict(seed=seed, draw0=draw0, Z=Z))
+        if local > 0:
+            part = nsim_power(gpT, gpC, tau, Xb, chi_null, mll_null, pval_invvar_null, local, compat_calib_bug=compat_calib_bug,
+                              gpNull=gpNull, **kw)
+        else:
+            part = np.empty((0, 5))
+        return np.column_stack([gather(np.ascontiguousarray(part[:, j])) for j in range(5)])
+    if gpNull is None:
+        gpNull = NullGPE(gpT, gpC, Xb, 0.0)
+    else:
+        gpNull._ensure(Xb, 0.0)
     Zf, nz = _zarg(Z, gpNull.nobs)
     nsim = nz if nz is not None else int(nsim)
     chi_null = np.ascontiguousarray(chi_null, dtype=np.float64)
@@ -1018,15 +1104,14 @@ class GPRealisations:
         self.groupKeys = list(groupKeys) if groupKeys is not None else list(rdict.keys())
         self.kernel, self.logNoise = spkern, float(logNoise)
         self.mean = mean if mean is not None else MeanZero()
-        self.mgp: Dict[Hashable, GPE] = {}
-        nobs = 0
         for key in self.groupKeys:
-            rd = rdict[key]
-            if rd.y.shape[0] == 0:
+            if rdict[key].y.shape[0] == 0:
                 raise ValueError("empty group")
-            self.mgp[key] = GPE(rd.x, rd.y, self.mean, spkern, logNoise, ctx=ctx)
-            nobs += rd.y.shape[0]
-        self.nobs = nobs
+        # the reference fits the regions one after another (src/GPrealisations.jl:13-17); here all of them in one call
+        fits = GPE.fit_many([rdict[k].x for k in self.groupKeys], [rdict[k].y for k in self.groupKeys], self.mean, spkern,
+                            logNoise, ctx=ctx)
+        self.mgp: Dict[Hashable, GPE] = dict(zip(self.groupKeys, fits))
+        self.nobs = sum(g.nobs for g in fits)
         self.mll = 0.0
         update_mll(self)
 
@@ -1167,8 +1252,7 @@ def _placebo_split(angle, X, Y, kern, mean, logNoise):
     Y = np.asarray(Y, dtype=np.float64)
     shift = shift_for_even_split(angle, X)
     left = left_points(angle, shift, X)
-    gl = GPE(X[:, left], Y[left], mean, kern, logNoise)
-    gr = GPE(X[:, ~left], Y[~left], mean, kern, logNoise)
+    gl, gr = GPE.fit_many([X[:, left], X[:, ~left]], [Y[left], Y[~left]], mean, kern, logNoise)
     return shift, gl, gr
 
 

@@ -94,6 +94,15 @@ GEORDD_API int geordd_cov_cross(geordd_ctx* ctx, const geordd_kernel* k, const d
  * jitter_rounds (nullable) are outputs. */
 GEORDD_API int geordd_gp_fit(geordd_ctx* ctx, const geordd_kernel* k, const double* X, int dim, int n, const double* y,
                   double log_noise, geordd_gp** out, double* alpha, double* mll, double* cholU, int* jitter_rounds);
+/* a6: the fits of GPRealisations(rdict, groupKeys, kernel, logNoise, mean) (src/GPrealisations.jl:10-19, reached from
+ * src/region_gp_fit.jl:23-37): `nfit` independent GPE fits in one call (also the two halves of a placebo split,
+ * src/hypotest_chi2.jl:66-69).  All covariance matrices are assembled, then factored by ONE dataflow launch in which the
+ * critical paths of the factorisations interleave; results are identical to nfit geordd_gp_fit calls, bit for bit.
+ * X[f]: dim x n[f]; y[f]: n[f]; k, log_noise: nfit entries; outputs out[f], alpha[f] (nullable, n[f]), mll[f],
+ * jitter_rounds[f], info[f] (nullable).  If any fit fails, every handle is released and the first LAPACK info is returned. */
+GEORDD_API int geordd_gp_fit_batch(geordd_ctx* ctx, int nfit, const geordd_kernel* k, const double* const* X, int dim, const int* n,
+                        const double* const* y, const double* log_noise, geordd_gp** out, double* const* alpha, double* mll,
+                        int* jitter_rounds, int* info);
 /* a9: gp.y = y; update_alpha!(gp); mll(gp) with the frozen factor (src/gp_utils.jl:15-22). */
 GEORDD_API int geordd_gp_set_y(geordd_gp* gp, const double* y, double* alpha, double* mll);
 /* predict_mu(gp, Xb, cK) = m(Xb) + cov(kernel, Xb, gp.x) * alpha (src/gp_utils.jl:1-5). */

