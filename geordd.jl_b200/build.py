@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libgeordd_b200.so")
 SOURCES = ["cov.cu", "potrf.cu", "solve.cu", "solve_narrow.cu", "gemm.cu", "stats.cu", "geom.cu", "api_core.cu", "api_null.cu", "api_multigp.cu",
-           "bench.cu"]
+           "api_multi.cu", "bench.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 
@@ -45,7 +45,7 @@ def build(force=False, verbose=False, defines=(), suffix=""):
     lib = LIB if not suffix else LIB.replace(".so", suffix + ".so")
     if procs or not os.path.exists(lib):
         cmd = [nvcc, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static",
-                                                      "-Xcompiler", "-fPIC"]
+                                                      "-Xcompiler", "-fPIC", "-ldl", "-lpthread"]
         subprocess.check_call(cmd)
     return lib
 

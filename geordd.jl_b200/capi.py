@@ -104,6 +104,31 @@ _SIGS = {
                                           C.c_int, C.c_int, c_double_p, c_double_p, c_int_p]),
     "geordd_multigp_postmean_beta": (C.c_int, [C.c_void_p, C.POINTER(Kernel), C.c_double, C.c_double, c_double_p]),
     "geordd_multigp_destroy": (C.c_int, [C.c_void_p]),
+    "geordd_group_create": (C.c_int, [c_void_pp, C.c_int, c_int_p]),
+    "geordd_group_destroy": (C.c_int, [C.c_void_p]),
+    "geordd_group_size": (C.c_int, [C.c_void_p]),
+    "geordd_group_last_error": (C.c_char_p, [C.c_void_p]),
+    "geordd_group_ctx": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "geordd_group_gp_fit": (C.c_int, [C.c_void_p, C.POINTER(Kernel), c_double_p, C.c_int, C.c_int, c_double_p, C.c_double,
+                                      c_void_pp, c_double_p, c_double_p, c_int_p]),
+    "geordd_group_gp_destroy": (C.c_int, [C.c_void_p]),
+    "geordd_group_gp_replica": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "geordd_group_null_prepare": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, C.c_int, C.c_double, c_void_pp, c_int_p,
+                                            c_double_p]),
+    "geordd_group_null_destroy": (C.c_int, [C.c_void_p]),
+    "geordd_group_null_replica": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "geordd_group_null_mll": (C.c_int, [C.c_void_p, C.c_long, C.c_ulonglong, C.c_ulonglong, c_double_p, C.c_double,
+                                        c_double_p, c_double_p, c_ll_p]),
+    "geordd_group_null_chi2": (C.c_int, [C.c_void_p, C.c_long, C.c_ulonglong, C.c_ulonglong, c_double_p, C.c_double,
+                                         c_double_p, c_ll_p]),
+    "geordd_group_null_invvar": (C.c_int, [C.c_void_p, C.c_long, C.c_ulonglong, C.c_ulonglong, c_double_p, C.c_double,
+                                           c_double_p, c_ll_p]),
+    "geordd_group_power": (C.c_int, [C.c_void_p, C.c_double, C.c_long, C.c_ulonglong, C.c_ulonglong, c_double_p, c_double_p,
+                                     c_double_p, c_double_p, C.c_long, C.c_int, c_double_p]),
+    "geordd_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "geordd_comm_init_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
+    "geordd_comm_allreduce_tally": (C.c_int, [C.c_void_p, c_ll_p, C.c_int]),
+    "geordd_comm_destroy": (C.c_int, [C.c_void_p]),
     "geordd_dbg_normals": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_ulonglong, C.c_int, C.c_int, c_double_p]),
     "geordd_dbg_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, c_double_p,
                                   C.c_int, c_double_p, C.c_int, C.c_double, c_double_p, C.c_int, C.c_int]),

@@ -4,7 +4,7 @@
 
 namespace geordd {
 
-long long g_kernel_launches = 0;
+std::atomic<long long> g_kernel_launches{0};
 
 const char* const kProfNames[PC_COUNT] = {"cov", "potrf", "solve_fwd", "solve_bwd", "trmm",
                                           "gemm", "rng", "finish", "lu", "misc", "solve_seq"};
@@ -404,7 +404,7 @@ extern "C" {
 
 int geordd_version(void) { return 100; }
 
-long long geordd_launch_count(void) { return geordd::g_kernel_launches; }
+long long geordd_launch_count(void) { return geordd::g_kernel_launches.load(); }
 
 int geordd_ctx_create(geordd_ctx** out, int device) {
     if (!out) return GEORDD_ERR_ARG;
@@ -451,6 +451,7 @@ int geordd_ctx_destroy(geordd_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    geordd_comm_destroy(c);
     for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     cudaFree(c->sched.counter); cudaFree(c->sched.flags); cudaFree(c->sched.abort_word); cudaFree(c->sched.jobs);

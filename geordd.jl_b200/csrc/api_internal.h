@@ -61,6 +61,8 @@ struct geordd_ctx {
     std::string err;
     long max_batch = 0;
     bool mll_forward_only = false;
+    void* comm = nullptr;                     // ncclComm_t of a one-process-per-GPU caller (geordd_comm_init_rank), api_multi.cu
+    int comm_size = 0;
     // caching device-memory pool
     std::multimap<size_t, void*> pool_free;
     std::unordered_map<void*, size_t> pool_live;

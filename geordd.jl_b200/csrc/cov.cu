@@ -3,10 +3,18 @@
 // (call sites: GPE ctor at src/region_gp_fit.jl:12,28 and src/hypotest.jl:4; addcov!/add_diag!
 // src/gp_utils.jl:24-44; cov(kernel, Xb, gp.x) src/hypotest_chi2.jl:38-39, src/power.jl:60-62).
 //
-// HBM-write bound: one 64x64 output tile per CTA, the 2x64 coordinate columns of the tile are staged
-// in shared memory once, distances are direct differences (no Gram trick), every
-// store is a coalesced 512-byte row segment.  Symmetric assembly computes only the tiles on or below
-// the diagonal and mirrors them through a padded smem transpose, halving the exp() work.
+// One 64x64 output tile per CTA, the 2x64 coordinate columns of the tile are staged in shared memory once, distances
+// are direct differences (no Gram trick), every store is a coalesced 512-byte row segment.  Symmetric
+// assembly computes only the tiles on or below the diagonal and mirrors them through a padded smem transpose, halving
+// the exp() work.
+//
+// What bounds it (round 2, measured): NOT the HBM write.  An entry costs ~50 FP64-pipe instructions with the CUDA math
+// library (sqrt ~10, the division by ell ~12, exp ~22, the rest ~6) against 8 bytes stored; B200 issues 64 FP64 FMA per
+// clock per SM, so 32.8 M lower-triangle entries of the n = 8064 pooled matrix need >= 88 us of FP64 issue, while the
+// 262 MB they occupy need 40 us of HBM time.  The fast path below (cov2_kernel: 2-d coordinates, the case of every fit)
+// therefore cuts FP64 instructions first -- reciprocals of ell hoisted to the host, r = r2 * rsqrt(r2) from the MUFU seed --
+// and only then widens the stores to 16 bytes (two rows per thread).
+#include <cstdint>
 #include "kernels.h"
 
 namespace geordd {
@@ -112,6 +120,101 @@ __global__ void __launch_bounds__(256) cov_kernel(CovParams p) {
     }
 }
 
+// ---- fast path: dim == 2, plain assignment, even leading dimension and 16-byte aligned K (all device-resident fits) ------
+struct Cov2Consts {
+    int kind;
+    double a;        // SE: -0.5 / ell^2 ; Matern: sqrt(1|3|5) / ell
+    double sigma2, csig2;
+};
+
+__device__ __forceinline__ double rsqrt_seeded(double x) {   // x > 0 normal; MUFU.RSQ64H + one third-order step
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);
+    return fma(y * e, fma(0.375, e, 0.5), y);
+}
+
+__device__ __forceinline__ double kern_eval2(const Cov2Consts& k, double r2) {
+    double v;
+    if (k.kind == 0) {
+        v = k.sigma2 * exp(r2 * k.a);
+    } else {
+        const double r = r2 > 0.0 ? r2 * rsqrt_seeded(r2) : 0.0;
+        const double s = k.a * r;
+        const double e = exp(-s);
+        if (k.kind == 1) v = k.sigma2 * e;
+        else if (k.kind == 2) v = k.sigma2 * (1.0 + s) * e;
+        else v = k.sigma2 * (1.0 + s + s * s * (1.0 / 3.0)) * e;
+    }
+    return v + k.csig2;
+}
+
+__global__ void __launch_bounds__(256) cov2_kernel(CovParams p, Cov2Consts kc) {
+    __shared__ double2 xs1[CT], xs2[CT];
+    __shared__ double tile[CT][CT + 2];
+    int bi, bj;
+    if (p.sym) {
+        int t = blockIdx.x;
+        int bjj = (int)floor((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+        while ((long)(bjj + 1) * (bjj + 2) / 2 <= t) ++bjj;
+        while ((long)bjj * (bjj + 1) / 2 > t) --bjj;
+        bi = bjj;
+        bj = t - bjj * (bjj + 1) / 2;
+    } else {
+        bi = blockIdx.x;
+        bj = blockIdx.y;
+    }
+    const int tid = threadIdx.x;
+    const int i0 = bi * CT, j0 = bj * CT;
+    if (tid < CT) {
+        const int i = i0 + tid;
+        xs1[tid] = i < p.n1 ? *reinterpret_cast<const double2*>(p.X1 + 2L * i) : make_double2(0.0, 0.0);
+    } else if (tid < 2 * CT) {
+        const int j = j0 + tid - CT;
+        xs2[tid - CT] = j < p.n2 ? *reinterpret_cast<const double2*>(p.X2 + 2L * j) : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    // thread = one PAIR of rows (2 li, 2 li + 1) x 8 columns; a warp stores 32 x 16 B = one 512-byte segment per column
+    const int li = tid % 32, lj0 = tid / 32;
+    const int r0 = i0 + 2 * li;
+    const double2 xa = xs1[2 * li], xb = xs1[2 * li + 1];
+#pragma unroll 4
+    for (int jj = 0; jj < CT / 8; ++jj) {
+        const int lj = lj0 + 8 * jj;
+        const int j = j0 + lj;
+        const double2 xc = xs2[lj];
+        double v[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = r0 + h;
+            const double2 xr = h ? xb : xa;
+            if (i < p.n1 && j < p.n2) {
+                const double dx = xr.x - xc.x, dy = xr.y - xc.y;
+                v[h] = kern_eval2(kc, fma(dy, dy, dx * dx));
+                if (p.sym && i == j) v[h] += p.diag_add;
+            } else {
+                v[h] = (p.sym && i == j) ? 1.0 : 0.0;
+            }
+        }
+        if (j < p.n2p && r0 < p.n1p)   // n1p is even on this path
+            *reinterpret_cast<double2*>(p.K + (long)j * p.ldk + r0) = make_double2(v[0], v[1]);
+        if (p.mirror) { tile[2 * li][lj] = v[0]; tile[2 * li + 1][lj] = v[1]; }
+    }
+    if (p.mirror && bi != bj) {
+        __syncthreads();
+        // transposed tile: element (row = j0 + a, col = i0 + b) = tile[b][a]; a contiguous, two rows per thread
+        const int a2 = 2 * (tid % 32), b0 = tid / 32;
+#pragma unroll 4
+        for (int bb = 0; bb < CT / 8; ++bb) {
+            const int b = b0 + 8 * bb;
+            const int row = j0 + a2, col = i0 + b;
+            if (row < p.n2p && col < p.n1p)
+                *reinterpret_cast<double2*>(p.K + (long)col * p.ldk + row) = make_double2(tile[b][a2], tile[b][a2 + 1]);
+        }
+    }
+}
+
 void launch_cov(cudaStream_t st, const KernelSpecDev& spec, const double* X1, int n1, const double* X2, int n2,
                 int dim, bool sym, bool mirror, double diag_add, double* K, long ldk, int n1p, int n2p,
                 bool accumulate) {
@@ -120,6 +223,21 @@ void launch_cov(cudaStream_t st, const KernelSpecDev& spec, const double* X1, in
     p.mirror = (sym && mirror) ? 1 : 0; p.diag_add = diag_add; p.K = K; p.ldk = ldk; p.n1p = n1p; p.n2p = n2p;
     p.accumulate = accumulate ? 1 : 0;
     int tb1 = (n1p + CT - 1) / CT, tb2 = (n2p + CT - 1) / CT;
+    const bool fast = dim == 2 && !accumulate && ldk % 2 == 0 && n1p % 2 == 0 && (!p.mirror || n2p % 2 == 0) &&
+                      reinterpret_cast<uintptr_t>(K) % 16 == 0 && reinterpret_cast<uintptr_t>(X1) % 16 == 0 &&
+                      reinterpret_cast<uintptr_t>(X2) % 16 == 0;
+    if (fast) {
+        Cov2Consts kc;
+        kc.kind = spec.kind; kc.sigma2 = spec.sigma2; kc.csig2 = spec.const_sigma2;
+        kc.a = spec.kind == 0 ? -0.5 / (spec.ell * spec.ell)
+             : (spec.kind == 1 ? 1.0 : spec.kind == 2 ? 1.7320508075688772 : 2.23606797749979) / spec.ell;
+        if (sym) {
+            cov2_kernel<<<tb1 * (tb1 + 1) / 2, 256, 0, st>>>(p, kc); ++g_kernel_launches;
+        } else {
+            cov2_kernel<<<dim3(tb1, tb2), 256, 0, st>>>(p, kc); ++g_kernel_launches;
+        }
+        return;
+    }
     if (sym) {
         int nt = tb1 * (tb1 + 1) / 2;
         cov_kernel<<<nt, 256, 0, st>>>(p); ++g_kernel_launches;

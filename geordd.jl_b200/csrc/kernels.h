@@ -58,7 +58,7 @@ struct Sched {
 };
 
 // Number of kernels this library has launched (bench.py reports it as gpu_launches).
-extern long long g_kernel_launches;
+extern std::atomic<long long> g_kernel_launches;   // (several host threads launch when a multi-device group is in use)
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 

@@ -750,6 +750,8 @@ def _vector_shard(nsim: int, seed_kw: dict):
 
 def boot_chi2test(gpT: GPE, gpC: GPE, Xb, nsim: int, **kw) -> float:
     """boot_chi2test(gpT, gpC, Xb, nsim) (src/hypotest_chi2.jl:54-59): mean(chi_sims .> chi_obs)."""
+    if isinstance(gpT, GroupGPE):
+        return _group_boot("chi", gpT, gpC, Xb, nsim, **kw)
     gpNull = make_null(gpT, gpC)
     chi_obs = chistat(gpT, gpC, Xb)
     total = np.asarray(kw["Z"]).shape[1] if kw.get("Z") is not None else int(nsim)
@@ -791,6 +793,8 @@ def nsim_invvar_pval_uncalib(gpT: GPE, gpC: GPE, Xb, nsim: int, nugget: float = 
 
 def boot_invvar(gpT: GPE, gpC: GPE, Xb, nsim: int, nugget: float = 1e-10, **kw) -> float:
     """boot_invvar (src/hypotest_invvar.jl:65-69): mean(pval_sims .< pval_obs)."""
+    if isinstance(gpT, GroupGPE):
+        return _group_boot("invvar", gpT, gpC, Xb, nsim, nugget, **kw)
     pobs = pval_invvar_uncalib(gpT, gpC, Xb, nugget)
     total = np.asarray(kw["Z"]).shape[1] if kw.get("Z") is not None else int(nsim)
     local, kw, reduce_ = _draw_shard(total, kw)
@@ -854,6 +858,8 @@ def nsim_logP(gpT: GPE, gpC: GPE, gpNull: NullGPE, nsim: int, *, seed: int = 0, 
 
 def boot_mlltest(gpT: GPE, gpC: GPE, nsim: int, **kw) -> float:
     """boot_mlltest(gpT, gpC, nsim) (src/hypotest_mll.jl:32-45): mean(dmll_sim .> dmll_obs)."""
+    if isinstance(gpT, GroupGPE):
+        return _group_boot("mll", gpT, gpC, None, nsim, **kw)
     mll_alt = gpT.mll + gpC.mll
     gpNull = make_null(gpT, gpC)
     d_obs = mll_alt - gpNull.mll
@@ -898,6 +904,163 @@ def nsim_power(gpT: GPE, gpC: GPE, tau: float, Xb, chi_null, mll_null, pval_invv
                                            dptr(mll_null), dptr(pinv), chi_null.shape[0], 1 if compat_calib_bug else 0,
                                            dptr(out)))
     return np.ascontiguousarray(out.T)
+
+
+# ----------------------------------------------------------------------------------------------
+# Multi-GPU inside ONE process: the group layer of the C ABI (geordd_group_*).  The same driver names accept the
+# group-fitted objects, so `boot_mlltest(gpT, gpC, nsim)` keeps its reference signature on 1 or 8 GPUs.
+# ----------------------------------------------------------------------------------------------
+class DeviceGroup:
+    """geordd_group: several GPUs of one box driven by this process; fits replicated, null draws sharded by index, tallies
+    summed with one NCCL all-reduce inside the library (no torch.distributed, no MPI)."""
+
+    def __init__(self, devices: Sequence[int]):
+        self.lib = capi.load_library()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        self._h = C.c_void_p()
+        rc = self.lib.geordd_group_create(C.byref(self._h), len(devices), devs)
+        if rc != 0:
+            raise GeorddError(rc, "geordd_group_create failed (no usable sm_100 devices, or NCCL missing for > 1 device)")
+        self.devices = list(devices)
+
+    def check(self, rc: int) -> None:
+        if rc == 0:
+            return
+        msg = self.lib.geordd_group_last_error(self._h).decode()
+        if rc > 0:
+            raise PosDefException(rc, msg)
+        if rc == capi_ERR_ARG:
+            raise ValueError("ArgumentError: " + msg)
+        raise GeorddError(rc, msg)
+
+    def context(self, i: int = 0) -> "Context":
+        """Borrowed single-GPU context of device i (observed statistics, cliff faces, other models)."""
+        ctx = Context.__new__(Context)
+        ctx.lib, ctx.device = self.lib, self.devices[i]
+        ctx._h = C.c_void_p(self.lib.geordd_group_ctx(self._h, i))
+        ctx.close = lambda: None          # owned by the group
+        return ctx
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h:
+            self.lib.geordd_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class GroupGPE:
+    """GPE(x, y, mean, kernel, logNoise) fitted on every device of a DeviceGroup (bit-identical replicas)."""
+
+    def __init__(self, group: DeviceGroup, x, y, mean, kernel, logNoise: float):
+        self.group = group
+        self.x, self.y = fmat(x), np.array(y, dtype=np.float64)
+        self.mean, self.kernel, self.logNoise = mean, kernel, float(logNoise)
+        self.dim, self.nobs = self.x.shape
+        spec = kernel_spec(kernel, mean)
+        self._h = C.c_void_p()
+        self.alpha = np.empty(self.nobs)
+        mll, jr = C.c_double(), C.c_int()
+        group.check(group.lib.geordd_group_gp_fit(group._h, C.byref(spec), dptr(self.x), self.dim, self.nobs, dptr(self.y),
+                                                  self.logNoise, C.byref(self._h), dptr(self.alpha), C.byref(mll), C.byref(jr)))
+        self.mll, self.jitter_rounds = mll.value, jr.value
+        # device 0's replica as a plain (borrowed) GPE for the single-GPU entry points
+        r = GPE.__new__(GPE)
+        r.ctx, r.x, r.y, r.mean, r.kernel, r.logNoise = group.context(0), self.x, self.y, mean, kernel, self.logNoise
+        r.dim, r.nobs, r.alpha, r.mll, r.jitter_rounds, r.cholU = self.dim, self.nobs, self.alpha, self.mll, self.jitter_rounds, None
+        r._h = C.c_void_p(group.lib.geordd_group_gp_replica(self._h, 0))
+        r.close = lambda: None
+        self.rep0 = r
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h:
+            self.group.lib.geordd_group_gp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class GroupNull:
+    """make_null + the draw-independent setup on every device of the group (geordd_group_null_prepare)."""
+
+    def __init__(self, gpT: GroupGPE, gpC: GroupGPE, Xb=None, nugget: float = 0.0):
+        self.group, self.gpT, self.gpC = gpT.group, gpT, gpC
+        self.Xb = fmat(Xb) if Xb is not None else None
+        nb = self.Xb.shape[1] if self.Xb is not None else 0
+        self._h = C.c_void_p()
+        jr, m = C.c_int(), C.c_double()
+        self.group.check(self.group.lib.geordd_group_null_prepare(gpT._h, gpC._h, dptr(self.Xb), nb, float(nugget),
+                                                                  C.byref(self._h), C.byref(jr), C.byref(m)))
+        self.jitter_rounds, self.mll, self.nugget = jr.value, m.value, nugget
+        self.nobs = gpT.nobs + gpC.nobs
+
+    def mll_draws(self, nsim: int, seed=0, draw0=0, Z=None, dmll_obs=math.inf):
+        Zf, nz = _zarg(Z, self.nobs)
+        nsim = nz if nz is not None else int(nsim)
+        mn, ma, cnt = np.empty(nsim), np.empty(nsim), C.c_longlong()
+        self.group.check(self.group.lib.geordd_group_null_mll(self._h, nsim, seed, draw0, dptr(Zf), float(dmll_obs), dptr(mn),
+                                                              dptr(ma), C.byref(cnt)))
+        return mn, ma, cnt.value
+
+    def chi2_draws(self, nsim: int, seed=0, draw0=0, Z=None, chi_obs=math.inf):
+        Zf, nz = _zarg(Z, self.nobs)
+        nsim = nz if nz is not None else int(nsim)
+        st, cnt = np.empty(nsim), C.c_longlong()
+        self.group.check(self.group.lib.geordd_group_null_chi2(self._h, nsim, seed, draw0, dptr(Zf), float(chi_obs), dptr(st),
+                                                               C.byref(cnt)))
+        return st, cnt.value
+
+    def invvar_draws(self, nsim: int, seed=0, draw0=0, Z=None, pval_obs=-1.0):
+        Zf, nz = _zarg(Z, self.nobs)
+        nsim = nz if nz is not None else int(nsim)
+        pv, cnt = np.empty(nsim), C.c_longlong()
+        self.group.check(self.group.lib.geordd_group_null_invvar(self._h, nsim, seed, draw0, dptr(Zf), float(pval_obs), dptr(pv),
+                                                                 C.byref(cnt)))
+        return pv, cnt.value
+
+    def power_draws(self, tau, chi_null, mll_null, pinv_null, nsim: int, seed=0, draw0=0, Z=None, compat_calib_bug=False):
+        Zf, nz = _zarg(Z, self.nobs)
+        nsim = nz if nz is not None else int(nsim)
+        a, b, c_ = (np.ascontiguousarray(v, dtype=np.float64) for v in (chi_null, mll_null, pinv_null))
+        out = np.empty((5, nsim), order="F")
+        self.group.check(self.group.lib.geordd_group_power(self._h, float(tau), nsim, seed, draw0, dptr(Zf), dptr(a), dptr(b),
+                                                           dptr(c_), a.shape[0], 1 if compat_calib_bug else 0, dptr(out)))
+        return np.ascontiguousarray(out.T)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h:
+            self.group.lib.geordd_group_null_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _group_boot(which: str, gpT: GroupGPE, gpC: GroupGPE, Xb, nsim: int, nugget: float = 0.0, **kw) -> float:
+    """boot_chi2test / boot_mlltest / boot_invvar on a DeviceGroup: observed statistic on device 0, draws on all devices."""
+    total = np.asarray(kw["Z"]).shape[1] if kw.get("Z") is not None else int(nsim)
+    if which == "mll":
+        gn = GroupNull(gpT, gpC)
+        _, _, cnt = gn.mll_draws(total, dmll_obs=gpT.mll + gpC.mll - gn.mll, **kw)
+    elif which == "chi":
+        gn = GroupNull(gpT, gpC, Xb, 0.0)
+        _, cnt = gn.chi2_draws(total, chi_obs=chistat(gpT.rep0, gpC.rep0, Xb), **kw)
+    else:
+        gn = GroupNull(gpT, gpC, Xb, nugget)
+        _, cnt = gn.invvar_draws(total, pval_obs=pval_invvar_uncalib(gpT.rep0, gpC.rep0, Xb, nugget), **kw)
+    gn.close()
+    return cnt / total
 
 
 # ----------------------------------------------------------------------------------------------

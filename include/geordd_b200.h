@@ -38,11 +38,15 @@ extern "C" {
 #define GEORDD_ERR_CUDA (-2)
 #define GEORDD_ERR_WATCHDOG (-3)
 #define GEORDD_ERR_NOMEM (-4)
+#define GEORDD_ERR_NCCL (-5)
 
 typedef struct geordd_ctx geordd_ctx;
 typedef struct geordd_gp geordd_gp;
 typedef struct geordd_null geordd_null;
 typedef struct geordd_multigp geordd_multigp;
+typedef struct geordd_group geordd_group;   /* several GPUs driven by one host process */
+typedef struct geordd_ggp geordd_ggp;       /* a fitted GP replicated on every device of a group */
+typedef struct geordd_gnull geordd_gnull;   /* a null handle replicated on every device of a group */
 
 /* Isotropic spatial kernel (+ optional Const kernel) and constant mean.
  * kind: 0 SEIso, 1 Mat12Iso, 2 Mat32Iso, 3 Mat52Iso (GaussianProcesses.jl kernels);
@@ -214,6 +218,48 @@ GEORDD_API int geordd_multigp_mll_grad(geordd_multigp* h, const geordd_kernel* k
 GEORDD_API int geordd_multigp_postmean_beta(geordd_multigp* h, const geordd_kernel* k, double lin_ell2, double log_noise,
                                  double* beta_hat);
 GEORDD_API int geordd_multigp_destroy(geordd_multigp* h);
+
+/* ---- multi-GPU inside the library (App. D geordd_ctx_create(ndev, devs)) -----------------------------------
+ * Only the embarrassingly parallel draw loops shard (src/hypotest_chi2.jl:49-50, src/hypotest_mll.jl:27-28,
+ * src/hypotest_invvar.jl:60-61, src/power.jl:67-71).  A group lets ONE host process (one Julia task) drive `ndev` GPUs:
+ * fits are replicated (one host thread per device, bit-identical replicas), draws are sharded contiguously by index --
+ * a draw depends only on (seed, draw index), so every result equals the single-GPU one bit for bit -- per-draw statistics
+ * land in the caller's arrays, and the exceedance tallies are summed with ONE ncclAllReduce(int64) over NVLink.
+ * devices == NULL selects devices 0 .. ndev-1.  NCCL is bound at run time (libnccl.so.2); a group of more than one device
+ * without it fails with GEORDD_ERR_NCCL (no host-side fallback). */
+GEORDD_API int geordd_group_create(geordd_group** out, int ndev, const int* devices);
+GEORDD_API int geordd_group_destroy(geordd_group* g);
+GEORDD_API int geordd_group_size(const geordd_group* g);
+GEORDD_API const char* geordd_group_last_error(const geordd_group* g);
+/* Borrow the context of device i of the group (for the single-GPU entry points: fits of other models, cliff faces ...). */
+GEORDD_API geordd_ctx* geordd_group_ctx(geordd_group* g, int i);
+/* geordd_gp_fit on every device of the group; alpha / mll / jitter_rounds are device 0's (all replicas are identical). */
+GEORDD_API int geordd_group_gp_fit(geordd_group* g, const geordd_kernel* k, const double* X, int dim, int n, const double* y,
+                                   double log_noise, geordd_ggp** out, double* alpha, double* mll, int* jitter_rounds);
+GEORDD_API int geordd_group_gp_destroy(geordd_ggp* h);
+GEORDD_API geordd_gp* geordd_group_gp_replica(geordd_ggp* h, int i);   /* borrowed */
+/* geordd_null_prepare on every device. */
+GEORDD_API int geordd_group_null_prepare(geordd_ggp* T, geordd_ggp* C, const double* Xb, int nb, double nugget, geordd_gnull** out,
+                                         int* jitter_rounds, double* mll_null);
+GEORDD_API int geordd_group_null_destroy(geordd_gnull* h);
+GEORDD_API geordd_null* geordd_group_null_replica(geordd_gnull* h, int i);   /* borrowed */
+/* The sharded forms of geordd_null_mll / _chi2 / _invvar / geordd_power: same arguments and results as on one GPU. */
+GEORDD_API int geordd_group_null_mll(geordd_gnull* h, long nsim, unsigned long long seed, unsigned long long draw0, const double* Z,
+                                     double dmll_obs, double* mll_null, double* mll_alt, long long* n_exceed);
+GEORDD_API int geordd_group_null_chi2(geordd_gnull* h, long nsim, unsigned long long seed, unsigned long long draw0, const double* Z,
+                                      double chi_obs, double* stats, long long* n_exceed);
+GEORDD_API int geordd_group_null_invvar(geordd_gnull* h, long nsim, unsigned long long seed, unsigned long long draw0, const double* Z,
+                                        double pval_obs, double* pvals, long long* n_below);
+GEORDD_API int geordd_group_power(geordd_gnull* h, double tau, long nsim, unsigned long long seed, unsigned long long draw0,
+                                  const double* Z, const double* chi_null, const double* mll_null, const double* pinv_null,
+                                  long nnull, int compat_calib_bug, double* out5);
+/* One process per GPU (MPI-launched Julia, torchrun): the same tally reduce on a plain context.  Rank 0 calls
+ * geordd_comm_unique_id and hands the 128 bytes to the other ranks by any means (a file, MPI_Bcast); every rank then calls
+ * geordd_comm_init_rank; geordd_comm_allreduce_tally sums up to 8 int64 counters in place over all ranks. */
+GEORDD_API int geordd_comm_unique_id(char* id128);
+GEORDD_API int geordd_comm_init_rank(geordd_ctx* ctx, int nranks, int rank, const char* id128);
+GEORDD_API int geordd_comm_allreduce_tally(geordd_ctx* ctx, long long* vals, int n);
+GEORDD_API int geordd_comm_destroy(geordd_ctx* ctx);
 
 /* ---- debug / test hooks (not part of the reference-facing surface) -----------------------------
  * Device Philox normals copied to the host: Z is n x ndraws. */

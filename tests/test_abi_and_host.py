@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol(G):
     hdr = open(os.path.join(ROOT, "include", "geordd_b200.h")).read()
-    declared = set(re.findall(r"GEORDD_API\s+(?:const\s+char\s*\*|int|long long)\s+(geordd_\w+)\s*\(", hdr))
+    declared = set(re.findall(r"GEORDD_API\s+(?:const\s+char\s*\*|int|long long|geordd_\w+\s*\*)\s*(geordd_\w+)\s*\(", hdr))
     assert len(declared) >= 40
     lib = G.capi.load_library()
     for name in sorted(declared):
@@ -186,3 +186,13 @@ def test_header_is_plain_c_and_links(G, tmp_path):
     if not torch.cuda.is_available():
         r = subprocess.run([exe], capture_output=True, text=True)
         assert r.returncode == 2 and "no usable GPU" in r.stderr
+    # the multi-GPU driver (group layer, NCCL bound at run time) is plain C99 as well
+    libdir = os.path.join(ROOT, "geordd.jl_b200", "lib")
+    exe2 = str(tmp_path / "c_driver_multi")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "c_driver_multi.c"), "-L" + libdir, "-lgeordd_b200", "-Wl,-rpath," + libdir, "-lm", "-o", exe2]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe2, "1"], capture_output=True, text=True)
+        assert r.returncode == 2
