@@ -53,6 +53,7 @@ _SIGS = {
     "geordd_ctx_profile_get": (C.c_int, [C.c_void_p, C.c_char_p, c_double_p, c_ll_p]),
     "geordd_ctx_set_max_batch": (C.c_int, [C.c_void_p, C.c_long]),
     "geordd_ctx_set_mll_forward_only": (C.c_int, [C.c_void_p, C.c_int]),
+    "geordd_ctx_last_min_margin": (C.c_int, [C.c_void_p, c_double_p]),
     "geordd_cov_sym": (C.c_int, [C.c_void_p, C.POINTER(Kernel), c_double_p, C.c_int, C.c_int, C.c_double, c_double_p]),
     "geordd_cov_cross": (C.c_int, [C.c_void_p, C.POINTER(Kernel), c_double_p, C.c_int, c_double_p, C.c_int, C.c_int,
                                    c_double_p]),

@@ -1,6 +1,7 @@
 // C ABI, part 1: context, profiling, covariance assembly, single-region GP fit.
 #include "api_internal.h"
 #include <algorithm>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges are no-ops unless a profiler is attached
 
 namespace geordd {
 
@@ -11,6 +12,7 @@ const char* const kProfNames[PC_COUNT] = {"cov", "potrf", "solve_fwd", "solve_bw
 
 // ---- profiling -------------------------------------------------------------------------------------
 ProfScope::ProfScope(geordd_ctx* ctx, int cls) : c(ctx) {
+    nvtxRangePushA(kProfNames[cls]);   // one NVTX range per kernel class / phase (nsys / ncu --nvtx)
     if (!c->prof_on) return;
     cudaEvent_t a, b;
     if (c->ev_pool.size() >= 2) {
@@ -26,6 +28,7 @@ ProfScope::ProfScope(geordd_ctx* ctx, int cls) : c(ctx) {
 }
 ProfScope::~ProfScope() {
     if (idx >= 0) cudaEventRecord(c->recs[idx].b, c->stream);
+    nvtxRangePop();
 }
 
 static void prof_collect(geordd_ctx* c) {
@@ -511,6 +514,12 @@ int geordd_ctx_profile_get(geordd_ctx* c, const char* name, double* ms, long lon
 int geordd_ctx_set_max_batch(geordd_ctx* c, long mb) {
     if (!c || mb < 0) return GEORDD_ERR_ARG;
     c->max_batch = mb;
+    return 0;
+}
+
+int geordd_ctx_last_min_margin(const geordd_ctx* c, double* margin3) {
+    if (!c || !margin3) return GEORDD_ERR_ARG;
+    for (int k = 0; k < 3; ++k) margin3[k] = c->min_margin[k];
     return 0;
 }
 

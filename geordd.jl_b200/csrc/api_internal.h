@@ -61,6 +61,7 @@ struct geordd_ctx {
     std::string err;
     long max_batch = 0;
     bool mll_forward_only = false;
+    double min_margin[3] = {INFINITY, INFINITY, INFINITY};   // last null call: min |stat - threshold| for chi2, invvar p, mll
     void* comm = nullptr;                     // ncclComm_t of a one-process-per-GPU caller (geordd_comm_init_rank), api_multi.cu
     int comm_size = 0;
     // caching device-memory pool

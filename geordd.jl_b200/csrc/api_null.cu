@@ -234,7 +234,8 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
         h->oAlt.ensure(rq.nsim, st, false);
     }
     h->cap_cols = std::max(h->cap_cols, cap);
-    GD_CUDA(cudaMemsetAsync(c->d_tally, 0, 8 * sizeof(unsigned long long), st));
+    GD_CUDA(cudaMemsetAsync(c->d_tally, 0, 4 * sizeof(unsigned long long), st));
+    GD_CUDA(cudaMemsetAsync(c->d_tally + 4, 0xff, 4 * sizeof(unsigned long long), st));   // minimum margins: [4] chi2, [5] invvar, [6] mll
 
     const double mN = N->k.mean_const, mTc = T->k.mean_const, mCc = C->k.mean_const;
     for (long done = 0; done < rq.nsim; done += cap) {
@@ -313,6 +314,7 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
             f.constN = (double)n * kLog2Pi / 2.0; f.constT = (double)mT * kLog2Pi / 2.0; f.constC = (double)mC * kLog2Pi / 2.0;
             f.dmll_obs = rq.dmll_obs; f.out_null = h->oNull.p; f.out_alt = h->oAlt.p; f.out_off = done;
             f.tally = c->d_tally + 2;
+            f.margin = c->d_tally + 6;
             ProfScope ps(c, PC_FINISH);
             launch_finish_mll(st, f);
         }
@@ -345,6 +347,7 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
             f.chi_obs = rq.chi_obs; f.denom = h->denom; f.pval_obs = rq.pval_obs;
             f.out_chi = h->oChi.p; f.out_pval = h->oPval.p; f.out_num = h->oNum.p; f.out_off = done;
             f.tally_chi = c->d_tally + 0; f.tally_inv = c->d_tally + 1;
+            f.margin_chi = c->d_tally + 4; f.margin_inv = c->d_tally + 5;
             ProfScope ps(c, PC_FINISH);
             launch_finish_cliff(st, f);
         }
@@ -379,6 +382,11 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
     rq.n_chi = (long long)c->h_tally[0];
     rq.n_inv = (long long)c->h_tally[1];
     rq.n_mll = (long long)c->h_tally[2];
+    for (int k = 0; k < 3; ++k) {   // +Inf when the statistic was not simulated (or the threshold was infinite / NaN)
+        double m;
+        std::memcpy(&m, &c->h_tally[4 + k], sizeof(double));
+        c->min_margin[k] = (c->h_tally[4 + k] == ~0ull || !(m == m)) ? INFINITY : m;
+    }
 }
 
 // draw-independent calibration constant for the 7-argument pval_invvar_calib (PD solves)

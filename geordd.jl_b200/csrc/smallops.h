@@ -15,6 +15,7 @@ struct FinishMll {
     double *out_null, *out_alt;             // nullable, indexed out_off + c
     long out_off;
     unsigned long long* tally;
+    unsigned long long* margin;             // atomicMin of the bits of |statistic - threshold| (certificate for the exact count)
 };
 void launch_finish_mll(cudaStream_t st, const FinishMll& f);
 
@@ -27,6 +28,7 @@ struct FinishCliff {
     double *out_chi, *out_pval, *out_num;   // nullable
     long out_off;
     unsigned long long *tally_chi, *tally_inv;
+    unsigned long long *margin_chi, *margin_inv;   // as FinishMll::margin
 };
 void launch_finish_cliff(cudaStream_t st, const FinishCliff& f);
 

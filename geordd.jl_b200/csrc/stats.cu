@@ -124,6 +124,19 @@ __device__ __forceinline__ double sum_partials(const double* part, int nblocks, 
     return s;
 }
 
+// Smallest distance between any simulated statistic and the observed threshold, kept as the bit pattern of a non-negative
+// double (ordered like the integers): the caller learns how far the exact exceedance count is from flipping
+// (SURVEY §5 "minimum margin") without fetching the statistics.
+__device__ __forceinline__ void margin_min(bool live, double dist, unsigned long long* slot) {
+    unsigned long long b = live && dist == dist ? (unsigned long long)__double_as_longlong(fabs(dist)) : ~0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long ob = __shfl_xor_sync(0xffffffffu, b, o);
+        b = ob < b ? ob : b;
+    }
+    if ((threadIdx.x & 31) == 0 && b != ~0ull) atomicMin(slot, b);
+}
+
 __device__ __forceinline__ void block_tally(bool hit, unsigned long long* counter) {
     unsigned ballot = __ballot_sync(0xffffffffu, hit);
     __shared__ int sh_cnt;
@@ -138,6 +151,7 @@ __device__ __forceinline__ void block_tally(bool hit, unsigned long long* counte
 __global__ void finish_mll_kernel(FinishMll f) {
     long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
     bool hit = false;
+    double dist = 0.0;
     if (c < f.ndraws) {
         double dN = sum_partials(f.partN, f.nbN, f.ncols, c);
         double dT = sum_partials(f.partT, f.nbT, f.ncols, c);
@@ -149,7 +163,9 @@ __global__ void finish_mll_kernel(FinishMll f) {
         if (f.out_null) f.out_null[f.out_off + c] = mllN;
         if (f.out_alt) f.out_alt[f.out_off + c] = alt;
         hit = (alt - mllN) > f.dmll_obs;     // mean(dmll_sim .> dmll_obs), src/hypotest_mll.jl:42-44
+        dist = (alt - mllN) - f.dmll_obs;
     }
+    if (f.margin) margin_min(c < f.ndraws, dist, f.margin);
     block_tally(hit, f.tally);
 }
 void launch_finish_mll(cudaStream_t st, const FinishMll& f) {
@@ -162,11 +178,13 @@ void launch_finish_mll(cudaStream_t st, const FinishMll& f) {
 __global__ void finish_cliff_kernel(FinishCliff f) {
     long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
     bool hit_chi = false, hit_inv = false;
+    double dist_chi = 0.0, dist_inv = 0.0;
     if (c < f.ndraws) {
         if (f.part_chi) {
             double chi = sum_partials(f.part_chi, f.nb, f.ncols, c);
             if (f.out_chi) f.out_chi[f.out_off + c] = chi;
             hit_chi = chi > f.chi_obs;
+            dist_chi = chi - f.chi_obs;
         }
         if (f.part_num) {
             double num = sum_partials(f.part_num, f.nb, f.ncols, c);
@@ -179,8 +197,11 @@ __global__ void finish_cliff_kernel(FinishCliff f) {
             if (f.out_pval) f.out_pval[f.out_off + c] = p;
             if (f.out_num) f.out_num[f.out_off + c] = num;
             hit_inv = p < f.pval_obs;
+            dist_inv = p - f.pval_obs;
         }
     }
+    if (f.part_chi && f.margin_chi) margin_min(c < f.ndraws, dist_chi, f.margin_chi);
+    if (f.part_num && f.margin_inv) margin_min(c < f.ndraws, dist_inv, f.margin_inv);
     if (f.part_chi) block_tally(hit_chi, f.tally_chi);
     if (f.part_num) block_tally(hit_inv, f.tally_inv);
 }

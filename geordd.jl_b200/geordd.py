@@ -216,6 +216,13 @@ class Context:
         self.check(self.lib.geordd_ctx_set_mll_forward_only(self._h, 1 if on else 0))
         self._mll_forward_only = bool(on)
 
+    def last_min_margin(self):
+        """(chi2, invvar p, delta-mll) minimum |statistic - threshold| of the last Monte-Carlo call: the certificate that the
+        exceedance count is exact (it can only change if statistics move by more than this)."""
+        out = (C.c_double * 3)()
+        self.check(self.lib.geordd_ctx_last_min_margin(self._h, out))
+        return tuple(out)
+
     def profile(self, enable: bool) -> None:
         self.check(self.lib.geordd_ctx_profile(self._h, 1 if enable else 0))
 
@@ -1410,43 +1417,62 @@ def placebo_sentinels(angle: float, shift: float, X, npoints: int) -> np.ndarray
     return fmat(np.vstack([np.linspace(ext[0][0], ext[1][0], npoints), np.linspace(ext[0][1], ext[1][1], npoints)]))
 
 
-def _placebo_split(angle, X, Y, kern, mean, logNoise):
+def _placebo_split(angle, X, Y, kern, mean, logNoise, ctx=None):
     X = fmat(X)
     Y = np.asarray(Y, dtype=np.float64)
     shift = shift_for_even_split(angle, X)
     left = left_points(angle, shift, X)
-    gl, gr = GPE.fit_many([X[:, left], X[:, ~left]], [Y[left], Y[~left]], mean, kern, logNoise)
+    gl, gr = GPE.fit_many([X[:, left], X[:, ~left]], [Y[left], Y[~left]], mean, kern, logNoise, ctx=ctx)
     return shift, gl, gr
 
 
-def placebo_chi(angle: float, X, Y, kern, mean, logNoise: float, nsim: int, **kw) -> float:
+def placebo_chi(angle: float, X, Y, kern, mean, logNoise: float, nsim: int, ctx=None, **kw) -> float:
     """placebo_chi (src/hypotest_chi2.jl:62-76)."""
-    shift, gl, gr = _placebo_split(angle, X, Y, kern, mean, logNoise)
+    shift, gl, gr = _placebo_split(angle, X, Y, kern, mean, logNoise, ctx)
     Xb = placebo_sentinels(angle, shift, X, 100)
     return boot_chi2test(gl, gr, Xb, nsim, **kw)
 
 
-def placebo_invvar(angle: float, X, Y, kern, mean, logNoise: float) -> float:
+def placebo_invvar(angle: float, X, Y, kern, mean, logNoise: float, ctx=None) -> float:
     """placebo_invvar (src/hypotest_invvar.jl:162-175)."""
-    shift, gl, gr = _placebo_split(angle, X, Y, kern, mean, logNoise)
+    shift, gl, gr = _placebo_split(angle, X, Y, kern, mean, logNoise, ctx)
     Xb = placebo_sentinels(angle, shift, X, 100)
     return pval_invvar_calib(gl, gr, Xb)
 
 
-def placebo_mll(angle: float, X, Y, kern, mean, logNoise: float, nsim: int, **kw) -> float:
+def placebo_mll(angle: float, X, Y, kern, mean, logNoise: float, nsim: int, ctx=None, **kw) -> float:
     """placebo_mll (src/hypotest_mll.jl:47-60)."""
-    _, gl, gr = _placebo_split(angle, X, Y, kern, mean, logNoise)
+    _, gl, gr = _placebo_split(angle, X, Y, kern, mean, logNoise, ctx)
     return boot_mlltest(gl, gr, nsim, **kw)
 
 
-def placebo_sweep(which: str, angles, X, Y, kern, mean, logNoise: float, nsim: int = 0, **kw) -> np.ndarray:
+def placebo_sweep(which: str, angles, X, Y, kern, mean, logNoise: float, nsim: int = 0, workers: int = 1, **kw) -> np.ndarray:
     """The placebo sweep of the notebooks (`[placebo_chi(angle, ...) for angle in 1:2:180]`,
-    notebooks/NYC_analysis-2015.ipynb:1452-1555): one p-value per angle.  Under torch.distributed the angles are dealt
-    to the ranks (one independent fit + test per GPU at a time, parallel.map_sharded); single process: a loop."""
+    notebooks/NYC_analysis-2015.ipynb:1452-1555): one p-value per angle.
+      * Under torch.distributed the angles are dealt to the ranks (parallel.map_sharded), one all-gather of the results.
+      * workers > 1: the angles of this process are additionally spread over `workers` host threads, each with its OWN
+        context (stream, scheduling scratch, memory pool) on the same GPU.  A half-district fit uses a few SMs, so several
+        independent (fit + test) problems then run side by side on the chip; the ABI calls release the GIL.
+        Results do not depend on `workers` (every problem is computed by the same kernels)."""
     from . import parallel
-    fns = {"chi": lambda a: placebo_chi(a, X, Y, kern, mean, logNoise, nsim, **kw),
-           "mll": lambda a: placebo_mll(a, X, Y, kern, mean, logNoise, nsim, **kw),
-           "invvar": lambda a: placebo_invvar(a, X, Y, kern, mean, logNoise)}
-    if which not in fns:
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+    if which not in ("chi", "mll", "invvar"):
         raise ValueError("which must be 'chi', 'mll' or 'invvar'")
-    return parallel.map_sharded(fns[which], list(angles))
+    base = default_context()
+    local = threading.local()
+
+    def one(a):
+        ctx = getattr(local, "ctx", None)
+        if ctx is None:
+            ctx = local.ctx = base if workers <= 1 else Context(base.device)
+        if which == "chi":
+            return placebo_chi(a, X, Y, kern, mean, logNoise, nsim, ctx=ctx, **kw)
+        if which == "mll":
+            return placebo_mll(a, X, Y, kern, mean, logNoise, nsim, ctx=ctx, **kw)
+        return placebo_invvar(a, X, Y, kern, mean, logNoise, ctx=ctx)
+
+    if workers <= 1:
+        return parallel.map_sharded(one, list(angles))
+    with ThreadPoolExecutor(max_workers=int(workers)) as pool:
+        return parallel.map_sharded(one, list(angles), mapper=lambda f, items: list(pool.map(f, items)))

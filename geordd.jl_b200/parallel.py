@@ -57,17 +57,19 @@ def gather_stats(local, nsim: int, device=None):
     return np.concatenate([o[:s].cpu().numpy() for o, s in zip(out, sizes)])
 
 
-def map_sharded(fn, items, device=None):
+def map_sharded(fn, items, device=None, mapper=None):
     """The second, coarser parallel axis of SURVEY §8e: independent problems (placebo angles, adjacent region pairs --
     notebooks/NYC_analysis-2015.ipynb:1452-1555, src/regiondata.jl:64-68) are dealt contiguously to the ranks, each
     rank evaluates `fn(item)` (a float) for its share on its own GPU with no data-path collective, and the results
-    are assembled with one all-gather.  Single process: plain map."""
+    are assembled with one all-gather.  Single process: plain map.  `mapper(fn, items)` replaces the in-process loop
+    (e.g. a thread pool whose workers own separate GPU contexts)."""
     import numpy as np
     import torch.distributed as dist
     items = list(items)
+    run = mapper if mapper is not None else (lambda f, its: [f(it) for it in its])
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return np.array([float(fn(it)) for it in items])
+        return np.array([float(v) for v in run(fn, items)])
     rank, world = dist.get_rank(), dist.get_world_size()
     lo, cnt = shard_draws(len(items), rank, world)
-    local = np.array([float(fn(it)) for it in items[lo:lo + cnt]])
+    local = np.array([float(v) for v in run(fn, items[lo:lo + cnt])])
     return gather_stats(local, len(items), device=device)

@@ -83,6 +83,11 @@ GEORDD_API int geordd_ctx_set_max_batch(geordd_ctx* ctx, long max_batch);
  * src/hypotest_mll.jl:1-19).  Same statistic in exact arithmetic (rounding-level differences, ~1e-12 relative), 6 m^2
  * instead of 16 m^2 flop per draw.  Ignored when the caller asks for the final draw's y / alpha. */
 GEORDD_API int geordd_ctx_set_mll_forward_only(geordd_ctx* ctx, int enable);
+/* Certificate for the exact exceedance counts of the LAST geordd_null_* / geordd_power call on this context: the smallest
+ * |simulated statistic - observed threshold| over all draws, for (chi2, inverse-variance p-value, delta-mll); +Inf where the
+ * statistic was not simulated or the threshold was infinite.  A count can only differ from the reference's if the
+ * statistics disagree by more than this margin (SURVEY §5, §7 hard part 2). */
+GEORDD_API int geordd_ctx_last_min_margin(const geordd_ctx* ctx, double* margin3);
 
 /* ---- K1 covariance assembly: cov(kernel, X, X) + diag_add*I and cov(kernel, X1, X2) ----------
  * replaces GaussianProcesses.cov / cov! (call sites src/hypotest_chi2.jl:38-39, src/power.jl:60-62,

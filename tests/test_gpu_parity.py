@@ -250,6 +250,9 @@ def test_null_chi2_invvar_mll_match_oracle(G, O, ctx, kind, ragged, mean):
     assert relerr(sims, sims_o) < TOL and np.max(np.abs(sims - sims_o) / sims_o) < 1e-7
     assert _margin(sims_o, obs_o) > 1e-6                   # certificate for the exact count
     assert cnt == c_o and cnt / S == p_o
+    # the library reports the same certificate itself (geordd_ctx_last_min_margin): min |chi2_s - chi_obs| over the draws
+    mm = ctx.last_min_margin()
+    assert abs(mm[0] - np.min(np.abs(sims - obs_o))) <= 1e-12 * obs_o and mm[1] == math.inf and mm[2] == math.inf
     assert abs(obs - obs_o) < 1e-7 * obs_o
     assert gN.jitter_rounds == O.null_setup(oT, oC, Xb, 0.0).jitter_rounds
     # mll (re-uses the same handle: sentinels not needed)
@@ -257,6 +260,7 @@ def test_null_chi2_invvar_mll_match_oracle(G, O, ctx, kind, ragged, mean):
     simsm, cntm, mnull, malt = G.nsim_logP(gT, gC, gN, S, Z=Z, dmll_obs=dobs_o, return_count=True)
     assert relerr(malt - mnull, dsim_o) < TOL
     assert _margin(dsim_o, dobs_o) > 1e-6 and cntm == cm_o
+    assert abs(ctx.last_min_margin()[2] - np.min(np.abs((malt - mnull) - dobs_o))) <= 1e-9 * abs(dobs_o)
     assert abs((gT.mll + gC.mll - oN_mll0) - dobs_o) < 1e-8 * (abs(gT.mll) + abs(gC.mll) + abs(oN_mll0))
     # nsim_logP leaves gpNull at the last draw (src/hypotest_mll.jl:6,10,14)
     oN = O.make_null(oT, oC)
@@ -521,6 +525,12 @@ def test_placebo_sweep_single_process(G, O, ctx):
     assert np.array_equal(ps, np.array([G.placebo_invvar(a, X, Y, k, G.MeanZero(), math.log(0.3)) for a in angles]))
     pc = G.placebo_sweep("chi", angles[:2], X, Y, k, G.MeanZero(), math.log(0.3), 200, seed=3)
     assert np.all((pc >= 0.0) & (pc <= 1.0))
+    # several independent (fit + test) problems side by side on the GPU: one context per host thread, same answers
+    many = [float(a) for a in range(1, 180, 12)]
+    for which in ("chi", "mll"):
+        p1 = G.placebo_sweep(which, many, X, Y, k, G.MeanZero(), math.log(0.3), 300, seed=5)
+        p4 = G.placebo_sweep(which, many, X, Y, k, G.MeanZero(), math.log(0.3), 300, seed=5, workers=4)
+        assert np.array_equal(p1, p4)
 
 
 def test_full_size_identities_c4(G, O, ctx):
