@@ -130,6 +130,7 @@ _SIGS = {
     "geordd_comm_init_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
     "geordd_comm_allreduce_tally": (C.c_int, [C.c_void_p, c_ll_p, C.c_int]),
     "geordd_comm_destroy": (C.c_int, [C.c_void_p]),
+    "geordd_dbg_guard_violations": (C.c_longlong, []),
     "geordd_dbg_normals": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_ulonglong, C.c_int, C.c_int, c_double_p]),
     "geordd_dbg_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, c_double_p,
                                   C.c_int, c_double_p, C.c_int, C.c_double, c_double_p, C.c_int, C.c_int]),

@@ -1,6 +1,7 @@
 // C ABI, part 1: context, profiling, covariance assembly, single-region GP fit.
 #include "api_internal.h"
 #include <algorithm>
+#include <mutex>
 #include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges are no-ops unless a profiler is attached
 
 namespace geordd {
@@ -88,6 +89,41 @@ void download2d(geordd_ctx* c, double* dst, long ldd, const double* src, long ld
 
 static const size_t kPoolCapBytes = (size_t)64 << 30;
 
+// ---- guard mode (GEORDD_GUARD=1): our own out-of-bounds detector ----------------------------------------------------
+// compute-sanitizer is closed on the B200 pool this library is developed on, so the allocator can bracket every device
+// buffer with 64 KiB guard zones filled with 0xFF (= a NaN pattern as doubles): an out-of-bounds WRITE is found when the
+// buffer is released (the guards are read back and compared), an out-of-bounds READ of up to 64 KiB turns into NaN in the
+// results (scripts/sanitize_driver.py asserts every statistic finite).  Buffers are not pooled and not rounded up in this
+// mode, so the first byte past the requested size is already guard.  geordd_dbg_guard_violations() counts the hits.
+static const bool kGuard = getenv("GEORDD_GUARD") != nullptr;
+static const size_t kGuardBytes = (size_t)64 << 10;
+static std::atomic<long long> g_guard_violations{0};
+static std::unordered_map<void*, size_t> g_guard_sizes;   // user pointer -> user bytes (guard mode only; one thread per ctx, global map locked)
+static std::mutex g_guard_mutex;
+
+static void guard_check_and_free(void* user, cudaStream_t st) {
+    size_t bytes = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_guard_mutex);
+        auto it = g_guard_sizes.find(user);
+        if (it == g_guard_sizes.end()) return;
+        bytes = it->second;
+        g_guard_sizes.erase(it);
+    }
+    char* raw = (char*)user - kGuardBytes;
+    std::vector<unsigned char> h(2 * kGuardBytes);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), raw, kGuardBytes, cudaMemcpyDeviceToHost);
+    cudaMemcpy(h.data() + kGuardBytes, raw + kGuardBytes + bytes, kGuardBytes, cudaMemcpyDeviceToHost);
+    long long bad = 0;
+    for (unsigned char v : h) bad += v != 0xFF;
+    if (bad) {
+        g_guard_violations += 1;
+        fprintf(stderr, "geordd_b200 GUARD: %lld guard bytes of a %zu-byte buffer were overwritten\n", bad, bytes);
+    }
+    cudaFree(raw);
+}
+
 static void pool_trim(geordd_ctx* c, size_t keep_bytes) {
     while (c->pool_cached_bytes > keep_bytes && !c->pool_free.empty()) {
         auto it = std::prev(c->pool_free.end());   // largest first
@@ -100,6 +136,19 @@ static void pool_trim(geordd_ctx* c, size_t keep_bytes) {
 double* dalloc(size_t count, cudaStream_t st, bool zero) {
     geordd_ctx* c = tl_ctx;
     if (count == 0) count = 1;
+    if (kGuard) {
+        const size_t ub = (count * sizeof(double) + 15) / 16 * 16;
+        char* raw = nullptr;
+        if (cudaMalloc(&raw, ub + 2 * kGuardBytes) != cudaSuccess) {
+            cudaGetLastError();
+            throw ApiError(GEORDD_ERR_NOMEM, "cudaMalloc (guard mode) failed");
+        }
+        GD_CUDA(cudaMemsetAsync(raw, 0xFF, ub + 2 * kGuardBytes, st));   // the buffer itself starts as NaN too: reads of
+        if (zero) GD_CUDA(cudaMemsetAsync(raw + kGuardBytes, 0, count * sizeof(double), st));   // never-written memory show up
+        std::lock_guard<std::mutex> lk(g_guard_mutex);
+        g_guard_sizes[raw + kGuardBytes] = ub;
+        return (double*)(raw + kGuardBytes);
+    }
     size_t bytes = (count * sizeof(double) + 511) / 512 * 512;
     void* p = nullptr;
     if (c) {
@@ -134,6 +183,10 @@ double* dalloc(size_t count, cudaStream_t st, bool zero) {
 void dfree(void* p) {
     if (!p) return;
     geordd_ctx* c = tl_ctx;
+    if (kGuard) {
+        guard_check_and_free(p, c ? c->stream : nullptr);
+        return;
+    }
     if (c) {
         auto it = c->pool_live.find(p);
         if (it != c->pool_live.end()) {
@@ -149,6 +202,8 @@ void dfree(void* p) {
     }
     cudaFree(p);
 }
+
+long long g_guard_violations_get() { return g_guard_violations.load(); }
 
 void ensure_ws(geordd_ctx* c, size_t count) { c->ws.ensure(count, c->stream, false); }
 
@@ -516,6 +571,8 @@ int geordd_ctx_set_max_batch(geordd_ctx* c, long mb) {
     c->max_batch = mb;
     return 0;
 }
+
+long long geordd_dbg_guard_violations(void) { return geordd::g_guard_violations_get(); }
 
 int geordd_ctx_last_min_margin(const geordd_ctx* c, double* margin3) {
     if (!c || !margin3) return GEORDD_ERR_ARG;

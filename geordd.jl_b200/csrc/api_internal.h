@@ -161,6 +161,7 @@ double read_scalar(geordd_ctx* c, const double* d);   // sync D2H of one double
 void upload2d(geordd_ctx* c, double* dst, long ldd, const double* src, long lds, int rows, int cols);
 void download2d(geordd_ctx* c, double* dst, long ldd, const double* src, long lds, int rows, int cols);
 void ensure_ws(geordd_ctx* c, size_t count);
+long long g_guard_violations_get();
 
 KernelSpecDev to_dev(const geordd_kernel& k);
 // make_posdef!(K) -> L (App. A.5).  K (npad x npad, lower tiles valid, logical size n) is jittered in

@@ -268,6 +268,9 @@ GEORDD_API int geordd_comm_destroy(geordd_ctx* ctx);
 
 /* ---- debug / test hooks (not part of the reference-facing surface) -----------------------------
  * Device Philox normals copied to the host: Z is n x ndraws. */
+/* GEORDD_GUARD=1 in the environment brackets every device buffer with NaN-filled guard zones (see api_core.cu): number of
+ * buffers whose guards were found overwritten when they were released. */
+GEORDD_API long long geordd_dbg_guard_violations(void);
 GEORDD_API int geordd_dbg_normals(geordd_ctx* ctx, unsigned long long seed, unsigned long long draw0, int ndraws, int n,
                        double* Z);
 /* C = alpha*op(A)*op(B) + beta*C through the DMMA mainloop (host matrices, column-major). transa/transb:

@@ -252,7 +252,7 @@ def test_null_chi2_invvar_mll_match_oracle(G, O, ctx, kind, ragged, mean):
     assert cnt == c_o and cnt / S == p_o
     # the library reports the same certificate itself (geordd_ctx_last_min_margin): min |chi2_s - chi_obs| over the draws
     mm = ctx.last_min_margin()
-    assert abs(mm[0] - np.min(np.abs(sims - obs_o))) <= 1e-12 * obs_o and mm[1] == math.inf and mm[2] == math.inf
+    assert abs(mm[0] - np.min(np.abs(sims - obs_o))) <= 1e-12 * obs_o and mm[2] == math.inf      # (mll not simulated)
     assert abs(obs - obs_o) < 1e-7 * obs_o
     assert gN.jitter_rounds == O.null_setup(oT, oC, Xb, 0.0).jitter_rounds
     # mll (re-uses the same handle: sentinels not needed)
