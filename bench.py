@@ -393,6 +393,8 @@ def main():
     e2e_step(1)
     n_e2e = max(10, args.steps)
     e2e_ms = []
+    sampler2 = ClockSampler(local_rank)
+    sampler2.start()
     for i in range(n_e2e):
         barrier()
         t_wall0 = time.perf_counter()
@@ -402,6 +404,7 @@ def main():
         f1.record(stream)
         torch.cuda.synchronize()
         e2e_ms.append(max_over_ranks(max(f0.elapsed_time(f1), (time.perf_counter() - t_wall0) * 1e3)))   # host work counts too
+    clocks_e2e = sampler2.stop()
     ms_e2e = float(np.median(e2e_ms))
     e2e_val = world * S / (ms_e2e * 1e-3)
     h2d = 8 * (XT.size + XC.size + YT.size + YC.size) * 2            # T, C and the pooled null each upload X and y
@@ -555,6 +558,50 @@ def main():
                            "grad_flops": n2 ** 3 / 3.0 + 2.0 * n2 ** 3, "grad_tflops": (n2 ** 3 / 3.0 + 2.0 * n2 ** 3) / (g_ms * 1e-3) / 1e12,
                            "grad_frac_of_dmma_peak": (n2 ** 3 / 3.0 + 2.0 * n2 ** 3) / (g_ms * 1e-3) / 1e12 / dmma_peak}
             mg.close()
+            # f2: optimize!(mgpcv) on the reference's own example (notebooks/SimulatedExample.ipynb cell 10: n = 300, the 604-column
+            # full-dummy design, 167 f + 99 grad evaluations in 7.95 s on the author's CPU, optimum 123.1640)
+            try:
+                fx = np.load(os.path.join(ROOT, "tests", "golden", "simulated_example.npz"))
+                dummy = lambda v: (np.asarray(v)[None, :] == np.sort(np.unique(v))[:, None]).astype(np.float64)
+                Dn = np.asfortranarray(np.vstack([np.ones((1, 300)), dummy(fx["covarA"]), dummy(fx["covarB"]), dummy(fx["categ"])]))
+                tr = fx["treat"]
+                rdn = {False: G.RegionData(np.asfortranarray(fx["X"][:, ~tr]), fx["Y"][~tr].copy(), np.asfortranarray(Dn[:, ~tr])),
+                       True: G.RegionData(np.asfortranarray(fx["X"][:, tr]), fx["Y"][tr].copy(), np.asfortranarray(Dn[:, tr]))}
+                best = None
+                for _ in range(2):
+                    mgn = G.MultiGPCovars(rdn, G.SEIso(math.log(0.5), 0.0) + G.fix(G.Const(-12.0)), G.LinIso(0.0), 1.0, groupKeys=[False, True], ctx=ctx)
+                    t0 = time.perf_counter()
+                    res = G.optimize(mgn, noise=True, kern=True, domean=False, beta=True, method="BFGS", options=dict(gtol=1e-7, maxiter=500))
+                    dt = time.perf_counter() - t0
+                    best = dt if best is None else min(best, dt)
+                    fmin = -mgn.mll
+                    mgn.close()
+                extra["f2_optimize"] = {"what": "optimize!(MultiGPCovars) on the data of notebooks/SimulatedExample.ipynb (n = 300, p = 604; replayed "
+                                                "bit for bit), from the notebook's initial point; every evaluation is one ABI call; host optimiser = SciPy BFGS",
+                                        "seconds": best, "evaluations": int(res.nfev), "minimum": fmin, "notebook_minimum": 123.1640,
+                                        "notebook_seconds": 7.95, "notebook_evaluations": "167 f + 99 grad"}
+            except Exception as err:
+                extra["f2_optimize"] = {"error": repr(err)}
+            # f3: placebo sweep of the NYC notebook shape (notebooks/NYC_analysis-2015.ipynb:1452-1512: 90 angles x 1000 draws; the
+            # notebook's @time outputs: mll 73.5 / 917.1 s, chi2 36.6 / 430.0 s for its two districts)
+            try:
+                rngp = np.random.default_rng(7)
+                npl = 1000
+                Xp = np.asfortranarray(rngp.random((2, npl)))
+                Yp = np.sin(2.0 * Xp[0]) + 3.0 * Xp[1] ** 2 + 0.3 * rngp.standard_normal(npl)
+                kp = G.Mat12Iso(math.log(ELL), 0.0) + G.Const(math.log(5.0))
+                angles = [float(a) for a in range(1, 180, 2)]
+                f3 = {"what": "placebo_mll / placebo_chi for angle in 1:2:180 (90 angles) x 1000 draws on a 1000-unit district, Matern-1/2 + Const; "
+                              "4 host threads, each with its own context, run independent (split, 2 fits, pooled fit, test) problems side by side",
+                      "notebook_seconds": {"mll": [73.5, 917.1], "chi2": [36.6, 430.0]}}
+                for which in ("mll", "chi"):
+                    G.placebo_sweep(which, angles[:4], Xp, Yp, kp, G.MeanZero(), ln, 1000, seed=1, workers=4)
+                    t0 = time.perf_counter()
+                    G.placebo_sweep(which, angles, Xp, Yp, kp, G.MeanZero(), ln, 1000, seed=1, workers=4)
+                    f3[f"placebo_{which}_seconds"] = time.perf_counter() - t0
+                extra["f3_placebo_sweep"] = f3
+            except Exception as err:
+                extra["f3_placebo_sweep"] = {"error": repr(err)}
             # K1: covariance assembly against the HBM peak (8 n^2 bytes written + 16 n read)
             try:
                 hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -614,7 +661,8 @@ def main():
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "what": "per step: GPRealisations(T, C) + make_null from pinned host X/y + 20000 mll draws + D2H of both "
                                 "statistic vectors (boot_mlltest through the host API); median over the steps", "steps": n_e2e,
-                        "ms_per_step_median": ms_e2e, "ms_per_step_min": float(np.min(e2e_ms)), "ms_per_step_max": float(np.max(e2e_ms))},
+                        "ms_per_step_median": ms_e2e, "ms_per_step_min": float(np.min(e2e_ms)), "ms_per_step_max": float(np.max(e2e_ms)),
+                        "clocks": clocks_e2e},
                 "gpu_launches": int(launches),
                 "roofline": roofline,
                 "cpu_baseline": cpu,
