@@ -381,6 +381,70 @@ geordd_gp* gp_create(geordd_ctx* c, const geordd_kernel* k, const double* X, int
     return gp;
 }
 
+// Tails of the fits of a batch -- mirror the factor, log-determinant, alpha = cK \ (y - m), y'alpha -- are independent chains
+// of small / latency-bound launches (the few-column solve is a chain of T dependent row blocks on T SMs).  They run side by
+// side on up to four side streams (own job counter and flag region per lane), forked from and joined back into the
+// context's stream with events; all scalars come back with ONE copy.  Same kernels, same arithmetic as gp_finish.
+static void gp_finish_batch(geordd_ctx* c, int nfit, geordd_gp** gps, const double* const* ys) {
+    for (int l = 0; l < NARROW_LANES; ++l) {
+        if (!c->side[l]) GD_CUDA(cudaStreamCreateWithFlags(&c->side[l], cudaStreamNonBlocking));
+        if (!c->ev_join[l]) GD_CUDA(cudaEventCreateWithFlags(&c->ev_join[l], cudaEventDisableTiming));
+    }
+    if (!c->ev_fork) GD_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    constexpr int kRound = 24;   // two scalars per fit in d_scal[8 .. 8 + 2 * kRound)
+    std::vector<std::vector<double>> resid(nfit);
+    for (int f0 = 0; f0 < nfit; f0 += kRound) {
+        const int nf = std::min(kRound, nfit - f0);
+        for (int f = f0; f < f0 + nf; ++f) {   // residuals y - m (host -> device) on the main stream
+            geordd_gp* gp = gps[f];
+            gp->y.assign(ys[f], ys[f] + gp->n);
+            resid[f].assign(gp->npad, 0.0);
+            for (int i = 0; i < gp->n; ++i) resid[f][i] = ys[f][i] - gp->k.mean_const;
+            GD_CUDA(cudaMemcpyAsync(gp->dR, resid[f].data(), (size_t)gp->npad * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        }
+        GD_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+        for (int f = f0; f < f0 + nf; ++f) {
+            geordd_gp* gp = gps[f];
+            const int lane = (f - f0) % NARROW_LANES;
+            cudaStream_t s = c->side[lane];
+            const int npad = gp->npad;
+            double* slot = c->d_scal + 8 + 2 * (f - f0);
+            if (f - f0 < NARROW_LANES) GD_CUDA(cudaStreamWaitEvent(s, c->ev_fork, 0));
+            gp->jitter_rounds = 0;
+            launch_mirror_factor(s, gp->dL, npad);
+            launch_logdiag_sum(s, gp->dL, npad, gp->n, slot);
+            GD_CUDA(cudaMemsetAsync(gp->dAlpha, 0, (size_t)npad * 64 * sizeof(double), s));
+            GD_CUDA(cudaMemcpyAsync(gp->dAlpha, gp->dR, (size_t)npad * sizeof(double), cudaMemcpyDeviceToDevice, s));
+            if (npad > TILE) {
+                launch_solve_narrow(s, c->sched, SOLVE_FWD, gp->dL, npad, gp->dAlpha, npad, 1, lane);
+                launch_solve_narrow(s, c->sched, SOLVE_BWD, gp->dL, npad, gp->dAlpha, npad, 1, lane);
+            } else {   // single tile: the wide kernel (gp_update_alpha's path for npad == TILE); serialised on the main stream below
+                continue;
+            }
+            launch_reduce(s, 2, gp->dR, gp->dAlpha, 0, gp->n, 0, slot + 1);
+        }
+        for (int l = 0; l < std::min(nf, NARROW_LANES); ++l) {
+            GD_CUDA(cudaEventRecord(c->ev_join[l], c->side[l]));
+            GD_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join[l], 0));
+        }
+        for (int f = f0; f < f0 + nf; ++f) {   // one-tile GPs: same launches as gp_update_alpha, on the main stream
+            geordd_gp* gp = gps[f];
+            if (gp->npad > TILE) continue;
+            SolveEpilogue none;
+            pd_solve(c, gp->dL, gp->npad, gp->dAlpha, gp->npad, 64, none, 1);
+            launch_reduce(c->stream, 2, gp->dR, gp->dAlpha, 0, gp->n, 0, c->d_scal + 8 + 2 * (f - f0) + 1);
+        }
+        GD_CUDA(cudaMemcpyAsync(c->h_scal + 8, c->d_scal + 8, (size_t)2 * nf * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        check_abort(c);   // synchronises the main stream (which has joined the side streams)
+        for (int f = f0; f < f0 + nf; ++f) {
+            geordd_gp* gp = gps[f];
+            gp->logdet = 2.0 * c->h_scal[8 + 2 * (f - f0)];
+            const double quad = c->h_scal[8 + 2 * (f - f0) + 1];
+            gp->mll = -quad / 2.0 - gp->logdet / 2.0 - (double)gp->n * std::log(2.0 * M_PI) / 2.0;
+        }
+    }
+}
+
 // Several independent fits (the regions of GPRealisations, the halves of a placebo split): all covariance matrices are
 // assembled first, then factored by ONE dataflow launch whose merged job list interleaves their critical paths
 // (potrf.cu).  A batch in which any matrix needs make_posdef! jitter is redone matrix by matrix (rare).
@@ -412,17 +476,15 @@ void gp_create_batch(geordd_ctx* c, int nfit, const geordd_kernel* ks, const dou
             if (info < 0) throw ApiError(GEORDD_ERR_WATCHDOG, "potrf watchdog fired");
             if (info > 0) fallback = true;
         }
-        for (int f = 0; f < nfit; ++f) {
-            geordd_gp* gp = gps[f];
-            if (fallback) {
+        if (fallback) {
+            for (int f = 0; f < nfit; ++f) {
+                geordd_gp* gp = gps[f];
                 infos[f] = make_posdef(c, gp->dK, gp->dL, gp->npad, gp->n, gp->npad, &gp->jitter_rounds);
                 if (infos[f] != 0) { gp_free(gp); gps[f] = nullptr; continue; }
-            } else {
-                gp->jitter_rounds = 0;
-                ProfScope ps(c, PC_MISC);
-                launch_mirror_factor(c->stream, gp->dL, gp->npad);
+                gp_finish(gp, ys[f]);
             }
-            gp_finish(gp, ys[f]);
+        } else {
+            gp_finish_batch(c, nfit, gps, ys);
         }
     } catch (...) {
         for (int f = 0; f < nfit; ++f) { if (gps[f]) gp_free(gps[f]); gps[f] = nullptr; }
@@ -510,6 +572,11 @@ int geordd_ctx_destroy(geordd_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     geordd_comm_destroy(c);
+    for (int l = 0; l < 4; ++l) {
+        if (c->side[l]) cudaStreamDestroy(c->side[l]);
+        if (c->ev_join[l]) cudaEventDestroy(c->ev_join[l]);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     cudaFree(c->sched.counter); cudaFree(c->sched.flags); cudaFree(c->sched.abort_word); cudaFree(c->sched.jobs);

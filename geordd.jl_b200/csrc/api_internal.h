@@ -75,6 +75,8 @@ struct geordd_ctx {
     int* h_info = nullptr;                    // pinned, 4 ints
     unsigned long long* d_tally = nullptr;    // 8 counters
     unsigned long long* h_tally = nullptr;    // pinned
+    cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};   // side streams: independent per-GP tails of a batched fit
+    cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
     geordd::DevBuf ws;                        // split-K workspace
     geordd::DevBuf tmp0, tmp1, tmp2, tmp3;    // generic scratch matrices
     // profiling

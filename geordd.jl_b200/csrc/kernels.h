@@ -165,8 +165,12 @@ struct SolveSeqItem {
     int after = -1;
 };
 void launch_solve_seq(cudaStream_t st, Sched& sched, const SolveSeqItem* items, int n, int ncols);
+// lane (0..NARROW_LANES-1) selects a private job counter / flag region: narrow solves on different lanes may run concurrently
+// on different streams (the alpha solves of the fits of a batch).
+constexpr int NARROW_LANES = 4;
+constexpr size_t NARROW_LANE_FLAGS = (size_t)1 << 16;
 void launch_solve_narrow(cudaStream_t st, Sched& sched, SolveMode mode, const double* L, int npad, double* B, long ldb,
-                         int live_cols);
+                         int live_cols, int lane = 0);
 
 // ---- gemm.cu --------------------------------------------------------------------------------------
 // C(M x N) = alpha * op(A) * op(B) + beta * C.  M multiple of 128, N multiple of 64, K multiple of 16.

@@ -117,6 +117,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) solve_dataflow_kernel(SolveParams
         const int job = sh_job;
         if (job >= njobs) break;
         const int lvl = job / p.nslabs, s = job % p.nslabs;
+        // FWD ascending, BWD descending (dependencies); TRMM has none and is dealt longest jobs first (row block rb multiplies
+        // rb + 1 tiles), so that the kernel's tail consists of its shortest jobs.
         const int rb = (MODE == SOLVE_FWD) ? lvl : (p.T - 1 - lvl);
         double* Bslab = (MODE == SOLVE_TRMM || XB) ? p.B + (long)s * (p.T * CHUNKS_PER_TILE_S) * ZB_ELEMS   // ZB: slab s
                                                    : p.B + (long)s * SLAB * p.ldb;

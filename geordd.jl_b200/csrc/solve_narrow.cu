@@ -238,11 +238,12 @@ static void launch_narrow_mode(cudaStream_t st, Sched& sched, const NarrowParams
 }
 
 void launch_solve_narrow(cudaStream_t st, Sched& sched, SolveMode mode, const double* L, int npad, double* B, long ldb,
-                         int live_cols) {
+                         int live_cols, int lane) {
     NarrowParams p;
     p.L = L; p.T = npad / TILE; p.B = B; p.ldb = ldb; p.nslabs = (live_cols + NCOL - 1) / NCOL;
-    p.flags = sched.flags; p.counter = sched.counter; p.abort_word = sched.abort_word;
-    cudaMemsetAsync(sched.counter, 0, sizeof(unsigned), st);
+    // lane > 0: own job counter and flag region, so that solves of independent GPs can run side by side on other streams
+    p.flags = sched.flags + (size_t)lane * NARROW_LANE_FLAGS; p.counter = sched.counter + lane; p.abort_word = sched.abort_word;
+    cudaMemsetAsync(p.counter, 0, sizeof(unsigned), st);
     sched.epoch++;
     p.epoch = sched.epoch;
     if (mode == SOLVE_FWD) launch_narrow_mode<SOLVE_FWD>(st, sched, p);

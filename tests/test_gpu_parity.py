@@ -93,6 +93,32 @@ def test_gp_fit_matches_oracle(G, O, ctx, n, kind):
     assert relerr(mu, O.predict_mu(o, X[:, :5], O.cov_cross(spec, X[:, :5], X))) < TOL
 
 
+def test_batched_fits_equal_single_fits_bit_for_bit(G, O, ctx):
+    """geordd_gp_fit_batch (GPRealisations, placebo halves): one merged dataflow Cholesky launch, per-GP tails on side
+    streams -- alpha, mll, log-determinant identical to one geordd_gp_fit per region, incl. one-tile and ragged sizes;
+    a batch containing a matrix that needs make_posdef! jitter falls back to the per-matrix protocol."""
+    rng = np.random.default_rng(11)
+    sizes = [100, 129, 300, 513, 128, 700, 64]
+    xs = [np.asfortranarray(rng.random((2, n))) for n in sizes]
+    ys = [rng.standard_normal(n) for n in sizes]
+    k = G.Mat52Iso(math.log(0.25), 0.1) + G.Const(math.log(3.0))
+    ln = math.log(0.2)
+    batch = G.GPE.fit_many(xs, ys, G.MeanConst(0.3), k, ln)
+    for g, x, y in zip(batch, xs, ys):
+        one = G.GPE(x, y, G.MeanConst(0.3), k, ln)
+        assert g.mll == one.mll and np.array_equal(g.alpha, one.alpha) and g.jitter_rounds == one.jitter_rounds == 0
+        oo = O.gp_fit(O.KernelSpec(3, 0.25, math.exp(0.2), 9.0, 0.3), x, y, ln)
+        assert abs(g.mll - oo.mll) < TOL * abs(oo.mll) and relerr(g.alpha, oo.alpha) < TOL
+    # duplicate units make the second matrix numerically singular without noise: jitter rounds, identical to the single fit
+    xd = np.asfortranarray(np.hstack([xs[1], xs[1][:, :40]]))
+    yd = rng.standard_normal(xd.shape[1])
+    kk = G.SEIso(math.log(0.3), 0.0)
+    pair = G.GPE.fit_many([xs[2], xd], [ys[2], yd], G.MeanZero(), kk, -30.0)
+    ref = G.GPE(xd, yd, G.MeanZero(), kk, -30.0)
+    assert pair[1].jitter_rounds == ref.jitter_rounds >= 1 and pair[1].mll == ref.mll and np.array_equal(pair[1].alpha, ref.alpha)
+    assert pair[0].mll == G.GPE(xs[2], ys[2], G.MeanZero(), kk, -30.0).mll
+
+
 def test_make_posdef_jitter_and_failure(G, O, ctx):
     """Duplicate points + tiny noise: Cholesky needs the jitter loop; rounds and results must match the
     oracle's restatement of make_posdef! (App. A.5).  A hopeless matrix raises PosDefException(info)."""
