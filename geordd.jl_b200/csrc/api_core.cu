@@ -12,7 +12,14 @@ const char* const kProfNames[PC_COUNT] = {"cov", "potrf", "solve_fwd", "solve_bw
                                           "gemm", "rng", "finish", "lu", "misc", "solve_seq"};
 
 // ---- profiling -------------------------------------------------------------------------------------
-ProfScope::ProfScope(geordd_ctx* ctx, int cls) : c(ctx) {
+// GEORDD_DEBUG_SYNC=1: synchronise before and after every profiled phase and name the phase in which a CUDA error first
+// shows up (errors otherwise surface at the next synchronising ABI call, far from the launch that caused them).
+static const bool kDebugSync = getenv("GEORDD_DEBUG_SYNC") != nullptr;
+ProfScope::ProfScope(geordd_ctx* ctx, int cls_) : c(ctx), cls(cls_) {
+    if (kDebugSync) {
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) fprintf(stderr, "geordd_b200 DEBUG_SYNC: %s BEFORE phase '%s' (an un-scoped launch)\n", cudaGetErrorString(e), kProfNames[cls]);
+    }
     nvtxRangePushA(kProfNames[cls]);   // one NVTX range per kernel class / phase (nsys / ncu --nvtx)
     if (!c->prof_on) return;
     cudaEvent_t a, b;
@@ -29,6 +36,10 @@ ProfScope::ProfScope(geordd_ctx* ctx, int cls) : c(ctx) {
 }
 ProfScope::~ProfScope() {
     if (idx >= 0) cudaEventRecord(c->recs[idx].b, c->stream);
+    if (kDebugSync) {
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) fprintf(stderr, "geordd_b200 DEBUG_SYNC: %s after phase '%s'\n", cudaGetErrorString(e), kProfNames[cls]);
+    }
     nvtxRangePop();
 }
 

@@ -152,6 +152,7 @@ namespace geordd {
 // ---- helpers implemented in api_core.cu ------------------------------------------------------------
 struct ProfScope {
     geordd_ctx* c;
+    int cls = 0;
     int idx = -1;
     ProfScope(geordd_ctx* ctx, int cls);
     ~ProfScope();

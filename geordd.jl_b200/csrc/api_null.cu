@@ -111,7 +111,10 @@ static void calib_cov_mu_delta(geordd_gp* T, geordd_gp* C, const double* dXb, in
             launch_cov(c->stream, to_dev(T->k), T->dX, mT, dXb, nb, 2, false, false, 0.0, WT, mTp, mTp, nbp, false);
         }
         pd_solve(c, T->dL, mTp, WT, mTp, nbp, none, nb);
-        P = dalloc((size_t)std::max(mTp, mCp) * nbp, c->stream, false);
+        // P also serves as the nbp x nbp transpose buffer of E below: with more sentinels than units per side (the
+        // Mississippi fixture: 82 / 64 units, 200 sentinels) max(mTp, mCp) * nbp alone is too small -- an out-of-bounds write
+        // that stayed silent inside the caching pool until a trimmed pool left the neighbouring pages unmapped (round 2)
+        P = dalloc((size_t)std::max(std::max(mTp, mCp), nbp) * nbp, c->stream, false);
         // P = KTT * WT_c ; out = WT_c' P
         gemm(c, true, false, mTp, nbp, mTp, 1.0, T->dK, mTp, WT, mTp, 0.0, P, mTp, 0);
         gemm(c, false, false, nbp, nbp, mTp, 1.0, WT, mTp, P, mTp, 0.0, dOut, nbp, 0);

@@ -25,6 +25,17 @@ pc = G.nsim_invvar_calib(gT, gC, d["Xb"], 64, seed=2)
 pw = G.nsim_power(gT, gC, 0.3, d["Xb"], chi, ma - mn, pv, 64, seed=3)
 w = G.weight_at_units(gT, d["Xb"], np.ones(40))
 Xp, dist = G.projection_points_all(gT, np.column_stack([np.linspace(0, 1, 50), np.linspace(0, 1, 50)]))
+# more sentinels than units per side (the Mississippi fixture's shape: 82 / 64 units, 200 sentinels)
+d2 = O.synth_two_region(73, 200, seed=2)
+hT, hC = G.GPE.fit_many([d2["X"][:, :82], d2["X"][:, 82:]], [d2["Y"][:82], d2["Y"][82:]], G.MeanZero(), k, ln)
+hN = G.NullGPE(hT, hC, d2["Xb"], 0.0)
+chi2 = G.nsim_chi(hT, hC, hN, d2["Xb"], 64, seed=1)
+_, _, mn2, ma2 = G.nsim_logP(hT, hC, hN, 64, seed=1, return_count=True)
+pv2 = G.nsim_invvar_pval_uncalib(hT, hC, d2["Xb"], 64, seed=1)
+pw2 = G.nsim_power(hT, hC, 0.2, d2["Xb"], chi2, ma2 - mn2, pv2, 64, seed=3)
+pc2 = G.pval_invvar_calib(hT, hC, d2["Xb"]); pcs2 = G.nsim_invvar_calib(hT, hC, d2["Xb"], 64, seed=4)
+assert np.isfinite(pw2).all() and np.isfinite(pcs2).all() and math.isfinite(pc2)
+hN.close(); hT.close(); hC.close()
 rd = {True: G.RegionData(XT, YT, d["D"][:, :mT]), False: G.RegionData(XC, YC, d["D"][:, mT:])}
 mg = G.MultiGPCovars(rd, G.SEIso(math.log(0.3), 0.0) + G.Const(math.log(20.0)), G.LinIso(0.0), 1.0, groupKeys=[True, False])
 G.update_mll_and_dmll(mg); G.postmean_beta(mg)
