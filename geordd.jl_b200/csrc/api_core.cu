@@ -302,7 +302,7 @@ void pd_solve(geordd_ctx* c, const double* L, int npad, double* B, long ldb, int
 // ---- GP ----------------------------------------------------------------------------------------------
 void gp_free(geordd_gp* gp) {
     if (!gp) return;
-    dfree(gp->dX); dfree(gp->dK); dfree(gp->dL); dfree(gp->dR); dfree(gp->dAlpha);
+    dfree(gp->dX); dfree(gp->dK); dfree(gp->dL); dfree(gp->dDinv); dfree(gp->dR); dfree(gp->dAlpha);
     delete gp;
 }
 
@@ -501,6 +501,19 @@ void gp_create_batch(geordd_ctx* c, int nfit, const geordd_kernel* ks, const dou
         for (int f = 0; f < nfit; ++f) { if (gps[f]) gp_free(gps[f]); gps[f] = nullptr; }
         throw;
     }
+}
+
+// GEORDD_SEQ_SUBST=1 keeps round 1's shared-memory substitution in the fused solve sequence (A/B measurements).
+static const bool kSeqSubst = getenv("GEORDD_SEQ_SUBST") != nullptr;
+const double* gp_diag_inverse(geordd_gp* gp) {
+    if (kSeqSubst) return nullptr;
+    if (!gp->dDinv) {
+        geordd_ctx* c = gp->ctx;
+        gp->dDinv = dalloc(diag_inverse_elems(gp->npad), c->stream, false);
+        ProfScope ps(c, PC_MISC);
+        launch_diag_inverse(c->stream, gp->dL, gp->npad, gp->dDinv);
+    }
+    return gp->dDinv;
 }
 
 void gp_ensure_full_K(geordd_gp* gp) {

@@ -96,6 +96,7 @@ struct geordd_gp {
     double* dX = nullptr;       // dim x n
     double* dK = nullptr;       // npad x npad  (cK.mat, lower tiles; full once mirrored)
     double* dL = nullptr;       // lower Cholesky factor (= U') in TBP storage, factor_elems(npad) doubles
+    double* dDinv = nullptr;    // inverse 32x32 diagonal blocks of dL (built on first use by the null simulations)
     double* dR = nullptr;       // npad         y - m (zero padded)
     double* dAlpha = nullptr;   // npad x 64 slab, column 0 = alpha
     bool k_full = false;
@@ -187,6 +188,7 @@ void gp_create_batch(geordd_ctx* c, int nfit, const geordd_kernel* ks, const dou
 void gp_update_alpha(geordd_gp* gp);   // alpha from dR, mll
 void gp_free(geordd_gp* gp);
 void gp_ensure_full_K(geordd_gp* gp);
+const double* gp_diag_inverse(geordd_gp* gp);   // builds gp->dDinv on first use; nullptr when switched off (GEORDD_SEQ_SUBST=1)
 
 // cliff face on device: mu (nbp), Sigma (nbp x nbp, ld nbp), exactly symmetric.
 void cliff_face_dev(geordd_gp* T, geordd_gp* C, const double* dXb, int nb, int nbp, double* dMu, double* dSigma);

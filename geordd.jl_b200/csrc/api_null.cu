@@ -276,8 +276,8 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
             eT.xb = eC.xb = true;
             eT.dot_self = eC.dot_self = true;
             eT.dot0 = h->partT.p; eC.dot0 = h->partC.p;
-            SolveSeqItem it[2] = {SolveSeqItem{SOLVE_FWD, T->dL, mTp, h->AT.p, eT, -1},
-                                  SolveSeqItem{SOLVE_FWD, C->dL, mCp, h->AC.p, eC, -1}};
+            SolveSeqItem it[2] = {SolveSeqItem{SOLVE_FWD, T->dL, mTp, h->AT.p, eT, -1, gp_diag_inverse(T)},
+                                  SolveSeqItem{SOLVE_FWD, C->dL, mCp, h->AC.p, eC, -1, gp_diag_inverse(C)}};
             ProfScope ps(c, PC_SEQ);
             launch_solve_seq(st, c->sched, it, 2, ncols);
         } else {
@@ -294,17 +294,17 @@ static void run_sims(geordd_null* h, SimRequest& rq) {
             // shortest jobs
             SolveSeqItem it[SOLVE_SEQ_MAX];
             int ns = 0, iN = -1;
-            if (rq.want_mll) { iN = ns; it[ns++] = SolveSeqItem{SOLVE_FWD, N->dL, npN, h->AN.p, none, -1}; }
-            const int iT = ns; it[ns++] = SolveSeqItem{SOLVE_FWD, T->dL, mTp, h->AT.p, none, -1};
-            const int iC = ns; it[ns++] = SolveSeqItem{SOLVE_FWD, C->dL, mCp, h->AC.p, none, -1};
+            if (rq.want_mll) { iN = ns; it[ns++] = SolveSeqItem{SOLVE_FWD, N->dL, npN, h->AN.p, none, -1, gp_diag_inverse(N)}; }
+            const int iT = ns; it[ns++] = SolveSeqItem{SOLVE_FWD, T->dL, mTp, h->AT.p, none, -1, gp_diag_inverse(T)};
+            const int iC = ns; it[ns++] = SolveSeqItem{SOLVE_FWD, C->dL, mCp, h->AC.p, none, -1, gp_diag_inverse(C)};
             if (rq.want_mll) {
                 SolveEpilogue eN;
                 eN.xb = true;
                 eN.wmat = h->RN.p; eN.ldw = npN; eN.dot0 = h->partN.p;
-                it[ns++] = SolveSeqItem{SOLVE_BWD, N->dL, npN, h->AN.p, eN, iN};
+                it[ns++] = SolveSeqItem{SOLVE_BWD, N->dL, npN, h->AN.p, eN, iN, gp_diag_inverse(N)};
             }
-            it[ns++] = SolveSeqItem{SOLVE_BWD, T->dL, mTp, h->AT.p, eT, iT};
-            it[ns++] = SolveSeqItem{SOLVE_BWD, C->dL, mCp, h->AC.p, eC, iC};
+            it[ns++] = SolveSeqItem{SOLVE_BWD, T->dL, mTp, h->AT.p, eT, iT, gp_diag_inverse(T)};
+            it[ns++] = SolveSeqItem{SOLVE_BWD, C->dL, mCp, h->AC.p, eC, iC, gp_diag_inverse(C)};
             ProfScope ps(c, PC_SEQ);
             launch_solve_seq(st, c->sched, it, ns, ncols);
         }

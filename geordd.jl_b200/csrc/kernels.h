@@ -106,6 +106,9 @@ int launch_potrf_batch(cudaStream_t st, Sched& sched, const PotrfItem* items, in
 // dense (n x n column-major, ldd) lower triangle -> TBP factor with identity padding; and back (optionally transposed).
 void launch_factor_pack(cudaStream_t st, const double* dense, long ldd, int n, double* L, int npad);
 void launch_factor_unpack(cudaStream_t st, const double* L, int npad, double* dense, long ldd, int n, bool transpose);
+// Inverses of the 32x32 diagonal blocks of every diagonal tile: Dinv holds (npad / 128) * 4608 doubles (tileops.cuh).
+inline size_t diag_inverse_elems(int npad) { return (size_t)(npad / TILE) * 4 * 32 * 36; }
+void launch_diag_inverse(cudaStream_t st, const double* L, int npad, double* Dinv);
 // Mirror L' into the tiles above the diagonal (needed before any SOLVE_BWD against this factor).
 void launch_mirror_factor(cudaStream_t st, double* L, int npad);
 // out[0] = sum_i log L(i,i) for i < n   (L in TBP storage)
@@ -163,6 +166,7 @@ struct SolveSeqItem {
     double* B;
     SolveEpilogue epi;
     int after = -1;
+    const double* Dinv = nullptr;   // inverse diagonal blocks of L (launch_diag_inverse); nullptr: substitution in shared memory
 };
 void launch_solve_seq(cudaStream_t st, Sched& sched, const SolveSeqItem* items, int n, int ncols);
 // lane (0..NARROW_LANES-1) selects a private job counter / flag region: narrow solves on different lanes may run concurrently

@@ -270,6 +270,34 @@ __global__ void __launch_bounds__(256) mirror_factor_kernel(double* __restrict__
     for (int c = ty0; c < 64; c += 4) dst[(long)c * TLD + tx] = t[tx][c];
 }
 
+// Inverses of the four 32x32 diagonal blocks of every diagonal tile (tileops.cuh: solve_tile_inv), one CTA per tile, one
+// warp per block, one lane per column of the inverse (forward substitution on e_j in registers; 496 FMAs per lane).
+__global__ void __launch_bounds__(128) diag_inverse_kernel(const double* __restrict__ L, int T, double* __restrict__ Dinv) {
+    __shared__ double Ls[TILE / NB][NB][NB + 1];
+    const int t = blockIdx.x, b = threadIdx.x >> 5, j = threadIdx.x & 31, o = NB * b;
+    const double* Lt = L + tile_off(t, t, T);
+#pragma unroll 4
+    for (int c = 0; c < NB; ++c) Ls[b][j][c] = Lt[(long)(o + c) * TLD + o + j];   // row j of the block, coalesced along j
+    __syncwarp();
+    double x[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        double s = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) s = fma(-Ls[b][i][k], x[k], s);
+        x[i] = s / Ls[b][i][i];
+    }
+    double* out = Dinv + (long)t * DINV_TILE + b * DINV_BLK + j * LRS;   // column j of the inverse, rows contiguous
+#pragma unroll
+    for (int i = 0; i < NB; ++i) out[i] = (i >= j) ? x[i] : 0.0;
+#pragma unroll
+    for (int i = NB; i < LRS; ++i) out[i] = 0.0;
+}
+
+void launch_diag_inverse(cudaStream_t st, const double* L, int npad, double* Dinv) {
+    diag_inverse_kernel<<<npad / TILE, 128, 0, st>>>(L, npad / TILE, Dinv); ++g_kernel_launches;
+}
+
 void launch_mirror_factor(cudaStream_t st, double* L, int npad) {
     const int T = npad / TILE;
     if (T < 2) return;

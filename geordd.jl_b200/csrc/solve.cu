@@ -88,7 +88,8 @@ constexpr int SOLVE_CS_ELEMS = SLAB * SC;                       // 8448
 constexpr int SOLVE_PANEL_ELEMS = TILE * LRS;                   // 4608 >= NB*SC = 4224
 constexpr int SOLVE_RING_ELEMS = SolveCfg<0, false>::ML::RING_ELEMS;   // identical for all modes
 constexpr int SOLVE_WORK_ELEMS = SOLVE_CS_ELEMS + SOLVE_PANEL_ELEMS + NB;
-constexpr int SOLVE_SMEM_ELEMS = (SOLVE_RING_ELEMS > SOLVE_WORK_ELEMS ? SOLVE_RING_ELEMS : SOLVE_WORK_ELEMS) + SolveCfg<0, false>::ML::BAR_WORDS;
+constexpr int SOLVE_SMEM_ELEMS = (SOLVE_RING_ELEMS > SOLVE_WORK_ELEMS ? SOLVE_RING_ELEMS : SOLVE_WORK_ELEMS) + SolveCfg<0, false>::ML::BAR_WORDS + 1;   // + the inverse-block barrier
+static_assert(SOLVE_PANEL_ELEMS >= DINV_TILE, "the panel area holds the four inverse diagonal blocks of a tile");
 constexpr size_t SOLVE_SMEM = (size_t)SOLVE_SMEM_ELEMS * sizeof(double);
 
 template <int MODE, bool XB>
@@ -245,6 +246,7 @@ static void launch_mode(cudaStream_t st, Sched& sched, const SolveParams& p) {
 // Right-hand sides are in ZB storage (one-thread TMA feed).
 struct SeqSolve {
     const double* L;
+    const double* Dinv;   // inverse 32x32 diagonal blocks (nullptr: shared-memory substitution)
     double* B;
     int T;
     int mode;        // SOLVE_FWD / SOLVE_BWD
@@ -297,7 +299,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) solve_seq_kernel(const __grid_con
     __shared__ int sh_job;
     const int tid = threadIdx.x;
     Ring ring;
-    ML::ring_init(ring, reinterpret_cast<uint64_t*>(smem + SOLVE_SMEM_ELEMS - ML::BAR_WORDS), p.abort_word);
+    ML::ring_init(ring, reinterpret_cast<uint64_t*>(smem + SOLVE_SMEM_ELEMS - ML::BAR_WORDS - 1), p.abort_word);
+    uint64_t* dbar = reinterpret_cast<uint64_t*>(smem + SOLVE_SMEM_ELEMS - 1);   // arrival of the inverse diagonal blocks
+    if (tid == 0) {
+        mbar_init(dbar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    unsigned dphase = 0;
     const int njobs = p.job_end[p.nsolves - 1];
     const long ncols = (long)p.nslabs * SLAB;
 
@@ -336,7 +345,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) solve_seq_kernel(const __grid_con
         SeqSrc src{q.L, Bslab, 0, 0, rb, T, s, p.nslabs, mode, flags, p.epoch, p.abort_word};
         const int nchunks = (mode == SOLVE_FWD ? rb : T - 1 - rb) * CHUNKS_PER_TILE_S;
         bool ok = ML::run(smem, ring, nchunks, src, acc);
-        if (__syncthreads_or(!ok)) break;
+        if (__syncthreads_or(!ok)) break;   // (every warp is done reading the ring: Cs / Lp alias it)
+        const double* Ldiag = q.L + tile_off(rb, rb, T);
+        if (q.Dinv && tid == 0) {   // the tile's four inverse diagonal blocks: one bulk copy into the panel area
+            fence_proxy_async();
+            mbar_arrive_expect_tx(dbar, (unsigned)(DINV_TILE * sizeof(double)));
+            bulk_g2s(Lp, q.Dinv + (long)rb * DINV_TILE, (unsigned)(DINV_TILE * sizeof(double)), dbar);
+        }
 #pragma unroll
         for (int a = 0; a < ML::MI; ++a)
 #pragma unroll
@@ -345,9 +360,18 @@ __global__ void __launch_bounds__(NTHREADS, 2) solve_seq_kernel(const __grid_con
                 for (int e = 0; e < 2; ++e) Cs[ML::acc_col(b, e) * SC + ML::acc_row(a)] = -acc.v[a][b][e];
         __syncthreads();
 
-        const double* Ldiag = q.L + tile_off(rb, rb, T);
-        if (mode == SOLVE_FWD) solve_fwd_tile(Cs, SLAB, Lp, invd, Ldiag, TLD);
-        else solve_bwd_tile(Cs, SLAB, Lp, invd, Ldiag, TLD);
+        if (q.Dinv) {
+            // warp-local solve of this warp's 8 columns on the tensor pipe (tileops.cuh: solve_tile_inv), no CTA barrier inside
+            const bool okd = mbar_wait(dbar, dphase, p.abort_word);
+            dphase ^= 1u;
+            if (__syncthreads_or(!okd)) break;
+            if (mode == SOLVE_FWD) solve_tile_inv<false>(Cs, Lp, Ldiag);
+            else solve_tile_inv<true>(Cs, Lp, Ldiag);
+            __syncthreads();   // the write-out below reads other warps' columns
+        } else {
+            if (mode == SOLVE_FWD) solve_fwd_tile(Cs, SLAB, Lp, invd, Ldiag, TLD);
+            else solve_bwd_tile(Cs, SLAB, Lp, invd, Ldiag, TLD);
+        }
 
         const SolveEpilogue& e = q.epi;
         for (int idx = tid; idx < SLAB * TILE; idx += NTHREADS) {
@@ -400,7 +424,7 @@ void launch_solve_seq(cudaStream_t st, Sched& sched, const SolveSeqItem* items, 
     int offs[SOLVE_SEQ_MAX];
     for (int k = 0; k < n; ++k) {
         SeqSolve& q = p.s[k];
-        q.L = items[k].L; q.B = items[k].B; q.T = items[k].npad / TILE; q.mode = (int)items[k].mode;
+        q.L = items[k].L; q.Dinv = items[k].Dinv; q.B = items[k].B; q.T = items[k].npad / TILE; q.mode = (int)items[k].mode;
         q.flag_off = off; offs[k] = off;
         q.after_off = items[k].after >= 0 ? offs[items[k].after] : -1;
         q.after_T = items[k].after >= 0 ? items[items[k].after].npad / TILE : 0;
