@@ -296,7 +296,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=4))   # a mismatched collective fails fast
     ctx = G.Context(local_rank)
     G.geordd._default_ctx = ctx          # the host drivers below (boot_*, GPRealisations) use this rank's context
     stream = torch.cuda.current_stream()
@@ -479,6 +480,10 @@ def main():
 
     if rank == 0:
         # ---- rank 0 only: FP64 tensor-pipe ceiling, Cholesky, cliff-face latency, C2, K1, vendor ----------------
+        # (the host drivers shard and all-reduce automatically under torch.distributed; nothing in this block may enter a
+        #  collective, the other ranks are not here)
+        _local = G.parallel.local_only()
+        _local.__enter__()
         dmma_live = ctx.dmma_peak_tflops()
         # The register-resident DMMA loop draws more power than any real kernel; on a power-capped box it measures
         # below what the solve kernels themselves sustain.  The roofline denominator is therefore the larger of the
@@ -668,6 +673,7 @@ def main():
                 "cpu_baseline": cpu,
                 "extra": extra}
         print(json.dumps(line))
+        _local.__exit__(None, None, None)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

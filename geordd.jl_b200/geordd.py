@@ -726,11 +726,10 @@ def _draw_shard(nsim: int, kw: dict):
     rank simulates its contiguous shard of the draw indices and the exceedance tallies are summed with one all-reduce;
     draws are keyed by (seed, index), so the p-value does not depend on the number of GPUs.  Returns
     (local nsim, kwargs with draw0 / Z adjusted, reducer)."""
-    import sys
-    dist = sys.modules.get("torch.distributed")
-    if dist is None or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return nsim, kw, (lambda cnt: cnt)
     from . import parallel
+    if not parallel.active():
+        return nsim, kw, (lambda cnt: cnt)
+    import torch.distributed as dist
     lo, cnt = parallel.shard_draws(nsim, dist.get_rank(), dist.get_world_size())
     kw = dict(kw)
     kw["draw0"] = int(kw.get("draw0", 0)) + lo
@@ -742,11 +741,10 @@ def _draw_shard(nsim: int, kw: dict):
 def _vector_shard(nsim: int, seed_kw: dict):
     """Vector-returning nsim_* forms with sharded=True: this rank simulates its contiguous shard of the draw indices and the
     statistics are assembled with one all-gather (8 * nsim bytes).  Returns (local nsim, kwargs, gather)."""
-    import sys
-    dist = sys.modules.get("torch.distributed")
-    if dist is None or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return nsim, seed_kw, (lambda v: v)
     from . import parallel
+    if not parallel.active():
+        return nsim, seed_kw, (lambda v: v)
+    import torch.distributed as dist
     lo, cnt = parallel.shard_draws(nsim, dist.get_rank(), dist.get_world_size())
     kw = dict(seed_kw)
     kw["draw0"] = int(kw.get("draw0", 0)) + lo

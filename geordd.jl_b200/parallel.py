@@ -6,7 +6,33 @@ the exceedance tallies (a few int64) are summed with ONE all-reduce (NCCL over N
 CPU tests).  Single fits and cliff faces stay on one GPU (BASELINE north_star)."""
 from __future__ import annotations
 
+import contextlib
 from typing import Sequence, Tuple
+
+_LOCAL_ONLY = 0
+
+
+@contextlib.contextmanager
+def local_only():
+    """Inside this block the host drivers behave as in a single process even if torch.distributed is initialised: no draw
+    sharding, no collectives.  For work that only SOME ranks execute (rank-0-only sections of a benchmark): a collective
+    entered by a subset of the ranks never returns."""
+    global _LOCAL_ONLY
+    _LOCAL_ONLY += 1
+    try:
+        yield
+    finally:
+        _LOCAL_ONLY -= 1
+
+
+def active():
+    """True if this process is one rank of an initialised torch.distributed job of more than one rank (and not inside
+    local_only())."""
+    import sys
+    if _LOCAL_ONLY:
+        return False
+    dist = sys.modules.get("torch.distributed")
+    return dist is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
 def shard_draws(nsim: int, rank: int, world: int) -> Tuple[int, int]:
@@ -33,9 +59,10 @@ def allreduce_tallies(counts: Sequence[int], device=None):
     """Sum integer tallies over all ranks (torch.distributed; backend chosen by the caller's init)."""
     import torch
     import torch.distributed as dist
+    if not active():
+        return [int(v) for v in counts]
     t = torch.tensor(list(counts), dtype=torch.int64, device=_auto_device(device))
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return [int(v) for v in t.cpu().tolist()]
 
 
@@ -44,7 +71,7 @@ def gather_stats(local, nsim: int, device=None):
     import numpy as np
     import torch
     import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+    if not active():
         return np.asarray(local)
     world = dist.get_world_size()
     device = _auto_device(device)
@@ -67,7 +94,7 @@ def map_sharded(fn, items, device=None, mapper=None):
     import torch.distributed as dist
     items = list(items)
     run = mapper if mapper is not None else (lambda f, its: [f(it) for it in its])
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+    if not active():
         return np.array([float(v) for v in run(fn, items)])
     rank, world = dist.get_rank(), dist.get_world_size()
     lo, cnt = shard_draws(len(items), rank, world)

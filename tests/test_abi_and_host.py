@@ -148,6 +148,15 @@ assert np.array_equal(gather(kw["Z"][0] * 2.0), Zfull[0] * 2.0)
 local_n, kw, reduce_ = G.geordd._draw_shard(1, dict(seed=1))
 assert local_n == (0 if rank == 0 else 1)
 assert reduce_(5 * local_n) == 5
+# rank-0-only work must not enter collectives: local_only() switches the automatic sharding off
+if rank == 0:
+    with G.parallel.local_only():
+        assert not G.parallel.active()
+        n_loc, kw2, red2 = G.geordd._draw_shard(10, dict(seed=1))
+        assert n_loc == 10 and red2(7) == 7
+        assert np.array_equal(G.parallel.map_sharded(lambda a: a * 2.0, [1.0, 2.0, 3.0]), [2.0, 4.0, 6.0])
+assert G.parallel.active()
+dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
