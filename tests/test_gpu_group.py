@@ -69,3 +69,48 @@ def test_plain_c_driver_runs_boot_tests_on_the_group(G, tmp_path):
     r = subprocess.run([exe, str(ndev), "500", "3000"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "identical bit for bit" in r.stdout
+
+
+_COMM_WORKER = r"""
+import ctypes as C, os, sys, time
+sys.path.insert(0, {root!r})
+import georddb200
+G = georddb200.load()
+rank, world, idfile = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
+lib = G.capi.load_library()
+ctx = G.Context(rank)                                   # one process per GPU
+buf = C.create_string_buffer(128)
+if rank == 0:
+    assert lib.geordd_comm_unique_id(buf) == 0
+    with open(idfile + ".tmp", "wb") as f:
+        f.write(buf.raw)
+    os.replace(idfile + ".tmp", idfile)
+else:
+    t0 = time.time()
+    while not os.path.exists(idfile):
+        assert time.time() - t0 < 120
+        time.sleep(0.05)
+    buf.raw = open(idfile, "rb").read()
+assert lib.geordd_comm_init_rank(ctx._h, world, rank, buf) == 0, lib.geordd_last_error(ctx._h)
+vals = (C.c_longlong * 3)(rank + 1, 10 * (rank + 1), 7)
+assert lib.geordd_comm_allreduce_tally(ctx._h, vals, 3) == 0, lib.geordd_last_error(ctx._h)
+assert list(vals) == [sum(r + 1 for r in range(world)), 10 * sum(r + 1 for r in range(world)), 7 * world], list(vals)
+assert lib.geordd_comm_destroy(ctx._h) == 0
+print("rank", rank, "ok")
+"""
+
+
+def test_comm_allreduce_one_process_per_gpu(G, tmp_path):
+    """geordd_comm_unique_id / _init_rank / _allreduce_tally: the tally reduce of the library for callers that run one process
+    per GPU without torch (MPI-launched Julia): two processes, two GPUs, the 128-byte id handed over through a file."""
+    import sys
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "comm_worker.py"
+    script.write_text(_COMM_WORKER.format(root=ROOT))
+    idfile = str(tmp_path / "nccl_id.bin")
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), "2", idfile], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)
