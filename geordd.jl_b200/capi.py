@@ -131,6 +131,7 @@ _SIGS = {
     "geordd_comm_allreduce_tally": (C.c_int, [C.c_void_p, c_ll_p, C.c_int]),
     "geordd_comm_destroy": (C.c_int, [C.c_void_p]),
     "geordd_dbg_guard_violations": (C.c_longlong, []),
+    "geordd_dbg_set_lu_blocked": (C.c_int, [C.c_int]),
     "geordd_dbg_normals": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_ulonglong, C.c_int, C.c_int, c_double_p]),
     "geordd_dbg_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, c_double_p,
                                   C.c_int, c_double_p, C.c_int, C.c_double, c_double_p, C.c_int, C.c_int]),

@@ -664,6 +664,7 @@ int geordd_ctx_set_max_batch(geordd_ctx* c, long mb) {
 }
 
 long long geordd_dbg_guard_violations(void) { return geordd::g_guard_violations_get(); }
+int geordd_dbg_set_lu_blocked(int on) { geordd::lu_set_blocked(on != 0); return 0; }
 
 int geordd_ctx_last_min_margin(const geordd_ctx* c, double* margin3) {
     if (!c || !margin3) return GEORDD_ERR_ARG;

@@ -35,6 +35,7 @@ void launch_finish_cliff(cudaStream_t st, const FinishCliff& f);
 void launch_frac_compare(cudaStream_t st, const double* ref, long nref, const double* x, long n, bool greater,
                          double* out);
 void launch_lu_solve(cudaStream_t st, double* A, long lda, int n, double* B, long ldb, int nrhs, int* info);
+void lu_set_blocked(bool on);   // test hook: false = always the unblocked kernel
 // The same n x n system against nrhs right-hand sides split over CTAs; scratch: ceil(nrhs / cols_per_cta) * n * n doubles.
 void launch_lu_solve_multi(cudaStream_t st, const double* A, long lda, int n, double* scratch, double* B, long ldb, long nrhs,
                            int cols_per_cta, int* info);

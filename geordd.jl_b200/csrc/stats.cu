@@ -327,15 +327,266 @@ __global__ void __launch_bounds__(1024) lu_solve_kernel(double* A, long lda, int
         __syncthreads();
     }
 }
+// ---------------------------------------------------------------------------------------------------
+// The same elimination, blocked for locality (n <= 640: the nb x nb cliff-face systems and the p x p precision of
+// postmean_beta).  The unblocked kernel above pays five CTA barriers and several L2 round trips per pivot (8.8 us per
+// pivot: 1.8 ms for the 200 x 200 system of one observed chi2 statistic).  Here a panel of NBL columns is held in REGISTERS
+// while its pivots are found -- thread t owns row t (and t + 512) of the panel; per pivot three barriers, two row images
+// exchanged through shared memory, no global access.  The columns to its right and the right-hand sides are then updated
+// warp by warp, JB columns at a time, a column held in registers across the lanes (row r of the panel-relative segment
+// in lane r % 32, slot r / 32) against the panel in shared memory -- the panel's row exchanges are applied while the
+// column is loaded (`src`: the permutation the NBL exchanges compose to).  Every entry still receives exactly the
+// operations of the unblocked kernel in the same order (a = fma(-l_ic, u_cj, a) for c ascending; reciprocal-pivot
+// scaling; true division in the back substitution), so factors, pivots and solutions are bit-identical to it -- tested
+// (geordd_dbg_set_lu_blocked).  Exchanges are not applied to the L part left of a panel: it is never read again, the
+// right-hand sides are eliminated together with the matrix.
+// ---------------------------------------------------------------------------------------------------
+template <int MQ, int NBL, int JB>
+__global__ void __launch_bounds__(512) lu_blocked_kernel(double* A, long lda, int n, double* B, long ldb, int nrhs, int* info,
+                                                         const double* Asrc, long ldsrc, int cols_per_cta) {
+    constexpr int LDP = 32 * MQ + 1, NT = 512, NW = NT / 32, R = (32 * MQ + NT - 1) / NT;
+    extern __shared__ double lu_sm[];
+    double* P = lu_sm;                               // NBL panel columns, LDP apart
+    int* src = (int*)(P + (size_t)NBL * LDP);        // row r of the permuted segment comes from row src[r]
+    __shared__ double sval[NW];
+    __shared__ double rowbuf[2 * NBL];               // [0, NBL): old row c, [NBL, 2 NBL): old row piv = the pivot row
+    __shared__ int sidx[NW];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (Asrc) {
+        A += (long)blockIdx.x * lda * n;
+        for (long idx = tid; idx < (long)n * n; idx += NT) A[(idx / n) * lda + idx % n] = Asrc[(idx / n) * ldsrc + idx % n];
+        B += (long)blockIdx.x * cols_per_cta * ldb;
+        nrhs = min(cols_per_cta, nrhs - (int)blockIdx.x * cols_per_cta);
+        if (blockIdx.x != 0) info = nullptr;
+        __syncthreads();
+    }
+    for (int k0 = 0; k0 < n; k0 += NBL) {
+        const int w = min(NBL, n - k0), m = n - k0;
+        // ---- pivots of the panel: thread t holds rows t (+ 512) of the panel in registers ----
+        double r[R][NBL];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const int row = tid + NT * rr;
+#pragma unroll
+            for (int cc = 0; cc < NBL; ++cc) r[rr][cc] = (row < m && cc < w) ? A[(long)(k0 + cc) * lda + k0 + row] : 0.0;
+        }
+        for (int i = tid; i < m; i += NT) src[i] = i;
+#pragma unroll
+        for (int c = 0; c < NBL; ++c) {
+            if (c < w) {
+                double best = -1.0;
+                int bi = m;
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                    const int row = tid + NT * rr;
+                    const double v = fabs(r[rr][c]);
+                    if (row >= c && row < m && v > best) { best = v; bi = row; }
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ov = __shfl_down_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+                    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+                }
+                if (lane == 0) { sval[warp] = best; sidx[warp] = bi; }
+                __syncthreads();
+                // every warp finishes the reduction itself (maximum with first-index tie-break is order independent): no
+                // second barrier to publish the pivot
+                best = lane < NW ? sval[lane] : -1.0;
+                bi = lane < NW ? sidx[lane] : m;
+#pragma unroll
+                for (int o = NW / 2; o > 0; o >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+                }
+                best = __shfl_sync(0xffffffffu, best, 0);
+                bi = __shfl_sync(0xffffffffu, bi, 0);
+                if (tid == 0 && info && !(best > 0.0) && *info == 0) *info = k0 + c + 1;
+                const int piv = bi < m ? bi : c;
+                // rows c and piv change owners through shared memory; rowbuf[1] (the old row piv) is the pivot row
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                    const int row = tid + NT * rr;
+                    if (row == c || row == piv) {
+#pragma unroll
+                        for (int cc = 0; cc < NBL; ++cc) {
+                            if (row == c) rowbuf[cc] = r[rr][cc];
+                            if (row == piv) rowbuf[NBL + cc] = r[rr][cc];
+                        }
+                    }
+                }
+                if (tid == NT - 1 && piv != c) {
+                    const int t = src[c];
+                    src[c] = src[piv];
+                    src[piv] = t;
+                }
+                __syncthreads();
+                const double rp = 1.0 / rowbuf[NBL + c];
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                    const int row = tid + NT * rr;
+                    if (row == c || row == piv) {
+#pragma unroll
+                        for (int cc = 0; cc < NBL; ++cc) r[rr][cc] = row == c ? rowbuf[NBL + cc] : rowbuf[cc];
+                    }
+                    if (row > c && row < m) {
+                        const double l = r[rr][c] * rp;
+                        r[rr][c] = l;
+#pragma unroll
+                        for (int jj = c + 1; jj < NBL; ++jj) r[rr][jj] = fma(-l, rowbuf[NBL + jj], r[rr][jj]);
+                    }
+                }
+            }
+        }
+        // the factored panel: to shared memory for the elimination below, and back to A
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const int row = tid + NT * rr;
+            if (row < m) {
+#pragma unroll
+                for (int cc = 0; cc < NBL; ++cc) {
+                    if (cc < w) {
+                        P[cc * LDP + row] = r[rr][cc];
+                        A[(long)(k0 + cc) * lda + k0 + row] = r[rr][cc];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- columns right of the panel and the right-hand sides: exchange rows, eliminate with the panel ----
+        const int nright = n - k0 - w, total = nright + nrhs;
+        for (int g = warp; g * JB < total; g += NW) {
+            double* cp[JB];
+#pragma unroll
+            for (int jb = 0; jb < JB; ++jb) {
+                const int jj = g * JB + jb;
+                cp[jb] = jj >= total ? nullptr : jj < nright ? A + (long)(k0 + w + jj) * lda + k0 : B + (long)(jj - nright) * ldb + k0;
+            }
+            double v[JB][MQ];
+#pragma unroll
+            for (int q = 0; q < MQ; ++q) {
+                const int row = q * 32 + lane;
+                const int sr = row < m ? src[row] : 0;
+#pragma unroll
+                for (int jb = 0; jb < JB; ++jb) v[jb][q] = (row < m && cp[jb]) ? cp[jb][sr] : 0.0;
+            }
+#pragma unroll
+            for (int c = 0; c < NBL; ++c) {
+                if (c < w) {
+                    double u[JB];
+#pragma unroll
+                    for (int jb = 0; jb < JB; ++jb) u[jb] = __shfl_sync(0xffffffffu, v[jb][0], c);
+#pragma unroll
+                    for (int q = 0; q < MQ; ++q) {
+                        const int row = q * 32 + lane;
+                        if (row > c && row < m) {
+                            const double l = P[c * LDP + row];
+#pragma unroll
+                            for (int jb = 0; jb < JB; ++jb) v[jb][q] = fma(-l, u[jb], v[jb][q]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < MQ; ++q) {
+                const int row = q * 32 + lane;
+#pragma unroll
+                for (int jb = 0; jb < JB; ++jb)
+                    if (row < m && cp[jb]) cp[jb][row] = v[jb][q];
+            }
+        }
+        __syncthreads();
+    }
+    // ---- back substitution with U: one warp per JB right-hand sides, the column in registers; the NBL columns of U a
+    // stage needs are copied into shared memory by the whole CTA first (the chain of n divisions is what the caller waits
+    // for with one or two right-hand sides: nothing on it may wait for L2) ----
+    const int ngroups = (nrhs + JB - 1) / JB;
+    for (int g0 = 0; g0 < ngroups; g0 += NW) {
+        const int g = g0 + warp;
+        double* cp[JB];
+#pragma unroll
+        for (int jb = 0; jb < JB; ++jb) cp[jb] = g * JB + jb < nrhs ? B + (long)(g * JB + jb) * ldb : nullptr;
+        double v[JB][MQ];
+#pragma unroll
+        for (int q = 0; q < MQ; ++q)
+#pragma unroll
+            for (int jb = 0; jb < JB; ++jb) v[jb][q] = (q * 32 + lane < n && cp[jb]) ? cp[jb][q * 32 + lane] : 0.0;
+#pragma unroll
+        for (int kb = MQ - 1; kb >= 0; --kb) {
+#pragma unroll
+            for (int h = 32 / NBL - 1; h >= 0; --h) {
+                const int k1 = kb * 32 + h * NBL;
+                if (k1 < n) {
+                    const int wc = min(NBL, n - k1), nr = min(n, k1 + NBL);
+                    __syncthreads();
+                    for (int idx = tid; idx < wc * nr; idx += NT) {
+                        const int cc = idx / nr, i = idx - cc * nr;
+                        P[cc * LDP + i] = A[(long)(k1 + cc) * lda + i];
+                    }
+                    __syncthreads();
+                    if (g < ngroups) {
+#pragma unroll 4
+                        for (int kk = NBL - 1; kk >= 0; --kk) {
+                            const int k = k1 + kk, lk = h * NBL + kk;   // lk: lane that owns row k
+                            if (k < n) {
+                                const double* Uk = P + kk * LDP;
+                                const double d = Uk[k];
+                                double x[JB];
+#pragma unroll
+                                for (int jb = 0; jb < JB; ++jb) x[jb] = __shfl_sync(0xffffffffu, v[jb][kb], lk) / d;
+                                const double ud = lane < lk ? Uk[kb * 32 + lane] : 0.0;
+#pragma unroll
+                                for (int jb = 0; jb < JB; ++jb)
+                                    v[jb][kb] = lane == lk ? x[jb] : lane < lk ? fma(-ud, x[jb], v[jb][kb]) : v[jb][kb];
+#pragma unroll
+                                for (int q = 0; q < MQ; ++q) {
+                                    if (q < kb) {
+                                        const double uu = Uk[q * 32 + lane];
+#pragma unroll
+                                        for (int jb = 0; jb < JB; ++jb) v[jb][q] = fma(-uu, x[jb], v[jb][q]);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < MQ; ++q)
+#pragma unroll
+            for (int jb = 0; jb < JB; ++jb)
+                if (q * 32 + lane < n && cp[jb]) cp[jb][q * 32 + lane] = v[jb][q];
+    }
+}
+
+static bool g_lu_blocked = true;
+void lu_set_blocked(bool on) { g_lu_blocked = on; }
+
+template <int MQ, int NBL, int JB>
+static void launch_lu_blocked(cudaStream_t st, int ctas, double* A, long lda, int n, double* B, long ldb, int nrhs, int* info,
+                              const double* Asrc, long ldsrc, int cols_per_cta) {
+    const size_t smem = (size_t)NBL * (32 * MQ + 1) * sizeof(double) + (size_t)32 * MQ * sizeof(int);
+    cudaFuncSetAttribute(lu_blocked_kernel<MQ, NBL, JB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    lu_blocked_kernel<MQ, NBL, JB><<<ctas, 512, smem, st>>>(A, lda, n, B, ldb, nrhs, info, Asrc, ldsrc, cols_per_cta); ++g_kernel_launches;
+}
+
+static void lu_dispatch(cudaStream_t st, int ctas, double* A, long lda, int n, double* B, long ldb, int nrhs, int* info,
+                        const double* Asrc, long ldsrc, int cols_per_cta) {
+    if (g_lu_blocked && n <= 256) launch_lu_blocked<8, 32, 4>(st, ctas, A, lda, n, B, ldb, nrhs, info, Asrc, ldsrc, cols_per_cta);
+    else if (g_lu_blocked && n <= 640) launch_lu_blocked<20, 16, 2>(st, ctas, A, lda, n, B, ldb, nrhs, info, Asrc, ldsrc, cols_per_cta);
+    else { lu_solve_kernel<<<ctas, 1024, 0, st>>>(A, lda, n, B, ldb, nrhs, info, Asrc, ldsrc, cols_per_cta); ++g_kernel_launches; }
+}
+
 void launch_lu_solve(cudaStream_t st, double* A, long lda, int n, double* B, long ldb, int nrhs, int* info) {
     cudaMemsetAsync(info, 0, sizeof(int), st);
-    lu_solve_kernel<<<1, 1024, 0, st>>>(A, lda, n, B, ldb, nrhs, info, nullptr, 0, 0); ++g_kernel_launches;
+    lu_dispatch(st, 1, A, lda, n, B, ldb, nrhs, info, nullptr, 0, 0);
 }
 void launch_lu_solve_multi(cudaStream_t st, const double* A, long lda, int n, double* scratch, double* B, long ldb, long nrhs,
                            int cols_per_cta, int* info) {
     cudaMemsetAsync(info, 0, sizeof(int), st);
     const int ctas = (int)((nrhs + cols_per_cta - 1) / cols_per_cta);
-    lu_solve_kernel<<<ctas, 1024, 0, st>>>(scratch, n, n, B, ldb, (int)nrhs, info, A, lda, cols_per_cta); ++g_kernel_launches;
+    lu_dispatch(st, ctas, scratch, n, n, B, ldb, (int)nrhs, info, A, lda, cols_per_cta);
 }
 
 // out[c] = sum_{r < rows} M(r, c), rows summed in order (one thread per column; rows <= a few hundred)

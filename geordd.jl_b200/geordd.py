@@ -1474,3 +1474,36 @@ def placebo_sweep(which: str, angles, X, Y, kern, mean, logNoise: float, nsim: i
         return parallel.map_sharded(one, list(angles))
     with ThreadPoolExecutor(max_workers=int(workers)) as pool:
         return parallel.map_sharded(one, list(angles), mapper=lambda f, items: list(pool.map(f, items)))
+
+
+def adjacent_sweep(gps, borders: Dict, nugget: float = 1e-10):
+    """The loop over `adjacent_pairs(rd_dict, buffer)` of the notebooks (src/regiondata.jl:64-68,
+    notebooks/NYC_analysis-2015.ipynb cell 74): for every pair of regions that share a border -- `borders` maps
+    (key_i, key_j) to that border's 2 x nb sentinels; finding the borders is LibGEOS work and stays with the caller --
+    the cliff face, the inverse-variance LATE and the calibrated p-value, from the already fitted per-region GPs
+    (`gps`: GPRealisations or a dict key -> GPE).  Returns (tau_post_pairs, pval_pairs) filled in both orientations like the
+    notebook's dictionaries.  Under torch.distributed the pairs are dealt to the ranks (every rank holds all fits; one
+    all-gather of three numbers per pair)."""
+    from . import parallel
+    pairs = list(borders.keys())
+    done: Dict[int, tuple] = {}
+
+    def pair_results(p):
+        if p not in done:
+            ki, kj = pairs[p]
+            a, b = gps[ki], gps[kj]
+            Xb = fmat(borders[(ki, kj)])
+            mu, Sigma = cliff_face(a, b, Xb)
+            tp = inverse_variance(mu, Sigma, nugget, ctx=a.ctx)
+            done[p] = (tp.mu, tp.sigma, pval_invvar_calib(a, b, Xb, nugget=nugget))
+        return done[p]
+
+    # every call deals the same pairs to the same rank, so each pair is evaluated once; one all-gather per output
+    cols = [parallel.map_sharded(lambda p, c=c: pair_results(p)[c], range(len(pairs))) for c in range(3)]
+    tau_post, pvals = {}, {}
+    for p, (ki, kj) in enumerate(pairs):
+        m, s, pv = (float(col[p]) for col in cols)
+        tau_post[(ki, kj)] = Normal(m, s)
+        tau_post[(kj, ki)] = Normal(-m, s)
+        pvals[(ki, kj)] = pvals[(kj, ki)] = pv
+    return tau_post, pvals

@@ -266,11 +266,14 @@ GEORDD_API int geordd_comm_init_rank(geordd_ctx* ctx, int nranks, int rank, cons
 GEORDD_API int geordd_comm_allreduce_tally(geordd_ctx* ctx, long long* vals, int n);
 GEORDD_API int geordd_comm_destroy(geordd_ctx* ctx);
 
-/* ---- debug / test hooks (not part of the reference-facing surface) -----------------------------
- * Device Philox normals copied to the host: Z is n x ndraws. */
+/* ---- debug / test hooks (not part of the reference-facing surface) ----------------------------- */
 /* GEORDD_GUARD=1 in the environment brackets every device buffer with NaN-filled guard zones (see api_core.cu): number of
  * buffers whose guards were found overwritten when they were released. */
 GEORDD_API long long geordd_dbg_guard_violations(void);
+/* Test hook (process-wide, default 1): 0 routes every pivoted-LU solve through the unblocked single-pass kernel, 1 through the
+ * blocked one (n <= 640); both perform the same operations in the same order, the parity tests compare them bit for bit. */
+GEORDD_API int geordd_dbg_set_lu_blocked(int on);
+/* Device Philox normals copied to the host: Z is n x ndraws. */
 GEORDD_API int geordd_dbg_normals(geordd_ctx* ctx, unsigned long long seed, unsigned long long draw0, int ndraws, int n,
                        double* Z);
 /* C = alpha*op(A)*op(B) + beta*C through the DMMA mainloop (host matrices, column-major). transa/transb:

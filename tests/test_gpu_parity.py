@@ -537,6 +537,62 @@ def test_placebo_drivers_match_oracle(G, O, ctx, angle):
     assert abs(pg - po) < 1e-7 * max(po, 1e-3)
 
 
+@pytest.mark.parametrize("n,nrhs", [(1, 1), (5, 3), (31, 1), (32, 2), (33, 9), (100, 1), (200, 2), (200, 202), (256, 5), (257, 3),
+                                    (604, 1), (640, 7), (641, 2)])
+def test_blocked_lu_equals_unblocked_bit_for_bit(G, O, ctx, n, nrhs):
+    """The pivoted LU solve behind Julia's `A \\ B` on a dense Matrix (observed chi2 / inverse-variance statistics,
+    src/hypotest_chi2.jl:10, src/average_treatment_effect.jl:5-8; postmean_beta's p x p system, src/GPrealisationsCovars.jl:342):
+    the blocked kernel performs the unblocked kernel's operations in the same order -- identical bits, pivots included --
+    and both agree with the oracle's LAPACK getrf/getrs.  Matrices: a well-conditioned random one (every column needs a row
+    exchange) and a cliff-face-like SPD one with a nugget (no exchanges)."""
+    rng = np.random.default_rng(100 * n + nrhs)
+    A1 = rng.standard_normal((n, n))
+    t = np.linspace(0.0, 1.0, n)
+    A2 = np.exp(-0.5 * ((t[:, None] - t[None, :]) / 0.3) ** 2) + 1e-6 * np.eye(n)
+    for A, gate in ((A1, None), (A2, None)):
+        B = rng.standard_normal((n, nrhs))
+        lib = ctx.lib
+        try:
+            lib.geordd_dbg_set_lu_blocked(0)
+            x0 = G.generic_solve(A, B)
+        finally:
+            lib.geordd_dbg_set_lu_blocked(1)
+        x1 = G.generic_solve(A, B)
+        assert np.array_equal(x0, x1)
+        xo = O.generic_solve(A, B)
+        cond = np.linalg.cond(A)
+        assert relerr(x1, xo) < max(TOL, 50 * cond * np.finfo(float).eps)
+
+
+def test_adjacent_sweep_matches_oracle(G, O, ctx):
+    """The adjacent-pairs loop of the notebooks (src/regiondata.jl:64-68, NYC_analysis-2015.ipynb cell 74): three strips of
+    the unit square, two shared borders; cliff face -> inverse-variance LATE -> calibrated p-value per pair against the
+    oracle, both orientations filled like the notebook's dictionaries."""
+    rng = np.random.default_rng(8)
+    X = np.asfortranarray(rng.random((2, 420)))
+    Y = np.sin(3.0 * X[0]) + 0.5 * (X[0] > 1 / 3) - 0.2 * (X[0] > 2 / 3) + 0.3 * rng.standard_normal(420)
+    strip = np.minimum((X[0] * 3).astype(int), 2)
+    rd = {name: G.RegionData(X[:, strip == i], Y[strip == i], np.empty((0, int((strip == i).sum())))) for i, name in enumerate("ABC")}
+    k = G.SEIso(math.log(0.3), 0.0) + G.Const(math.log(20.0)); ln = math.log(0.3)
+    spec = O.KernelSpec(O.SE_ISO, 0.3, 1.0, 400.0)
+    gpr = G.GPRealisations(rd, k, ln)
+    yy = np.linspace(0.02, 0.98, 40)
+    borders = {("A", "B"): np.asfortranarray(np.vstack([np.full(40, 1 / 3), yy])),
+               ("B", "C"): np.asfortranarray(np.vstack([np.full(40, 2 / 3), yy]))}
+    tau, pv = G.adjacent_sweep(gpr, borders)
+    assert set(tau) == {("A", "B"), ("B", "A"), ("B", "C"), ("C", "B")} and set(pv) == set(tau)
+    og = {name: O.gp_fit(spec, rd[name].x, rd[name].y, ln) for name in "ABC"}
+    for (ki, kj), Xb in borders.items():
+        mu, Sig = O.cliff_face(og[ki], og[kj], Xb)
+        tp = O.inverse_variance(mu, Sig)
+        po = O.pval_invvar_calib(og[ki], og[kj], Xb)
+        cond = np.linalg.cond(Sig + 1e-10 * np.eye(40))
+        gate = max(TOL, 10 * cond * np.finfo(float).eps)
+        assert abs(tau[(ki, kj)].mu - tp.mu) < gate * max(abs(tp.mu), tp.sigma) and abs(tau[(ki, kj)].sigma - tp.sigma) < gate * tp.sigma
+        assert tau[(kj, ki)].mu == -tau[(ki, kj)].mu and tau[(kj, ki)].sigma == tau[(ki, kj)].sigma
+        assert abs(pv[(ki, kj)] - po) < gate * max(po, 1e-3) and pv[(kj, ki)] == pv[(ki, kj)]
+
+
 # ---------------------------------------------------------------------------------------------
 # Full-size (BASELINE configs) size-independent properties
 # ---------------------------------------------------------------------------------------------
