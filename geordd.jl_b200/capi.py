@@ -83,6 +83,8 @@ _SIGS = {
     "geordd_null_prepare": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, C.c_int, C.c_double, c_void_pp, c_int_p,
                                       c_double_p]),
     "geordd_null_set_sentinels": (C.c_int, [C.c_void_p, c_double_p, C.c_int, C.c_double, c_int_p]),
+    "geordd_null_chistat_obs": (C.c_int, [C.c_void_p, c_double_p]),
+    "geordd_null_invvar_obs": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p]),
     "geordd_null_gp": (C.c_int, [C.c_void_p, c_void_pp]),
     "geordd_gp_prior_rand": (C.c_int, [C.c_void_p, C.c_long, C.c_ulonglong, C.c_ulonglong, c_double_p, c_double_p]),
     "geordd_null_chi2": (C.c_int, [C.c_void_p, C.c_long, C.c_ulonglong, C.c_ulonglong, c_double_p, C.c_double,

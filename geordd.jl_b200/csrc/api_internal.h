@@ -118,6 +118,7 @@ struct geordd_null {
     double* dKbC = nullptr;     // nbp x mpadC
     double* dSig = nullptr;     // nbp x nbp raw cliff covariance (+ nugget, + jitter) = Sigma_raw
     double* dSigRaw = nullptr;  // nbp x nbp cliff covariance + nugget BEFORE make_posdef! jitter (LU solves of the calibration)
+    double* dMuObs = nullptr;   // cliff-face mean of the OBSERVED outcomes at the sentinels (geordd_null_chistat_obs / _invvar_obs)
     double* dLSig = nullptr;    // its lower factor
     double* dOnes = nullptr;    // nbp (1 on rows < nb)
     double denom = 0.0;         // sum(Sigma \ 1) with the PD factor

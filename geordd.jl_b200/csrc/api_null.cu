@@ -153,7 +153,7 @@ static void calib_cov_mu_delta(geordd_gp* T, geordd_gp* C, const double* dXb, in
 static void null_free(geordd_null* h) {
     if (!h) return;
     if (h->N) gp_free(h->N);
-    dfree(h->dXb); dfree(h->dKbT); dfree(h->dKbC); dfree(h->dSig); dfree(h->dSigRaw); dfree(h->dLSig); dfree(h->dOnes);
+    dfree(h->dXb); dfree(h->dKbT); dfree(h->dKbC); dfree(h->dSig); dfree(h->dSigRaw); dfree(h->dLSig); dfree(h->dOnes); dfree(h->dMuObs);
     h->oNumLU.release();
     h->Z.release(); h->RN.release(); h->AN.release(); h->AT.release(); h->AC.release(); h->M.release(); h->W.release();
     h->partN.release(); h->partT.release(); h->partC.release(); h->partChi.release(); h->partNum.release();
@@ -614,6 +614,55 @@ int geordd_invvar_obs(geordd_gp* T, geordd_gp* C, const double* Xb, int nb, doub
     API_END
 }
 
+// The observed statistics from a prepared null handle: geordd_null_set_sentinels has already evaluated the cliff face of the
+// observed outcomes with the kernels geordd_chistat_obs / geordd_invvar_obs use, so boot_chi2test / boot_invvar need not
+// evaluate it a second time.  Same operations on the same numbers: results are bit-identical to the stand-alone calls.
+int geordd_null_chistat_obs(geordd_null* h, double* chi2) {
+    if (!h) return GEORDD_ERR_ARG;
+    API_BEGIN(h->ctx)
+    if (!chi2) throw ApiError(GEORDD_ERR_ARG, "null_chistat_obs: output is NULL");
+    if (h->nb <= 0 || !h->dMuObs) throw ApiError(GEORDD_ERR_ARG, "null handle was prepared without sentinels");
+    if (h->nugget != 0.0) throw ApiError(GEORDD_ERR_ARG, "null_chistat_obs: chistat uses the cliff covariance without a nugget; this handle has one");
+    const int nb = h->nb, nbp = h->nbp;
+    double* x = dalloc((size_t)nbp, c__->stream, true);
+    double* sig = nullptr;
+    try {
+        sig = dalloc((size_t)nbp * nbp, c__->stream, false);
+        GD_CUDA(cudaMemcpyAsync(sig, h->dSigRaw, (size_t)nbp * nbp * sizeof(double), cudaMemcpyDeviceToDevice, c__->stream));
+        GD_CUDA(cudaMemcpyAsync(x, h->dMuObs, (size_t)nbp * sizeof(double), cudaMemcpyDeviceToDevice, c__->stream));
+        lu_solve_dev(c__, sig, nb, nbp, 0.0, x, 1);
+        launch_reduce(c__->stream, 2, h->dMuObs, x, 0, nb, 0, c__->d_scal);
+        check_abort(c__);
+        *chi2 = read_scalar(c__, c__->d_scal);
+    } catch (...) {
+        dfree(x); dfree(sig);
+        throw;
+    }
+    dfree(x); dfree(sig);
+    API_END
+}
+
+int geordd_null_invvar_obs(geordd_null* h, double* tau_hat, double* var_tau, double* pval) {
+    if (!h) return GEORDD_ERR_ARG;
+    API_BEGIN(h->ctx)
+    if (h->nb <= 0 || !h->dMuObs) throw ApiError(GEORDD_ERR_ARG, "null handle was prepared without sentinels");
+    const int nb = h->nb, nbp = h->nbp;
+    double* sig = dalloc((size_t)nbp * nbp, c__->stream, false);
+    double tau = 0, var = 0;
+    try {
+        GD_CUDA(cudaMemcpyAsync(sig, h->dSigRaw, (size_t)nbp * nbp * sizeof(double), cudaMemcpyDeviceToDevice, c__->stream));
+        invvar_dev(c__, sig, h->dMuObs, nb, nbp, 0.0 /* the handle's nugget is already inside dSigRaw */, &tau, &var);
+    } catch (...) {
+        dfree(sig);
+        throw;
+    }
+    dfree(sig);
+    if (tau_hat) *tau_hat = tau;
+    if (var_tau) *var_tau = var;
+    if (pval) *pval = normal_two_sided_at_zero(tau, var);
+    API_END
+}
+
 int geordd_inverse_variance(geordd_ctx* c, const double* mu, const double* Sigma, int nb, double nugget, double* tau_hat,
                             double* var_tau) {
     API_BEGIN(c)
@@ -747,8 +796,8 @@ static int null_set_sentinels(geordd_null* h, const double* Xb, int nb, double n
     geordd_gp *T = h->T, *C = h->C;
     check_pair(T, C);
     if (!Xb || nb <= 0) throw ApiError(GEORDD_ERR_ARG, "sentinels missing");
-    dfree(h->dXb); dfree(h->dKbT); dfree(h->dKbC); dfree(h->dSig); dfree(h->dSigRaw); dfree(h->dLSig); dfree(h->dOnes);
-    h->dXb = h->dKbT = h->dKbC = h->dSig = h->dSigRaw = h->dLSig = h->dOnes = nullptr;
+    dfree(h->dXb); dfree(h->dKbT); dfree(h->dKbC); dfree(h->dSig); dfree(h->dSigRaw); dfree(h->dLSig); dfree(h->dOnes); dfree(h->dMuObs);
+    h->dXb = h->dKbT = h->dKbC = h->dSig = h->dSigRaw = h->dLSig = h->dOnes = h->dMuObs = nullptr;
     h->calib_lu_ready = false;
     if (round_up(nb, TILE) != h->nbp) {   // sentinel-sized simulation buffers must be re-made
         h->M.release(); h->W.release(); h->partChi.release(); h->partNum.release();
@@ -763,14 +812,9 @@ static int null_set_sentinels(geordd_null* h, const double* Xb, int nb, double n
     GD_CUDA(cudaMemcpyAsync(h->dXb, Xb, (size_t)2 * nb * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     h->dSig = dalloc((size_t)nbp * nbp, c->stream, true);
     h->dLSig = dalloc(factor_elems(nbp), c->stream, true);
-    double* mu = dalloc((size_t)nbp * 64, c->stream, true);
-    try {
-        cliff_face_dev(T, C, h->dXb, nb, nbp, mu, h->dSig);
-    } catch (...) {
-        dfree(mu);
-        throw;
-    }
-    dfree(mu);
+    // the cliff face of the observed outcomes: Sigma_b for the simulations, mu_b kept for the observed statistics
+    h->dMuObs = dalloc((size_t)nbp * 64, c->stream, true);
+    cliff_face_dev(T, C, h->dXb, nb, nbp, h->dMuObs, h->dSig);
     if (nugget != 0.0) launch_add_diag(c->stream, h->dSig, nbp, nb, nugget);
     // keep Sigma + nugget I as it is BEFORE make_posdef! may jitter it: the analytic calibration solves against it by LU
     h->dSigRaw = dalloc((size_t)nbp * nbp, c->stream, false);

@@ -669,6 +669,19 @@ class NullGPE:
         if self.Xb is None or self.Xb.shape != Xb.shape or not np.array_equal(self.Xb, Xb) or self.nugget != nugget:
             self.set_sentinels(Xb, nugget)
 
+    def chistat_obs(self) -> float:
+        """chistat(gpT, gpC, Xb) of the observed outcomes from the cliff face this handle evaluated when its sentinels were
+        set (bit-identical to chistat(); saves boot_chi2test the second cliff face)."""
+        out = C.c_double()
+        self.ctx.check(self.ctx.lib.geordd_null_chistat_obs(self._h, C.byref(out)))
+        return out.value
+
+    def invvar_obs(self):
+        """(tau_hat, var, p) of pval_invvar_uncalib(gpT, gpC, Xb; nugget) from this handle's cliff face."""
+        tau, var, p = C.c_double(), C.c_double(), C.c_double()
+        self.ctx.check(self.ctx.lib.geordd_null_invvar_obs(self._h, C.byref(tau), C.byref(var), C.byref(p)))
+        return tau.value, var.value, p.value
+
     def close(self):
         if getattr(self, "_h", None) and self._h:
             self.ctx.lib.geordd_null_destroy(self._h)
@@ -757,13 +770,14 @@ def boot_chi2test(gpT: GPE, gpC: GPE, Xb, nsim: int, **kw) -> float:
     """boot_chi2test(gpT, gpC, Xb, nsim) (src/hypotest_chi2.jl:54-59): mean(chi_sims .> chi_obs)."""
     if isinstance(gpT, GroupGPE):
         return _group_boot("chi", gpT, gpC, Xb, nsim, **kw)
-    gpNull = make_null(gpT, gpC)
-    chi_obs = chistat(gpT, gpC, Xb)
+    gpNull = NullGPE(gpT, gpC, Xb, 0.0)       # make_null + the sentinel-dependent setup (one cliff face)
+    chi_obs = gpNull.chistat_obs()            # == chistat(gpT, gpC, Xb), from that cliff face
     total = np.asarray(kw["Z"]).shape[1] if kw.get("Z") is not None else int(nsim)
     local, kw, reduce_ = _draw_shard(total, kw)
     cnt = 0                                   # a rank whose shard is empty (world > nsim) still joins the all-reduce
     if local > 0:
         _, cnt = nsim_chi(gpT, gpC, gpNull, Xb, local, chi_obs=chi_obs, return_count=True, **kw)
+    gpNull.close()
     return reduce_(cnt) / total
 
 
@@ -800,12 +814,14 @@ def boot_invvar(gpT: GPE, gpC: GPE, Xb, nsim: int, nugget: float = 1e-10, **kw) 
     """boot_invvar (src/hypotest_invvar.jl:65-69): mean(pval_sims .< pval_obs)."""
     if isinstance(gpT, GroupGPE):
         return _group_boot("invvar", gpT, gpC, Xb, nsim, nugget, **kw)
-    pobs = pval_invvar_uncalib(gpT, gpC, Xb, nugget)
+    gpNull = NullGPE(gpT, gpC, Xb, nugget)
+    pobs = gpNull.invvar_obs()[2]             # == pval_invvar_uncalib(gpT, gpC, Xb; nugget), from the handle's cliff face
     total = np.asarray(kw["Z"]).shape[1] if kw.get("Z") is not None else int(nsim)
     local, kw, reduce_ = _draw_shard(total, kw)
     cnt = 0
     if local > 0:
-        _, cnt = nsim_invvar_pval_uncalib(gpT, gpC, Xb, local, nugget, pval_obs=pobs, return_count=True, **kw)
+        _, cnt = nsim_invvar_pval_uncalib(gpT, gpC, Xb, local, nugget, pval_obs=pobs, return_count=True, gpNull=gpNull, **kw)
+    gpNull.close()
     return reduce_(cnt) / total
 
 

@@ -172,6 +172,12 @@ GEORDD_API int geordd_null_prepare(geordd_gp* T, geordd_gp* C, const double* Xb,
                         int* jitter_rounds, double* mll_null);
 /* Re-run only the sentinel-dependent part of the setup on an existing handle (new Xb and/or nugget). */
 GEORDD_API int geordd_null_set_sentinels(geordd_null* h, const double* Xb, int nb, double nugget, int* jitter_rounds);
+/* chistat(gpT, gpC, Xb) (src/hypotest_chi2.jl:4-11) and pval_invvar_uncalib(gpT, gpC, Xb; nugget) (src/hypotest_invvar.jl:1-8)
+ * of the OBSERVED outcomes from a handle whose sentinels are set: the cliff face evaluated there is reused instead of
+ * being evaluated again (boot_chi2test :54-59, boot_invvar :65-69 call both).  Bit-identical to geordd_chistat_obs /
+ * geordd_invvar_obs with the handle's sentinels and nugget; geordd_null_chistat_obs requires nugget == 0 (chistat has none). */
+GEORDD_API int geordd_null_chistat_obs(geordd_null* h, double* chi2);
+GEORDD_API int geordd_null_invvar_obs(geordd_null* h, double* tau_hat, double* var_tau, double* pval);
 /* Borrow the pooled null GP (make_null result; owned by the handle). */
 GEORDD_API int geordd_null_gp(geordd_null* h, geordd_gp** gp);
 /* a8: prior_rand(gp) for nsim draws (src/hypotest.jl:13-18): Y (n x nsim) = m + L z. Z as below. */

@@ -257,6 +257,8 @@ mutable struct B200Null               # make_null + draw-independent setup (src/
     nobs::Int
     y::Vector{Float64}
     alpha::Vector{Float64}
+    Xb::Union{Nothing,Matrix{Float64}}   # sentinels the handle is currently prepared for (and their nugget)
+    nugget::Float64
 end
 
 function make_null(gpT::B200GPE, gpC::B200GPE; Xb::Union{Nothing,AbstractMatrix}=nothing, nugget::Real=0.0)
@@ -267,16 +269,33 @@ function make_null(gpT::B200GPE, gpC::B200GPE; Xb::Union{Nothing,AbstractMatrix}
                    gpT.ptr, gpC.ptr, size(X, 2) == 0 ? C_NULL : pointer(X), size(X, 2), Float64(nugget), out, rounds, mll)
     check(gpT.ctx, rc)
     n = gpT.nobs + gpC.nobs
-    h = B200Null(gpT.ctx, out[], gpT, gpC, mll[], n, vcat(gpT.y, gpC.y), Vector{Float64}(undef, n))
+    h = B200Null(gpT.ctx, out[], gpT, gpC, mll[], n, vcat(gpT.y, gpC.y), Vector{Float64}(undef, n),
+                 size(X, 2) == 0 ? nothing : X, Float64(nugget))
     finalizer(n -> ccall((:geordd_null_destroy, LIB), Cint, (Ptr{Cvoid},), n.ptr), h)
     return h
 end
 
 function set_sentinels!(h::B200Null, Xb::AbstractMatrix, nugget::Real)
     X = Matrix{Float64}(Xb); rounds = Ref{Cint}(0)
+    h.Xb !== nothing && h.Xb == X && h.nugget == nugget && return 0     # already prepared for these sentinels
     GC.@preserve X check(h.ctx, ccall((:geordd_null_set_sentinels, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Cint, Cdouble, Ref{Cint}),
                                       h.ptr, X, size(X, 2), Float64(nugget), rounds))
+    h.Xb = X; h.nugget = Float64(nugget)
     return rounds[]
+end
+
+"chistat(gpT, gpC, Xb) of the observed outcomes from the cliff face the handle evaluated for its sentinels (bit-identical to chistat)"
+function chistat(h::B200Null)
+    out = Ref{Cdouble}(0.0)
+    check(h.ctx, ccall((:geordd_null_chistat_obs, LIB), Cint, (Ptr{Cvoid}, Ref{Cdouble}), h.ptr, out))
+    return out[]
+end
+
+"pval_invvar_uncalib(gpT, gpC, Xb; nugget) from the handle's cliff face (bit-identical to the three-argument method)"
+function pval_invvar_uncalib(h::B200Null)
+    τ = Ref{Cdouble}(0.0); V = Ref{Cdouble}(0.0); p = Ref{Cdouble}(0.0)
+    check(h.ctx, ccall((:geordd_null_invvar_obs, LIB), Cint, (Ptr{Cvoid}, Ref{Cdouble}, Ref{Cdouble}, Ref{Cdouble}), h.ptr, τ, V, p))
+    return p[]
 end
 
 "chistat(gpT, gpC, Xb) observed statistic (src/hypotest_chi2.jl:4-10)"
@@ -301,8 +320,8 @@ end
 
 "boot_chi2test(gpT, gpC, Xb, nsim) (src/hypotest_chi2.jl:54-59)"
 function boot_chi2test(gpT::B200GPE, gpC::B200GPE, Xb::AbstractMatrix, nsim::Integer; kwargs...)
-    gpNull = make_null(gpT, gpC)
-    chi_obs = chistat(gpT, gpC, Xb)
+    gpNull = make_null(gpT, gpC; Xb=Xb, nugget=0.0)      # one cliff face serves the observed statistic and the draws
+    chi_obs = chistat(gpNull)
     chi_sims = nsim_chi(gpT, gpC, gpNull, Xb, nsim; kwargs...)
     return mean(chi_sims .> chi_obs)
 end
@@ -341,8 +360,8 @@ end
 
 "nsim_invvar_pval_uncalib(gpT, gpC, Xb, nsim; nugget) (src/hypotest_invvar.jl:48-63)"
 function nsim_invvar_pval_uncalib(gpT::B200GPE, gpC::B200GPE, Xb::AbstractMatrix, nsim::Integer; nugget=1e-10,
-                                  seed::Integer=rand(UInt64), draw0::Integer=0, Z=nothing)
-    gpNull = make_null(gpT, gpC; Xb=Xb, nugget=nugget)
+                                  seed::Integer=rand(UInt64), draw0::Integer=0, Z=nothing, gpNull::Union{Nothing,B200Null}=nothing)
+    gpNull === nothing ? (gpNull = make_null(gpT, gpC; Xb=Xb, nugget=nugget)) : set_sentinels!(gpNull, Xb, nugget)
     Zm = zmat(Z, gpNull.nobs); ns = ndraws(Zm, nsim)
     pv = Vector{Float64}(undef, ns); cnt = Ref{Clonglong}(0)
     GC.@preserve Zm pv check(gpT.ctx, ccall((:geordd_null_invvar, LIB), Cint,
@@ -353,8 +372,9 @@ end
 
 "boot_invvar(gpT, gpC, Xb, nsim; nugget) (src/hypotest_invvar.jl:65-69)"
 function boot_invvar(gpT::B200GPE, gpC::B200GPE, Xb::AbstractMatrix, nsim::Integer; nugget=1e-10, kwargs...)
-    pval_obs = pval_invvar_uncalib(gpT, gpC, Xb; nugget=nugget)
-    pval_sims = nsim_invvar_pval_uncalib(gpT, gpC, Xb, nsim; nugget=nugget, kwargs...)
+    gpNull = make_null(gpT, gpC; Xb=Xb, nugget=nugget)
+    pval_obs = pval_invvar_uncalib(gpNull)
+    pval_sims = nsim_invvar_pval_uncalib(gpT, gpC, Xb, nsim; nugget=nugget, gpNull=gpNull, kwargs...)
     return mean(pval_sims .< pval_obs)
 end
 

@@ -30,10 +30,16 @@ for it in range(6):
         ctx.profile(False)
     print(line)
     nn.close()
-t0 = time.perf_counter()
-for _ in range(5):
-    G.boot_chi2test(a, b, Xb, S3, seed=6)
-ctx.sync(); print(f"boot_chi2test wall {(time.perf_counter()-t0)/5*1e3:.2f} ms")
+def three_step():
+    nn = G.make_null(a, b); obs = G.chistat(a, b, Xb)
+    _, cnt = G.nsim_chi(a, b, nn, Xb, S3, chi_obs=obs, return_count=True, seed=6); nn.close(); return cnt / S3
+for name, fn in (("boot_chi2test", lambda: G.boot_chi2test(a, b, Xb, S3, seed=6)), ("three explicit steps", three_step),
+                 ("boot_invvar", lambda: G.boot_invvar(a, b, Xb, S3, seed=6))):
+    ts = []
+    for _ in range(25):
+        ctx.sync(); t0 = time.perf_counter(); p = fn(); ctx.sync(); ts.append((time.perf_counter() - t0) * 1e3)
+    ts.sort()
+    print(f"{name}: min {ts[0]:.2f}  median {ts[len(ts)//2]:.2f}  max {ts[-1]:.2f} ms   (p = {p})")
 # pivoted LU solve alone: unblocked vs blocked kernel (CUDA-event time of the kernel)
 rng = np.random.default_rng(0)
 for n, nrhs in ((100, 1), (200, 1), (200, 202), (604, 1)):

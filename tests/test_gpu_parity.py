@@ -564,6 +564,31 @@ def test_blocked_lu_equals_unblocked_bit_for_bit(G, O, ctx, n, nrhs):
         assert relerr(x1, xo) < max(TOL, 50 * cond * np.finfo(float).eps)
 
 
+def test_observed_statistics_from_the_null_handle_are_bit_identical(G, O, ctx):
+    """geordd_null_chistat_obs / geordd_null_invvar_obs reuse the cliff face the handle evaluated when its sentinels were set;
+    they must return exactly what chistat / pval_invvar_uncalib (src/hypotest_chi2.jl:4-11, src/hypotest_invvar.jl:1-8)
+    return for the same sentinels and nugget, and refuse what they cannot serve."""
+    d = O.synth_two_region(300, 40, seed=12)
+    k = G.Mat32Iso(math.log(0.3), 0.0) + G.Const(math.log(20.0)); ln = math.log(0.3)
+    gT, gC = G.GPE.fit_many([d["XT"], d["XC"]], [d["YT"], d["YC"]], G.MeanZero(), k, ln)
+    n0 = G.NullGPE(gT, gC, d["Xb"], 0.0)
+    assert n0.chistat_obs() == G.chistat(gT, gC, d["Xb"])
+    n1 = G.NullGPE(gT, gC, d["Xb"], 1e-10)
+    assert n1.invvar_obs()[2] == G.pval_invvar_uncalib(gT, gC, d["Xb"], 1e-10)
+    with pytest.raises(ValueError):
+        n1.chistat_obs()                       # chistat has no nugget
+    with pytest.raises(ValueError):
+        G.NullGPE(gT, gC).chistat_obs()        # no sentinels
+    # and the bootstrap drivers built on them still equal the explicit three-step form
+    Z = np.asfortranarray(np.random.default_rng(3).standard_normal((600, 256)))
+    p = G.boot_chi2test(gT, gC, d["Xb"], 256, Z=Z)
+    sims = G.nsim_chi(gT, gC, G.make_null(gT, gC), d["Xb"], 256, Z=Z)
+    assert p == float(np.mean(sims > G.chistat(gT, gC, d["Xb"])))
+    p = G.boot_invvar(gT, gC, d["Xb"], 256, Z=Z)
+    pv = G.nsim_invvar_pval_uncalib(gT, gC, d["Xb"], 256, Z=Z)
+    assert p == float(np.mean(pv < G.pval_invvar_uncalib(gT, gC, d["Xb"])))
+
+
 def test_adjacent_sweep_matches_oracle(G, O, ctx):
     """The adjacent-pairs loop of the notebooks (src/regiondata.jl:64-68, NYC_analysis-2015.ipynb cell 74): three strips of
     the unit square, two shared borders; cliff face -> inverse-variance LATE -> calibrated p-value per pair against the
