@@ -35,6 +35,8 @@
 // The chunk source `Src` supplies per-chunk base pointers (so a K loop can walk over many tiles of a big matrix)
 // and a warp-level `ready(chunk)` hook where dataflow kernels wait for producer tiles.
 #pragma once
+#include <type_traits>
+#include <utility>
 #include "common.cuh"
 
 namespace geordd {
@@ -50,6 +52,14 @@ struct Ring {
     unsigned it;       // chunks pushed through the ring so far (same value in every thread)
     unsigned zero;     // 0 at run time, opaque to nvcc and ptxas (mbar_arrive_after)
     int* abort_word;
+};
+
+// Does the operand source offer the non-blocking try_ready(chunk)?  (see Mainloop::run)
+template <class S>
+struct src_can_defer {
+    template <class U> static auto probe(int) -> decltype(std::declval<U&>().try_ready(0), std::true_type{});
+    template <class> static std::false_type probe(...);
+    static constexpr bool value = decltype(probe<S>(0))::value;
 };
 
 template <int BN_, bool A_MC_, bool B_NC_, int STAGES_, int A_MODE_ = ROWS_TMA, int B_MODE_ = ROWS_TMA>
@@ -171,13 +181,22 @@ struct Mainloop {
         }
     }
 
-    template <class Src>
-    __device__ static __forceinline__ bool produce(double* smem, Ring& ring, unsigned it_load, int chunk, Src& src) {
-        if (SOLO && threadIdx.x >= 32) return true;   // warp 0 alone feeds the ring
+    // TRY = false: waits until the chunk's operands are published; false = the wait was aborted.
+    // TRY = true (sources with try_ready): one poll; PRODUCE_NOT_READY leaves the ring untouched -- the caller goes on
+    // consuming what it has and asks again.
+    static constexpr int PRODUCE_ABORT = 0, PRODUCE_OK = 1, PRODUCE_NOT_READY = 2;
+    template <bool TRY, class Src>
+    __device__ static __forceinline__ int produce(double* smem, Ring& ring, unsigned it_load, int chunk, Src& src) {
+        if (SOLO && threadIdx.x >= 32) return PRODUCE_OK;   // warp 0 alone feeds the ring
         const int s = it_load % STAGES;
         const unsigned ph = (it_load / STAGES) & 1u;
-        if (!mbar_wait(ring.empty + s, ph ^ 1u, ring.abort_word)) return false;   // all warps done with this stage
-        if (!src.ready(chunk)) return false;                                       // dataflow: operand tiles published
+        if constexpr (TRY) {
+            if (!src.try_ready(chunk)) return PRODUCE_NOT_READY;
+        }
+        if (!mbar_wait(ring.empty + s, ph ^ 1u, ring.abort_word)) return PRODUCE_ABORT;   // all warps done with this stage
+        if constexpr (!TRY) {
+            if (!src.ready(chunk)) return PRODUCE_ABORT;                                   // dataflow: operand tiles published
+        }
         double* As = smem + s * STAGE_ELEMS;
         double* Bs = As + A_ELEMS;
         uint64_t* bar = ring.full + s;
@@ -194,7 +213,7 @@ struct Mainloop {
         if (A_MODE == BLK_GEN) blk_gen<A_ELEMS>(As, src.a_ptr(chunk));
         if (B_MODE == BLK_GEN) blk_gen<B_ELEMS>(Bs, src.b_ptr(chunk));
         if (ANY_GEN) cp_async_mbar_arrive_noinc(bar);   // fires when this thread's cp.async of the stage have landed
-        return true;
+        return PRODUCE_OK;
     }
 
     // Returns the OR of the high words of every fragment loaded from the stage (the release dependency; only
@@ -239,15 +258,29 @@ struct Mainloop {
     // has been consumed by this warp.
     template <class Src>
     __device__ static bool run(double* smem, Ring& ring, int nchunks, Src& src, Acc& acc) {
-        unsigned it_load = ring.it, it_use = ring.it;
+        // Sources with a non-blocking try_ready (the dataflow Cholesky): a chunk whose operands are not published yet is
+        // DEFERRED -- the warp keeps consuming the chunks already in the ring and asks again after each, and blocks only
+        // when it has nothing left to compute.  Without this a consumer sat in the wait with STAGES-2 loaded chunks
+        // unconsumed, and their compute time landed on the critical path once the flag arrived (round 2 trace: 4.5 of the
+        // 46 us per tile column of the factorisation).
+        constexpr bool DEFER = src_can_defer<Src>::value;
+        const unsigned it0 = ring.it;
+        unsigned it_use = ring.it;
         ring.it += (unsigned)nchunks;
         const int lane = threadIdx.x & 31;
+        int nl = 0;   // chunks this warp has issued
         const int npro = nchunks < STAGES - 1 ? nchunks : STAGES - 1;
-        for (int c = 0; c < npro; ++c) {
-            if (!produce(smem, ring, it_load, c, src)) return false;
-            ++it_load;
+        while (nl < npro) {
+            const int r = (DEFER && nl > 0) ? produce<DEFER>(smem, ring, it0 + nl, nl, src) : produce<false>(smem, ring, it0 + nl, nl, src);
+            if (r == PRODUCE_ABORT) return false;
+            if (r == PRODUCE_NOT_READY) break;
+            ++nl;
         }
         for (int kc = 0; kc < nchunks; ++kc) {
+            if (DEFER && nl <= kc) {   // nothing left to compute: wait for this chunk's operands
+                if (produce<false>(smem, ring, it0 + nl, nl, src) == PRODUCE_ABORT) return false;
+                ++nl;
+            }
             const int s = it_use % STAGES;
             if (!mbar_wait(ring.full + s, (it_use / STAGES) & 1u, ring.abort_word)) return false;
             const unsigned token = compute(smem, s, acc);
@@ -268,10 +301,18 @@ struct Mainloop {
             // Refill AFTER computing: the stage to refill held chunk kc-1, which the other warps have had a whole
             // chunk time to release -- refilling before the compute made every producer wait for the slowest warp
             // once per chunk (7 % of all warp samples sat in that wait, profiles/r01d).
-            const int nxt = kc + STAGES - 1;
-            if (nxt < nchunks) {
-                if (!produce(smem, ring, it_load, nxt, src)) return false;
-                ++it_load;
+            if constexpr (DEFER) {
+                while (nl < nchunks && nl <= kc + STAGES - 1) {   // catches up after a deferral
+                    const int r = produce<true>(smem, ring, it0 + nl, nl, src);
+                    if (r == PRODUCE_ABORT) return false;
+                    if (r == PRODUCE_NOT_READY) break;
+                    ++nl;
+                }
+            } else {
+                const int nxt = kc + STAGES - 1;
+                if (nxt < nchunks) {
+                    if (produce<false>(smem, ring, it0 + nxt, nxt, src) == PRODUCE_ABORT) return false;
+                }
             }
         }
         return true;

@@ -73,6 +73,24 @@ struct PotrfSrc {
         if (tile_ok) return true;
         return warp_wait_flags(sflags + ta * SUBS + b, i != j ? sflags + tb * SUBS + b : nullptr, epoch, abort_word);
     }
+    // One poll instead of a wait (Mainloop::run defers the chunk and keeps computing).  May be asked repeatedly for the
+    // same chunk; chunks are still requested in increasing order, so an odd chunk's block column has been acquired by
+    // the successful call for the even chunk before it.
+    __device__ __forceinline__ bool try_ready(int c) {
+        if (c & 1) return true;
+        const int kt = c / CHUNKS_PER_TILE, b = (c % CHUNKS_PER_TILE) >> 1;
+        const long ta = (long)i * T + kt, tb = (long)j * T + kt;
+        if (b == 0) {
+            bool ok = ld_acquire(tflags + ta) == epoch;
+            if (i != j) ok = ok && ld_acquire(tflags + tb) == epoch;
+            tile_ok = __all_sync(0xffffffffu, ok) != 0;
+        }
+        if (tile_ok) return true;
+        // every lane acquires the flags itself (as warp_wait_flags does after its wait) before it touches the tile
+        bool ok = ld_acquire(sflags + ta * SUBS + b) == epoch;
+        if (i != j) ok = ok && ld_acquire(sflags + tb * SUBS + b) == epoch;
+        return __all_sync(0xffffffffu, ok) != 0;
+    }
 };
 
 constexpr int POTRF_CS_ELEMS = TILE * SC;
@@ -105,6 +123,11 @@ potrf_dataflow_kernel(const __grid_constant__ PotrfBatch pb, const int2* __restr
         __syncthreads();
         const int job = sh_job;
         if (job >= njobs) break;
+#ifdef GEORDD_POTRF_TRACE
+        if (tid == 0) { g_ptrace_base = flags; g_ptrace_cur[blockIdx.x] = job; }
+        __syncthreads();
+        if (tid == 0) PTRACE_JOB(0);
+#endif
         const int2 ij = jobs[job];
         const int mat = ij.x >> 16, i = ij.x & 0xffff, j = ij.y;
         const PotrfMat& M = pb.m[mat];
@@ -129,6 +152,7 @@ potrf_dataflow_kernel(const __grid_constant__ PotrfBatch pb, const int2* __restr
         PotrfSrc src{L, 0, 0, i, j, T, tflags, sflags, epoch, abort_word, false};
         bool ok = PotrfML::run(smem, ring, j * CHUNKS_PER_TILE, src, acc);
         if (__syncthreads_or(!ok)) break;   // also: every warp is done reading the ring before Cs overwrites it
+        if (tid == 0) PTRACE_JOB(1);
 #pragma unroll
         for (int a = 0; a < PotrfML::MI; ++a)
 #pragma unroll
@@ -137,6 +161,7 @@ potrf_dataflow_kernel(const __grid_constant__ PotrfBatch pb, const int2* __restr
                 for (int e = 0; e < 2; ++e)
                     Cs[PotrfML::acc_col(b, e) * SC + PotrfML::acc_row(a)] = -acc.v[a][b][e];
         __syncthreads();
+        if (tid == 0) PTRACE_JOB(2);
 
         double* Lij = L + tile_off(i, j, T);   // stored image: (m, n) at n * TLD + m, same as Cs (SC == TLD)
         unsigned* my_sub = sflags + ((long)i * T + j) * SUBS;
@@ -154,9 +179,21 @@ potrf_dataflow_kernel(const __grid_constant__ PotrfBatch pb, const int2* __restr
                 break;
         }
         // all block columns of the tile have been stored (and their stores ordered before a barrier) by the tile operation
-        if (tid == 0) st_release(tflags + (long)i * T + j, epoch);
+        if (tid == 0) { st_release(tflags + (long)i * T + j, epoch); PTRACE_JOB(3); }
     }
 }
+
+#ifdef GEORDD_POTRF_TRACE
+}  // namespace geordd
+// debug builds only: the stamps of the last factorisation (jobs: 8192 x 16, flags: 65536 words), nanoseconds of %globaltimer
+extern "C" __attribute__((visibility("default"))) int geordd_dbg_potrf_trace(unsigned long long* jobs_out, unsigned long long* flags_out) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(jobs_out, geordd::g_ptrace_job, sizeof(unsigned long long) * 8192 * 16) != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(flags_out, geordd::g_ptrace_flag, sizeof(unsigned long long) * 65536) != cudaSuccess) return -1;
+    return 0;
+}
+namespace geordd {
+#endif
 
 // Column-major job list of one matrix; tiles of a prefilled leading block are not jobs.
 static void build_potrf_jobs(int mat, int T, int P, std::vector<int2>& out) {

@@ -148,6 +148,24 @@ static __device__ __noinline__ void potrf_diag32(double* Cs, double* invd, int* 
 }
 
 // Named barriers (barrier 0 is __syncthreads): producer / consumer hand-over between warp 0 and warps 1..7 inside potrf_tile.
+// ---- in-situ timeline of the dataflow Cholesky (debug builds with -DGEORDD_POTRF_TRACE only; scripts/gpu_potrf_trace.py) ----
+#ifdef GEORDD_POTRF_TRACE
+static __device__ unsigned long long g_ptrace_job[8192 * 16];    // per job: 0 picked, 1 updates done, 2 tile op begins, 3 done, 4.. waits
+static __device__ unsigned long long g_ptrace_flag[65536];       // release time of every flag word
+static __device__ unsigned* g_ptrace_base;
+static __device__ int g_ptrace_cur[256];                         // job of the CTA (by block index)
+__device__ __forceinline__ unsigned long long ptrace_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define PTRACE_JOB(slot) do { int jb__ = g_ptrace_cur[blockIdx.x]; if (jb__ < 8192) g_ptrace_job[jb__ * 16 + (slot)] = ptrace_now(); } while (0)
+#define PTRACE_FLAG(ptr) do { long o__ = (ptr) - g_ptrace_base; if (o__ >= 0 && o__ < 65536) g_ptrace_flag[o__] = ptrace_now(); } while (0)
+#else
+#define PTRACE_JOB(slot) do {} while (0)
+#define PTRACE_FLAG(ptr) do {} while (0)
+#endif
+
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
@@ -230,7 +248,7 @@ __device__ inline void potrf_tile(double* Cs, double* invd, int* sh_info, long l
             if (Lg && !bad) {
                 store_block_col(o, tid, NTHREADS);
                 __syncthreads();
-                if (tid == 0) st_release(sub + o / NB, epoch);
+                if (tid == 0) { st_release(sub + o / NB, epoch); PTRACE_FLAG(sub + o / NB); }
             }
             break;
         }
@@ -295,7 +313,7 @@ __device__ inline void potrf_tile(double* Cs, double* invd, int* sh_info, long l
             if (Lg && !bad) {                // block column o is final: store it, publish it
                 store_block_col(o, tid - 32, NTHREADS - 32);
                 named_bar_sync(2, NTHREADS - 32);
-                if (tid == 32) st_release(sub + o / NB, epoch);
+                if (tid == 32) { st_release(sub + o / NB, epoch); PTRACE_FLAG(sub + o / NB); }
             }
             // 3b. trailing lower triangle -= P P^T for the rows below the next diagonal block (8x8 m-tiles 4.. of the trailing part)
             const int mtiles = rest / 8;
@@ -404,7 +422,7 @@ __device__ inline bool trsm_right_tile(double* Cs, double* Lp0, double* Lp1, dou
         if (loaded < b) {
             if (!whole) {
                 int ok = 1;
-                if (tid == 0) ok = wait_flag(dsub + b, epoch, abort_word);
+                if (tid == 0) { ok = wait_flag(dsub + b, epoch, abort_word); PTRACE_JOB(4 + b); }
                 if (!__syncthreads_and(ok)) return false;
             }
             load_col_panel_async(Lp, Lt, ld, o);
@@ -424,6 +442,7 @@ __device__ inline bool trsm_right_tile(double* Cs, double* Lp0, double* Lp1, dou
             cp_async_wait<0>();
         }
         __syncthreads();
+        if (tid == 0) PTRACE_JOB(8 + b);   // panel b is in shared memory
         if (tid < NB) invd[tid] = 1.0 / Lp[tid * SC + o + tid];
         __syncthreads();
         lap(0);
@@ -454,7 +473,7 @@ __device__ inline bool trsm_right_tile(double* Cs, double* Lp0, double* Lp1, dou
         }
         __syncthreads();
         lap(2);
-        if (Xg && tid == 0) st_release(xsub + b, epoch);   // every thread's stores precede the barrier above
+        if (Xg && tid == 0) { st_release(xsub + b, epoch); PTRACE_FLAG(xsub + b); }   // every thread's stores precede the barrier above
     }
     return true;
 }

@@ -1,0 +1,59 @@
+"""In-situ timeline of the dataflow Cholesky (build with -DGEORDD_POTRF_TRACE: `python scripts/gpu_potrf_trace.py --build`
+here, then run the same script without --build on the GPU box).  Prints, for a few tile columns j, when the diagonal job and
+the first right solve below it were picked / had their updates done / started and ended their tile operation, when each block
+column flag was released, and the resulting length of the critical path per column."""
+import ctypes as C, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+if "--build" in sys.argv:
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gbuild", os.path.join(ROOT, "geordd.jl_b200", "build.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    print(m.build(defines=["GEORDD_POTRF_TRACE"], suffix="_trace"))
+    sys.exit(0)
+os.environ["GEORDD_B200_LIB"] = os.path.join(ROOT, "geordd.jl_b200", "lib", "libgeordd_b200_trace.so")
+import numpy as np
+import georddb200
+G = georddb200.load(); ctx = G.default_context()
+lib = ctx.lib
+n = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 4096
+T, SUBS = n // 128, 4
+b, m = ctx.bench_potrf(n, 3)
+print(f"potrf n={n}: best {b:.3f} ms (traced build)")
+jobs = np.zeros(8192 * 16, dtype=np.uint64); flags = np.zeros(65536, dtype=np.uint64)
+fn = lib.geordd_dbg_potrf_trace
+fn.restype = C.c_int; fn.argtypes = [C.c_void_p, C.c_void_p]
+assert fn(jobs.ctypes.data, flags.ctypes.data) == 0
+jobs = jobs.reshape(8192, 16).astype(np.int64); flags = flags.astype(np.int64)
+index = {}
+k = 0
+for j in range(T):
+    for i in range(j, T):
+        index[(i, j)] = k; k += 1
+t0 = jobs[index[(0, 0)], 0]
+us = lambda t: (t - t0) / 1e3
+def sub(i, j, s): return flags[T * T + (i * T + j) * SUBS + s]
+prev_end = None
+rows = []
+for j in range(T - 1):
+    d, r = jobs[index[(j, j)]], jobs[index[(j + 1, j)]]
+    rows.append((j, us(d[0]), us(d[1]), us(d[2]), us(d[3]), [us(sub(j, j, s)) for s in range(SUBS)],
+                 us(r[0]), us(r[1]), us(r[2]), [us(r[4 + s]) for s in range(SUBS)], [us(r[8 + s]) for s in range(SUBS)],
+                 [us(sub(j + 1, j, s)) for s in range(SUBS)], us(r[3])))
+print("times in us since the first job was picked")
+for j, dp, dm, dt, dd, dsub, rp, rm, rt, rwait, rpan, xsub, rd in rows:
+    if j in (0, 1, 2) or (T // 2 - 1 <= j <= T // 2 + 1) or j >= T - 3:
+        print(f"col {j:2d}  diag: picked {dp:8.1f} updates done {dm:8.1f} tile op {dt:8.1f} -> {dd:8.1f} ({dd - dt:5.1f})  subs " + " ".join(f"{x:8.1f}" for x in dsub))
+        print(f"        trsm({j+1},{j}): picked {rp:8.1f} updates done {rm:8.1f} tile op {rt:8.1f}  saw subs " + " ".join(f"{x:8.1f}" for x in rwait)
+              + "  panels in smem " + " ".join(f"{x:8.1f}" for x in rpan) + "  xsubs " + " ".join(f"{x:8.1f}" for x in xsub) + f"  done {rd:8.1f}")
+per = [rows[q + 1][3] - rows[q][3] for q in range(len(rows) - 1)]
+print("diag tile-op start to next diag tile-op start, per column (us): " + " ".join(f"{x:.1f}" for x in per))
+seg = {"potrf_tile (start -> last sub released)": [r[5][3] - r[3] for r in rows],
+       "last diag sub released -> trsm saw it": [r[9][3] - r[5][3] for r in rows],
+       "trsm saw last sub -> panel in smem": [r[10][3] - r[9][3] for r in rows],
+       "panel in smem -> last xsub released": [r[11][3] - r[10][3] for r in rows],
+       "last xsub released -> next diag updates done": [rows[q + 1][2] - rows[q][11][3] for q in range(len(rows) - 1)],
+       "updates done -> tile op begins": [r[3] - r[2] for r in rows]}
+for name, v in seg.items():
+    v = np.array(v[1:-1])
+    print(f"  {name:48s} median {np.median(v):6.2f}  min {v.min():6.2f}  max {v.max():6.2f}")
