@@ -125,22 +125,26 @@ static __device__ __noinline__ void potrf_diag32(double* Cs, double* invd, int* 
                 const double inv = __shfl_sync(0xffffffffu, inv_own, c);
                 if (lane == c && !pos) first_bad = c + 1;          // branch-free in SASS: keeps the block one basic block
                 const double l = a[c] * inv;                       // column c of L below the diagonal (lanes > c)
-                if (lane == c) {
-                    a[c] = diag * inv;                             // L(c,c)
-                    invd[o + c] = inv;
-                } else {
-                    a[c] = l;
-                }
+                if (lane == c) invd[o + c] = inv;
+                // The finished column goes to its place in shared memory at once: that store is also how the other lanes
+                // get L(c2, c) for their updates (broadcast LDS.128, two entries per load) -- the 2 x 496 shuffles of the
+                // first version made this function 48 KB of straight-line code, more than an SM's instruction cache.
+                double* colc = Cs + (o + c) * SC + o;
+                if (lane >= c) colc[lane] = lane == c ? diag * inv : l;
                 diag = fma(-l, l, diag);                           // own pivot, no shuffle (only lanes > c still need it)
+                if (c + 1 < NB) {                                  // the next pivot's column stays on the shuffle: it is on the chain
+                    const double l1 = __shfl_sync(0xffffffffu, l, c + 1);
+                    a[c + 1] = fma(-l, l1, a[c + 1]);
+                }
+                __syncwarp();
+                if (((c + 2) & 1) != 0 && c + 2 < NB) a[c + 2] = fma(-l, colc[c + 2], a[c + 2]);
 #pragma unroll
-                for (int c2 = c + 1; c2 < NB; ++c2) {              // branch-free: entries on/above the diagonal are
-                    double l2 = __shfl_sync(0xffffffffu, l, c2);   // never read again
-                    a[c2] = fma(-l, l2, a[c2]);
+                for (int c2 = (c + 3) & ~1; c2 + 1 < NB; c2 += 2) {   // entries on/above the diagonal are never read again
+                    const double2 v = *reinterpret_cast<const double2*>(colc + c2);
+                    a[c2] = fma(-l, v.x, a[c2]);
+                    a[c2 + 1] = fma(-l, v.y, a[c2 + 1]);
                 }
             }
-#pragma unroll
-            for (int c = 0; c < NB; ++c)
-                if (lane >= c) Cs[(o + c) * SC + o + lane] = a[c];
             // LAPACK info = first non-positive pivot: smallest failing column over the lanes
             unsigned bad = __ballot_sync(0xffffffffu, first_bad != 0);
             if (bad != 0 && lane == 0) atomicCAS(sh_info, 0, o + __ffs(bad));
@@ -160,9 +164,11 @@ __device__ __forceinline__ unsigned long long ptrace_now() {
     return t;
 }
 #define PTRACE_JOB(slot) do { int jb__ = g_ptrace_cur[blockIdx.x]; if (jb__ < 8192) g_ptrace_job[jb__ * 16 + (slot)] = ptrace_now(); } while (0)
+#define PTRACE_IT(o, k) do { if ((o) / NB < 2 && 4 + 6 * ((o) / NB) + (k) < 13) PTRACE_JOB(4 + 6 * ((o) / NB) + (k)); } while (0)
 #define PTRACE_FLAG(ptr) do { long o__ = (ptr) - g_ptrace_base; if (o__ >= 0 && o__ < 65536) g_ptrace_flag[o__] = ptrace_now(); } while (0)
 #else
 #define PTRACE_JOB(slot) do {} while (0)
+#define PTRACE_IT(o, k) do {} while (0)
 #define PTRACE_FLAG(ptr) do {} while (0)
 #endif
 
@@ -238,7 +244,18 @@ __device__ inline void potrf_tile(double* Cs, double* invd, int* sh_info, long l
     }
     return;
 #endif
+#ifdef GEORDD_POTRF_TRACE
+    const long long c0__ = clock64();
+    const unsigned long long g0__ = ptrace_now();
+#endif
     if (warp == 0) potrf_diag32(Cs, invd, sh_info, 0);
+    if (Lg && tid == 0) PTRACE_JOB(15);   // first diagonal block factored (warp 0, before the barrier)
+#ifdef GEORDD_POTRF_TRACE
+    if (Lg && tid == 0) {   // cycles and nanoseconds of this call: the SM clock the chain actually runs at
+        int jb__ = g_ptrace_cur[blockIdx.x];
+        if (jb__ < 8192) { g_ptrace_job[jb__ * 16 + 14] = (unsigned long long)(clock64() - c0__); g_ptrace_job[jb__ * 16 + 13] = ptrace_now() - g0__; }
+    }
+#endif
     __syncthreads();
     lap(0);
     for (int o = 0; o < TILE; o += NB) {
@@ -266,6 +283,7 @@ __device__ inline void potrf_tile(double* Cs, double* invd, int* sh_info, long l
         if (warp == 0) {
             named_bar_arrive(1, NTHREADS);   // my panel rows are written (the others need them for their update)
             __syncwarp();
+            if (Lg && tid == 0) PTRACE_IT(o, 0);
             // 3a. next diagonal block -= P0 P0^T (the 10 lower 8x8 tiles), from this warp's own 32 panel rows.  A and B
             //     fragments coincide (same panel), all ten accumulators are live so the DMMAs issue back to back.
             const int lane = tid & 31, g = lane >> 2, tq = lane & 3;
@@ -305,15 +323,18 @@ __device__ inline void potrf_tile(double* Cs, double* invd, int* sh_info, long l
             }
             __syncwarp();
             lap(1);
+            if (Lg && tid == 0) PTRACE_IT(o, 1);
             // 1'. factor the next diagonal block while warps 1..7 finish the trailing update
             potrf_diag32(Cs, invd, sh_info, o + NB);
             lap(0);
+            if (Lg && tid == 0) PTRACE_IT(o, 2);
         } else {
             named_bar_sync(1, NTHREADS);     // all panel rows of this iteration are in shared memory
+            if (Lg && tid == 32) PTRACE_IT(o, 3);
             if (Lg && !bad) {                // block column o is final: store it, publish it
                 store_block_col(o, tid - 32, NTHREADS - 32);
                 named_bar_sync(2, NTHREADS - 32);
-                if (tid == 32) { st_release(sub + o / NB, epoch); PTRACE_FLAG(sub + o / NB); }
+                if (tid == 32) { PTRACE_IT(o, 4); st_release(sub + o / NB, epoch); PTRACE_FLAG(sub + o / NB); }
             }
             // 3b. trailing lower triangle -= P P^T for the rows below the next diagonal block (8x8 m-tiles 4.. of the trailing part)
             const int mtiles = rest / 8;
@@ -356,6 +377,7 @@ __device__ inline void potrf_tile(double* Cs, double* invd, int* sh_info, long l
                     }
                 }
             }
+            if (Lg && tid == 32) PTRACE_IT(o, 5);
         }
         __syncthreads();
         lap(2);

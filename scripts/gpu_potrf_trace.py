@@ -54,6 +54,16 @@ seg = {"potrf_tile (start -> last sub released)": [r[5][3] - r[3] for r in rows]
        "panel in smem -> last xsub released": [r[11][3] - r[10][3] for r in rows],
        "last xsub released -> next diag updates done": [rows[q + 1][2] - rows[q][11][3] for q in range(len(rows) - 1)],
        "updates done -> tile op begins": [r[3] - r[2] for r in rows]}
+names = ["w0 panel rows done", "w0 next-diag update done", "w0 next diag32 done", "w1-7 past bar1", "w1-7 stored (bar2)", "w1-7 trailing update done"]
+v0 = np.array([jobs[index[(j, j)], 15] - jobs[index[(j, j)], 2] for j in range(1, T - 1)]) / 1e3
+print(f"  first diag32 done {np.median(v0):.2f} us after the tile op began")
+cyc = np.array([jobs[index[(j, j)], 14] for j in range(1, T - 1)]); ns = np.array([jobs[index[(j, j)], 13] for j in range(1, T - 1)])
+print(f"  first diag32: {np.median(cyc):.0f} cycles in {np.median(ns):.0f} ns -> SM clock {np.median(cyc / np.maximum(ns, 1)):.3f} GHz")
+for it in range(2):
+    print(f"  inside potrf_tile, iteration {it} (us after the tile op began; median over the columns):")
+    for k, nm in enumerate(names[:3] if it == 1 else names):
+        v = np.array([jobs[index[(j, j)], 4 + 6 * it + k] - jobs[index[(j, j)], 2] for j in range(1, T - 1)]) / 1e3
+        print(f"      {nm:30s} {np.median(v):6.2f}")
 for name, v in seg.items():
     v = np.array(v[1:-1])
     print(f"  {name:48s} median {np.median(v):6.2f}  min {v.min():6.2f}  max {v.max():6.2f}")
