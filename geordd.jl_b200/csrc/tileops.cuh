@@ -60,6 +60,53 @@ __device__ __forceinline__ void tile_update(double* Cs, int m0, int mtiles, int 
                                             bool lower) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, tq = lane & 3;
+    if (!lower && mtiles == 16) {
+        // Full-height rectangular update (the in-tile update of the right solve, on the critical path of the Cholesky): the
+        // warp's two m-tiles (warp, warp + 8) advance together, so every B fragment is loaded once for two DMMAs.
+        // Per entry the same accumulation in the same order as below.
+        const int mt0 = warp, mt1 = warp + 8;
+        double a0[NB / 4], a1[NB / 4];
+#pragma unroll
+        for (int kk = 0; kk < NB / 4; ++kk) {
+            a0[kk] = fa(mt0 * 8 + g, kk * 4 + tq);
+            a1[kk] = fa(mt1 * 8 + g, kk * 4 + tq);
+        }
+        for (int nt0 = 0; nt0 < ntiles; nt0 += 4) {
+            double c0[4][2], c1[4][2];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (nt0 + u < ntiles) {
+                    const int n = n0 + (nt0 + u) * 8 + 2 * tq, ma = m0 + mt0 * 8 + g, mb = m0 + mt1 * 8 + g;
+                    c0[u][0] = -Cs[n * SC + ma];
+                    c0[u][1] = -Cs[(n + 1) * SC + ma];
+                    c1[u][0] = -Cs[n * SC + mb];
+                    c1[u][1] = -Cs[(n + 1) * SC + mb];
+                }
+            }
+#pragma unroll
+            for (int kk = 0; kk < NB / 4; ++kk) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (nt0 + u < ntiles) {
+                        const double b = fb(kk * 4 + tq, (nt0 + u) * 8 + g);
+                        dmma(c0[u][0], c0[u][1], a0[kk], b);
+                        dmma(c1[u][0], c1[u][1], a1[kk], b);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (nt0 + u < ntiles) {
+                    const int n = n0 + (nt0 + u) * 8 + 2 * tq, ma = m0 + mt0 * 8 + g, mb = m0 + mt1 * 8 + g;
+                    Cs[n * SC + ma] = -c0[u][0];
+                    Cs[(n + 1) * SC + ma] = -c0[u][1];
+                    Cs[n * SC + mb] = -c1[u][0];
+                    Cs[(n + 1) * SC + mb] = -c1[u][1];
+                }
+            }
+        }
+        return;
+    }
     for (int mt = warp; mt < mtiles; mt += 8) {
         double a[NB / 4];
 #pragma unroll
