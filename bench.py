@@ -478,6 +478,12 @@ def main():
                        "frac_of_dmma_peak_power": f5p / world / (ms_c5p * 1e-3) / 1e12 / dmma_peak}
         n5.close(); g5[True].close(); g5[False].close()
 
+    if world > 1:
+        # every collective of the run is behind us: leave the process group BEFORE rank 0's private measurements, so that no
+        # rank sits in an NCCL barrier (with its watchdog) while rank 0 times single-GPU shapes and the CPU baseline
+        dist.barrier()
+        dist.destroy_process_group()
+
     if rank == 0:
         # ---- rank 0 only: FP64 tensor-pipe ceiling, Cholesky, cliff-face latency, C2, K1, vendor ----------------
         # (the host drivers shard and all-reduce automatically under torch.distributed; nothing in this block may enter a
@@ -674,9 +680,6 @@ def main():
                 "extra": extra}
         print(json.dumps(line))
         _local.__exit__(None, None, None)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
