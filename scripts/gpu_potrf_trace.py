@@ -25,11 +25,13 @@ fn = lib.geordd_dbg_potrf_trace
 fn.restype = C.c_int; fn.argtypes = [C.c_void_p, C.c_void_p]
 assert fn(jobs.ctypes.data, flags.ctypes.data) == 0
 jobs = jobs.reshape(8192, 16).astype(np.int64); flags = flags.astype(np.int64)
-index = {}
+# the job list of launch_potrf_batch (potrf.cu: build_potrf_jobs): column-major
+index, segs, ktiles = {}, {}, {}
 k = 0
 for j in range(T):
     for i in range(j, T):
-        index[(i, j)] = k; k += 1
+        index[(i, j)] = k; ktiles[k] = j; k += 1
+njobs_total = k
 t0 = jobs[index[(0, 0)], 0]
 us = lambda t: (t - t0) / 1e3
 def sub(i, j, s): return flags[T * T + (i * T + j) * SUBS + s]
@@ -67,3 +69,23 @@ for it in range(2):
 for name, v in seg.items():
     v = np.array(v[1:-1])
     print(f"  {name:48s} median {np.median(v):6.2f}  min {v.min():6.2f}  max {v.max():6.2f}")
+# ---- where the CTA time goes (all jobs): K-loop span vs the DMMA time it needs, tile operations, and the rest ----
+njobs = njobs_total
+J = jobs[:njobs]
+t_begin, t_end = J[:, 0].min(), J[:, 3].max()
+chunk_us = 2.0 * 128 * 128 * 16 / (37.07e12 / 148) * 1e6
+ideal = sum(kt * 8 * chunk_us for kt in ktiles.values())
+span_ml = float(np.sum(J[:, 1] - J[:, 0])) / 1e3
+span_tile = float(np.sum(J[:, 3] - J[:, 2])) / 1e3
+span_epi = float(np.sum(J[:, 2] - J[:, 1])) / 1e3
+total = 148 * (t_end - t_begin) / 1e3
+print(f"CTA time, n={n}: kernel {1e-3 * (t_end - t_begin):.0f} us x 148 CTAs = {total / 1e3:.1f} ms;  K loops {span_ml / 1e3:.1f} ms "
+      f"(DMMA time they need at the pipe peak: {ideal / 1e3:.1f} ms = {100 * ideal / span_ml:.0f} %), tile operations {span_tile / 1e3:.1f} ms, "
+      f"epilogues {span_epi / 1e3:.2f} ms, not in a job {(total - span_ml - span_tile - span_epi) / 1e3:.1f} ms")
+# K-loop efficiency by tile column
+for lo in range(0, T, max(1, T // 8)):
+    hi = min(T, lo + max(1, T // 8))
+    sel = [q for (i, j), q in index.items() if lo <= j < hi] + [q for (i, j, sg), q in segs.items() if lo <= j < hi]
+    need = sum(ktiles[q] * 8 * chunk_us for q in sel)
+    sp = float(np.sum(J[sel, 1] - J[sel, 0])) / 1e3
+    print(f"   columns {lo:3d}..{hi - 1:3d}: K-loop spans {sp / 1e3:7.2f} ms, needed {need / 1e3:7.2f} ms ({100 * need / max(sp, 1e-9):3.0f} %)")
