@@ -589,7 +589,7 @@ end
 function B200Realisations(rdict::Dict{KEY,RegionData}, kernel::Kernel, logNoise, mean::Mean=MeanZero();
                           groupKeys::Vector{KEY}=collect(keys(rdict))) where {KEY}
     all(length(rdict[key].y) > 0 for key in groupKeys) || throw("empty group")
-    gps = fit_many([rdict[key].X for key in groupKeys], [rdict[key].y for key in groupKeys], mean, kernel, logNoise)
+    gps = fit_many([rdict[key].x for key in groupKeys], [rdict[key].y for key in groupKeys], mean, kernel, logNoise)
     d = Dict{KEY,B200GPE}(zip(groupKeys, gps))
     return B200Realisations{KEY}(groupKeys, d, kernel, lognoise(logNoise), mean, sum(g.nobs for g in gps), sum(g.mll for g in gps))
 end
