@@ -396,12 +396,16 @@ geordd_gp* gp_create(geordd_ctx* c, const geordd_kernel* k, const double* X, int
 // of small / latency-bound launches (the few-column solve is a chain of T dependent row blocks on T SMs).  They run side by
 // side on up to four side streams (own job counter and flag region per lane), forked from and joined back into the
 // context's stream with events; all scalars come back with ONE copy.  Same kernels, same arithmetic as gp_finish.
-static void gp_finish_batch(geordd_ctx* c, int nfit, geordd_gp** gps, const double* const* ys) {
+void ensure_side_streams(geordd_ctx* c) {
     for (int l = 0; l < NARROW_LANES; ++l) {
         if (!c->side[l]) GD_CUDA(cudaStreamCreateWithFlags(&c->side[l], cudaStreamNonBlocking));
         if (!c->ev_join[l]) GD_CUDA(cudaEventCreateWithFlags(&c->ev_join[l], cudaEventDisableTiming));
     }
     if (!c->ev_fork) GD_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+}
+
+static void gp_finish_batch(geordd_ctx* c, int nfit, geordd_gp** gps, const double* const* ys) {
+    ensure_side_streams(c);
     constexpr int kRound = 24;   // two scalars per fit in d_scal[8 .. 8 + 2 * kRound)
     std::vector<std::vector<double>> resid(nfit);
     for (int f0 = 0; f0 < nfit; f0 += kRound) {
@@ -608,6 +612,7 @@ int geordd_ctx_destroy(geordd_ctx* c) {
     cudaFree(c->d_tally); cudaFreeHost(c->h_tally);
     tl_ctx = c;
     c->ws.release(); c->tmp0.release(); c->tmp1.release(); c->tmp2.release(); c->tmp3.release();
+    c->ws2.release(); c->tmp4.release(); c->tmp5.release();
     pool_trim(c, 0);
     for (auto& kv : c->pool_live) cudaFree(kv.first);
     c->pool_live.clear();

@@ -79,6 +79,7 @@ struct geordd_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
     geordd::DevBuf ws;                        // split-K workspace
     geordd::DevBuf tmp0, tmp1, tmp2, tmp3;    // generic scratch matrices
+    geordd::DevBuf ws2, tmp4, tmp5;           // side-stream twins (cliff face: the control side runs beside the treated side)
     // profiling
     bool prof_on = false;
     struct Rec { int cls; cudaEvent_t a, b; };
@@ -166,6 +167,7 @@ double read_scalar(geordd_ctx* c, const double* d);   // sync D2H of one double
 void upload2d(geordd_ctx* c, double* dst, long ldd, const double* src, long lds, int rows, int cols);
 void download2d(geordd_ctx* c, double* dst, long ldd, const double* src, long lds, int rows, int cols);
 void ensure_ws(geordd_ctx* c, size_t count);
+void ensure_side_streams(geordd_ctx* c);   // c->side[], c->ev_fork, c->ev_join[] (created on first use)
 long long g_guard_violations_get();
 
 KernelSpecDev to_dev(const geordd_kernel& k);

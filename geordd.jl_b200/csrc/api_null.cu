@@ -10,12 +10,36 @@ static const double kLog2Pi = 1.8378770664093453;   // log(2*pi)
 void cliff_face_dev(geordd_gp* T, geordd_gp* C, const double* dXb, int nb, int nbp, double* dMuSlab, double* dSigma) {
     geordd_ctx* c = T->ctx;
     geordd_gp* sides[2] = {T, C};
+    // The two sides are independent chains of small launches (covariance -> K_xb' alpha -> whitening solve, a chain of T
+    // dependent row blocks -> V'V).  With few sentinels (the latency-optimised few-column solve, private job counter / flag
+    // region per lane) the control side runs on a side stream beside the treated side; its two contributions are subtracted
+    // on the main stream afterwards, in the order and with the roundings of the sequential form below (alpha = -1, beta = 1:
+    // c - acc either way), so mu and Sigma are bit-identical to it.
+    const bool two_streams = nb <= NARROW_MAX_COLS && T->npad > TILE && C->npad > TILE;
+    double *KxbC = nullptr, *dotC = nullptr, *GC = nullptr;
+    if (two_streams) {
+        ensure_side_streams(c);
+        const int mp = C->npad;
+        c->tmp4.ensure((size_t)mp * nbp, c->stream, false);
+        c->tmp5.ensure((size_t)nbp * 64 + (size_t)nbp * nbp, c->stream, false);
+        const int sk_mu = pick_splitk(c, nbp, 64, mp), sk_g = pick_splitk(c, nbp, nbp, mp);
+        c->ws2.ensure((size_t)std::max(sk_mu * 64, sk_g * nbp) * nbp, c->stream, false);
+        KxbC = c->tmp4.p; dotC = c->tmp5.p; GC = dotC + (size_t)nbp * 64;
+        cudaStream_t ss = c->side[0];
+        GD_CUDA(cudaEventRecord(c->ev_fork, c->stream));   // after everything queued so far (the fits, the sentinels' upload)
+        GD_CUDA(cudaStreamWaitEvent(ss, c->ev_fork, 0));
+        launch_cov(ss, to_dev(C->k), C->dX, C->n, dXb, nb, C->dim, false, false, 0.0, KxbC, mp, mp, nbp, false);
+        launch_gemm(ss, false, false, nbp, 64, mp, 1.0, KxbC, mp, C->dAlpha, mp, 0.0, dotC, nbp, sk_mu, c->ws2.p);
+        launch_solve_narrow(ss, c->sched, SOLVE_FWD, C->dL, mp, KxbC, mp, nb, 1);
+        launch_gemm(ss, false, false, nbp, nbp, mp, 1.0, KxbC, mp, KxbC, mp, 0.0, GC, nbp, sk_g, c->ws2.p);
+        GD_CUDA(cudaEventRecord(c->ev_join[0], ss));
+    }
     // Sigma = K_bb(T) + K_bb(C)  (each side's own kernel), then -= V'V per side
     for (int s = 0; s < 2; ++s) {
         ProfScope ps(c, PC_COV);
         launch_cov(c->stream, to_dev(sides[s]->k), dXb, nb, dXb, nb, 2, true, true, 0.0, dSigma, nbp, nbp, nbp, s == 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < (two_streams ? 1 : 2); ++s) {
         geordd_gp* gp = sides[s];
         const int m = gp->n, mp = gp->npad;
         const double sign = s == 0 ? 1.0 : -1.0;
@@ -35,6 +59,12 @@ void cliff_face_dev(geordd_gp* T, geordd_gp* C, const double* dXb, int nb, int n
             launch_solve(c->stream, c->sched, SOLVE_FWD, gp->dL, mp, Kxb, mp, nbp, none, nb);
         }
         gemm(c, false, false, nbp, nbp, mp, -1.0, Kxb, mp, Kxb, mp, 1.0, dSigma, nbp, 0);
+    }
+    if (two_streams) {
+        GD_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join[0], 0));
+        launch_axpby(c->stream, (long)nbp * 64, -1.0, dotC, 1.0, dMuSlab);
+        launch_add_const(c->stream, dMuSlab, nbp, nb, 1, -C->k.mean_const);
+        launch_axpby(c->stream, (long)nbp * nbp, -1.0, GC, 1.0, dSigma);
     }
     launch_mirror_lower(c->stream, dSigma, nbp, nbp);   // copytri!: exactly symmetric
 }
