@@ -439,8 +439,8 @@ def main():
         X3T, X3C, Y3T, Y3C, X3b = synth(m3, nb3, seed=3)
         g3 = G.GPRealisations({True: G.RegionData(X3T, Y3T, np.empty((0, m3))), False: G.RegionData(X3C, Y3C, np.empty((0, m3)))},
                               k, ln, groupKeys=[True, False], ctx=ctx)
-        ms_chi = wall(lambda: G.boot_chi2test(g3[True], g3[False], X3b, S3, seed=6))
-        ms_inv = wall(lambda: G.boot_invvar(g3[True], g3[False], X3b, S3, seed=6))
+        ms_chi = wall(lambda: G.boot_chi2test(g3[True], g3[False], X3b, S3, seed=6), reps=9)
+        ms_inv = wall(lambda: G.boot_invvar(g3[True], g3[False], X3b, S3, seed=6), reps=9)
         f3 = flops_per_chi_draw(m3, nb3) * S3
         extra["c3"] = {"what": "1000 units/side, 200 sentinels, 10000 draws in total sharded over the ranks; wall time per call "
                                "incl. make_null, cliff face and the observed statistic",

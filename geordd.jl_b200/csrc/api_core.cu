@@ -364,6 +364,8 @@ static void gp_finish(geordd_gp* gp, const double* y) {
     gp_update_alpha(gp);
 }
 
+static void gp_finish_batch(geordd_ctx* c, int nfit, geordd_gp** gps, const double* const* ys);
+
 geordd_gp* gp_create(geordd_ctx* c, const geordd_kernel* k, const double* X, int dim, int n, const double* y,
                      double log_noise, int* info_out, const geordd_gp* lead) {
     if (!y) throw ApiError(GEORDD_ERR_ARG, "gp_fit: bad X / y / n / dim (1..8)");
@@ -378,13 +380,25 @@ geordd_gp* gp_create(geordd_ctx* c, const geordd_kernel* k, const double* X, int
             Lpre = lead->dL;
             ptiles = lead->n / TILE;   // tiles entirely inside the leading block
         }
-        int info = make_posdef(c, gp->dK, gp->dL, gp->npad, n, gp->npad, &gp->jitter_rounds, Lpre, lead ? lead->npad : 0, ptiles);
+        // Fast path (no jitter needed, the rule): factorisation and tails queued back to back, one host synchronisation (see
+        // gp_create_batch).  Same kernels and arithmetic as make_posdef + gp_finish, which remain the path after a
+        // non-positive pivot.
+        {
+            ProfScope ps(c, PC_POTRF);
+            launch_potrf(c->stream, c->sched, gp->dK, gp->dL, gp->npad, gp->npad, Lpre, lead ? lead->npad : 0, ptiles);
+        }
+        gp_finish_batch(c, 1, &gp, &y);
+        int info = 0;
+        if (c->h_info[0] > 0) {
+            GD_CUDA(cudaMemsetAsync(c->sched.abort_word, 0, sizeof(int), c->stream));
+            info = make_posdef(c, gp->dK, gp->dL, gp->npad, n, gp->npad, &gp->jitter_rounds, Lpre, lead ? lead->npad : 0, ptiles);
+            if (info == 0) gp_finish(gp, y);
+        }
         if (info_out) *info_out = info;
         if (info != 0) {
             gp_free(gp);
             return nullptr;
         }
-        gp_finish(gp, y);
     } catch (...) {
         gp_free(gp);
         throw;
@@ -483,6 +497,11 @@ void gp_create_batch(geordd_ctx* c, int nfit, const geordd_kernel* ks, const dou
                 rc = launch_potrf_batch(c->stream, c->sched, items, nm);
             }
             if (rc != 0) { fallback = true; break; }
+            // One launch for the whole batch (the usual case): the tails are queued behind it at once and the factorisation's
+            // status comes back with their scalars -- ONE host synchronisation per call (each one costs the caller a wake-up,
+            // milliseconds on a busy host).  A non-positive pivot raises the abort word: the tails then bail out at their first
+            // wait, and the batch is redone matrix by matrix below.
+            if (nfit <= POTRF_MAX_BATCH) break;
             GD_CUDA(cudaMemcpyAsync(c->h_info, c->sched.abort_word, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
             GD_CUDA(cudaStreamSynchronize(c->stream));
             GD_CUDA(cudaGetLastError());
@@ -491,6 +510,13 @@ void gp_create_batch(geordd_ctx* c, int nfit, const geordd_kernel* ks, const dou
             if (info < 0) throw ApiError(GEORDD_ERR_WATCHDOG, "potrf watchdog fired");
             if (info > 0) fallback = true;
         }
+        if (!fallback && nfit <= POTRF_MAX_BATCH) {
+            gp_finish_batch(c, nfit, gps, ys);   // its check_abort leaves the abort word in h_info (and throws on a watchdog)
+            if (c->h_info[0] > 0) {
+                GD_CUDA(cudaMemsetAsync(c->sched.abort_word, 0, sizeof(int), c->stream));
+                fallback = true;
+            }
+        }
         if (fallback) {
             for (int f = 0; f < nfit; ++f) {
                 geordd_gp* gp = gps[f];
@@ -498,7 +524,7 @@ void gp_create_batch(geordd_ctx* c, int nfit, const geordd_kernel* ks, const dou
                 if (infos[f] != 0) { gp_free(gp); gps[f] = nullptr; continue; }
                 gp_finish(gp, ys[f]);
             }
-        } else {
+        } else if (nfit > POTRF_MAX_BATCH) {
             gp_finish_batch(c, nfit, gps, ys);
         }
     } catch (...) {

@@ -214,6 +214,9 @@ static long pick_batch(geordd_null* h, long nsim) {
     if (want <= h->cap_cols) return want;   // buffers of an earlier call suffice: no driver query on the hot path
     const long npN = h->N->npad, mT = h->T->npad, mC = h->C->npad, nbp = h->nbp;
     const long per_col = 8 * ((3 * npN + mT + mC) * 5 / 4 + 2 * nbp + (npN + mT + mC + 2 * nbp) / TILE + 8);   // ZB storage: 20/16
+    // small requests (C3-sized calls, placebo halves) skip the driver query: cudaMemGetInfo costs up to milliseconds on a busy
+    // host, and a request of under 1 GiB either fits or fails in dalloc with GEORDD_ERR_NOMEM
+    if ((size_t)want * (size_t)per_col <= ((size_t)1 << 30)) return want;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     long budget = (long)std::min<size_t>((size_t)24 << 30, free_b / 2);
